@@ -1,0 +1,634 @@
+// msda.cu — multi-scale deformable attention for B200 (sm_100a).
+//
+// Replaces the reference launchers ms_deformable_im2col_cuda<float|__half>, …_h2 and …_int8<float|__half2>
+// (TensorRT/plugin/multi_scale_deformable_attn/multiScaleDeformableAttnKernel.cu:1106-1218) and their kernels
+// (:611-1104). Semantics follow the FP32 kernel (:611-688 with the tap rule :133-178); see include/b200_bev_ops.h.
+//
+// Work decomposition (the reference uses one thread per output scalar, re-reading all logits/offsets per channel):
+//   item            = one (batch, query, head): NP = L*P sampling points, C channels.
+//   lane group      = LPI = C*sizeof(T)/16 lanes own one item; every lane holds 16 bytes of channels, so each
+//                     bilinear tap of an item is ONE 128-bit load per lane and a warp covers 32/LPI items.
+//   point ownership = offsets/logits are read exactly once with vector loads: chunk c (4 consecutive points) of an
+//                     item belongs to lane c % LPI of its group. The owner evaluates the index arithmetic once
+//                     (fp32, bit-exact with the reference), folds softmax numerator x bilinear weight x tap validity
+//                     into four tap weights, and broadcasts {packed address code, 4 weights} to its group with warp
+//                     shuffles. Softmax max / sum are shuffle reductions inside the lane group.
+//   gather          = all lanes of the group then issue the four 128-bit taps of that point for their channel slice
+//                     and accumulate in fp32 registers; points that are out of range in every item of the warp are
+//                     skipped with one ballot (the common case for cameras that do not see the BEV query).
+// Memory: value taps go through the read-only path and are meant to hit L1/L2 (the 95 MB value stack of the base
+// config fits the 126 MB L2); offsets/logits/out are streamed with L1::no_allocate so they do not evict taps.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kMaxLevels = 16;
+constexpr int kThreads = 256;
+
+static int g_f16_mode = 1;
+
+struct MsdaParams {
+  const void *value;
+  const int32_t *shapes;
+  const void *ref;
+  const void *off;
+  const void *logits;
+  void *out;
+  int B, S, M, C, L, Q, P, G;
+  long long items;
+  int ref_is_half;  // int8 path: dtype of reference_points
+  float scale_value, scale_offset, scale_weight, scale_out;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Index arithmetic — the part that must be bit-exact with the reference (…Kernel.cu:657-674 and :138-172).
+// ---------------------------------------------------------------------------------------------------------------
+struct PointRec {
+  bool in_range;
+  int h_low, w_low;
+  float lh, lw;  // fractional parts
+};
+
+__device__ __forceinline__ PointRec point_record(float ref_x, float ref_y, float off_x, float off_y, int H, int W) {
+  // loc = ref * size + off is ONE fused multiply-add in the reference binary (nvcc -fmad default, checked in its
+  // SASS: FFMA then FADD -0.5); __fmaf_rn pins that here regardless of compiler flags.
+  const float w_im = __fadd_rn(__fmaf_rn(ref_x, static_cast<float>(W), off_x), -0.5f);
+  const float h_im = __fadd_rn(__fmaf_rn(ref_y, static_cast<float>(H), off_y), -0.5f);
+  PointRec r;
+  r.in_range = (h_im > -1.f) && (w_im > -1.f) && (h_im < static_cast<float>(H)) && (w_im < static_cast<float>(W));
+  const float hf = floorf(h_im), wf = floorf(w_im);
+  r.h_low = r.in_range ? static_cast<int>(hf) : 0;
+  r.w_low = r.in_range ? static_cast<int>(wf) : 0;
+  r.lh = __fsub_rn(h_im, hf);
+  r.lw = __fsub_rn(w_im, wf);
+  return r;
+}
+
+__device__ __forceinline__ int tap_mask_of(const PointRec &r, int H, int W) {
+  int m = 0;
+  if (r.h_low >= 0 && r.w_low >= 0) m |= 1;
+  if (r.h_low >= 0 && r.w_low + 1 <= W - 1) m |= 2;
+  if (r.h_low + 1 <= H - 1 && r.w_low >= 0) m |= 4;
+  if (r.h_low + 1 <= H - 1 && r.w_low + 1 <= W - 1) m |= 8;
+  return m;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-dtype I/O
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Io;
+
+template <>
+struct Io<float> {
+  static constexpr int kVec = 4;
+  __device__ static void load_off4(const float *p, float s, float (&ox)[4], float (&oy)[4]) {
+    const uint4 a = ldg128_stream(p), b = ldg128_stream(p + 4);
+    ox[0] = __uint_as_float(a.x), oy[0] = __uint_as_float(a.y), ox[1] = __uint_as_float(a.z),
+    oy[1] = __uint_as_float(a.w);
+    ox[2] = __uint_as_float(b.x), oy[2] = __uint_as_float(b.y), ox[3] = __uint_as_float(b.z),
+    oy[3] = __uint_as_float(b.w);
+  }
+  __device__ static void load_lg4(const float *p, float s, float (&lg)[4]) {
+    const uint4 a = ldg128_stream(p);
+    lg[0] = __uint_as_float(a.x), lg[1] = __uint_as_float(a.y), lg[2] = __uint_as_float(a.z),
+    lg[3] = __uint_as_float(a.w);
+  }
+  template <int MODE>
+  __device__ static void fma_tap(float (&acc)[4], const uint4 &t, float w) {
+    acc[0] = fmaf(w, __uint_as_float(t.x), acc[0]);
+    acc[1] = fmaf(w, __uint_as_float(t.y), acc[1]);
+    acc[2] = fmaf(w, __uint_as_float(t.z), acc[2]);
+    acc[3] = fmaf(w, __uint_as_float(t.w), acc[3]);
+  }
+  __device__ static void store(float *p, const float (&acc)[4], float sum, const MsdaParams &) {
+    uint4 o;
+    o.x = __float_as_uint(acc[0] / sum), o.y = __float_as_uint(acc[1] / sum);
+    o.z = __float_as_uint(acc[2] / sum), o.w = __float_as_uint(acc[3] / sum);
+    stg128_stream(p, o);
+  }
+};
+
+template <>
+struct Io<__half> {
+  static constexpr int kVec = 8;
+  __device__ static void load_off4(const __half *p, float s, float (&ox)[4], float (&oy)[4]) {
+    const uint4 a = ldg128_stream(p);
+    const float2 p0 = h2_to_f2(a.x), p1 = h2_to_f2(a.y), p2 = h2_to_f2(a.z), p3 = h2_to_f2(a.w);
+    ox[0] = p0.x, oy[0] = p0.y, ox[1] = p1.x, oy[1] = p1.y, ox[2] = p2.x, oy[2] = p2.y, ox[3] = p3.x, oy[3] = p3.y;
+  }
+  __device__ static void load_lg4(const __half *p, float s, float (&lg)[4]) {
+    const uint2 a = ldg64_stream(p);
+    const float2 p0 = h2_to_f2(a.x), p1 = h2_to_f2(a.y);
+    lg[0] = p0.x, lg[1] = p0.y, lg[2] = p1.x, lg[3] = p1.y;
+  }
+  // MODE 0: exact (tap -> fp32, FFMA with the fp32 weight). MODE 1: the weight arrives as fp16 bits in the low half
+  // of `wbits` and the product is formed by FHFMA (fp16 x fp16 + fp32, single rounding into the fp32 accumulator).
+  template <int MODE>
+  __device__ static void fma_tap(float (&acc)[8], const uint4 &t, float w) {
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 v = h2_to_f2(u[i]);
+        acc[2 * i] = fmaf(w, v.x, acc[2 * i]);
+        acc[2 * i + 1] = fmaf(w, v.y, acc[2 * i + 1]);
+      }
+    } else {
+      const unsigned short wh = static_cast<unsigned short>(__float_as_uint(w) & 0xffffu);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] = fma_f32_f16(static_cast<unsigned short>(u[i] & 0xffffu), wh, acc[2 * i]);
+        acc[2 * i + 1] = fma_f32_f16(static_cast<unsigned short>(u[i] >> 16), wh, acc[2 * i + 1]);
+      }
+    }
+  }
+  __device__ static void store(__half *p, const float (&acc)[8], float sum, const MsdaParams &) {
+    uint4 o;
+    o.x = f2_to_h2(acc[0] / sum, acc[1] / sum), o.y = f2_to_h2(acc[2] / sum, acc[3] / sum);
+    o.z = f2_to_h2(acc[4] / sum, acc[5] / sum), o.w = f2_to_h2(acc[6] / sum, acc[7] / sum);
+    stg128_stream(p, o);
+  }
+};
+
+template <>
+struct Io<int8_t> {
+  static constexpr int kVec = 16;
+  __device__ static float deq(uint32_t word, int byte, float s) {
+    return static_cast<float>(static_cast<int8_t>(word >> (8 * byte))) * s;
+  }
+  // off*scale is rounded to fp32 first, then fused with ref*size — as in the reference INT8 kernel (…Kernel.cu:916-921)
+  __device__ static void load_off4(const int8_t *p, float s, float (&ox)[4], float (&oy)[4]) {
+    const uint2 a = ldg64_stream(p);
+    ox[0] = deq(a.x, 0, s), oy[0] = deq(a.x, 1, s), ox[1] = deq(a.x, 2, s), oy[1] = deq(a.x, 3, s);
+    ox[2] = deq(a.y, 0, s), oy[2] = deq(a.y, 1, s), ox[3] = deq(a.y, 2, s), oy[3] = deq(a.y, 3, s);
+  }
+  __device__ static void load_lg4(const int8_t *p, float s, float (&lg)[4]) {
+    const uint32_t a = ldg32_stream(p);
+    lg[0] = deq(a, 0, s), lg[1] = deq(a, 1, s), lg[2] = deq(a, 2, s), lg[3] = deq(a, 3, s);
+  }
+  template <int MODE>
+  __device__ static void fma_tap(float (&acc)[16], const uint4 &t, float w) {
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = static_cast<float>(static_cast<int8_t>(u[i] >> (8 * j)));
+        acc[4 * i + j] = fmaf(w, v, acc[4 * i + j]);
+      }
+    }
+  }
+  __device__ static void store(int8_t *p, const float (&acc)[16], float sum, const MsdaParams &prm) {
+    // real = acc * scale_value / sum ; q = T2int8(real / scale_out)
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float real = acc[4 * i + j] * prm.scale_value / sum;
+        word |= (static_cast<uint32_t>(to_int8_sat(real / prm.scale_out)) & 0xffu) << (8 * j);
+      }
+      o[i] = word;
+    }
+    stg128_stream(p, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+};
+
+template <typename R>
+__device__ __forceinline__ float ref_to_float(const R *p, long long i);
+template <>
+__device__ __forceinline__ float ref_to_float<float>(const float *p, long long i) {
+  return __ldg(p + i);
+}
+template <>
+__device__ __forceinline__ float ref_to_float<__half>(const __half *p, long long i) {
+  return __half2float(__ldg(p + i));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Main kernel. T = storage type of value/offsets/logits/out, R = storage type of reference points.
+// Requirements checked on the host: LPI = C*sizeof(T)/16 in {1,2,4,8,16,32}, P % 4 == 0, G in {1,2,4},
+// ceil(NP/4 / LPI) <= ROUNDS, NP/4 <= kMaxChunks, (S + 1) * M * C * sizeof(T) < 2^31, 16-byte aligned tensors.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxChunks = 64;
+
+template <typename T, typename R, int C, int ROUNDS, int MODE>
+__global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams prm) {
+  constexpr int VEC = Io<T>::kVec;
+  constexpr int LPI = C / VEC;
+  constexpr int IPW = 32 / LPI;
+  constexpr int IPB = IPW * (kThreads / 32);
+  constexpr int NW = MODE == 1 ? 2 : 4;  // weight registers broadcast per point (fp16 pairs in mixed mode)
+  // lanes whose sub-index is 0 (one per item of the warp); shifted by j it selects the owner lanes j
+  constexpr unsigned OWNER0 = LPI == 1 ? 0xffffffffu
+                              : LPI == 2 ? 0x55555555u
+                              : LPI == 4 ? 0x11111111u
+                              : LPI == 8 ? 0x01010101u
+                              : LPI == 16 ? 0x00010001u
+                                          : 0x00000001u;
+
+  extern __shared__ float s_ref[];  // [(b,q) of this block][2G]
+  // per chunk of 4 points: the level it samples (all four share it because P % 4 == 0)
+  __shared__ int s_H[kMaxChunks], s_W[kMaxChunks], s_start[kMaxChunks];
+
+  const int M = prm.M, Q = prm.Q, P = prm.P, G = prm.G, L = prm.L;
+  const int NP = L * P, NCH = NP >> 2, CPL = P >> 2;  // chunks (4 points) in total / per level
+  const long long item0 = static_cast<long long>(blockIdx.x) * IPB;
+  const long long item_last = min(prm.items, item0 + IPB) - 1;
+  const long long bq0 = item0 / M;
+
+  if (threadIdx.x < NCH) {
+    const int l = threadIdx.x / CPL;
+    int st = 0;
+    for (int i = 0; i < l; ++i) st += prm.shapes[2 * i] * prm.shapes[2 * i + 1];
+    s_H[threadIdx.x] = prm.shapes[2 * l];
+    s_W[threadIdx.x] = prm.shapes[2 * l + 1];
+    s_start[threadIdx.x] = st;
+  }
+  {
+    const int n = static_cast<int>(item_last / M - bq0 + 1) * 2 * G;
+    const R *rp = static_cast<const R *>(prm.ref);
+    for (int i = threadIdx.x; i < n; i += kThreads) s_ref[i] = ref_to_float<R>(rp, bq0 * 2 * G + i);
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPI;
+  const long long it_raw = item0 + warp * IPW + lane / LPI;
+  const bool active = it_raw < prm.items;
+  const long long it = active ? it_raw : prm.items - 1;  // inactive lanes shadow the last item, never store
+  const long long bq = it / M;
+  const int m = static_cast<int>(it - bq * M);
+  const int b = static_cast<int>(bq / Q);
+  const float *rp = s_ref + (bq - bq0) * 2 * G;
+  const T *off_item = static_cast<const T *>(prm.off) + it * NP * 2;
+  const T *lg_item = static_cast<const T *>(prm.logits) + it * NP;
+
+  // ---- softmax statistics over the item's NP logits (…Kernel.cu:642-648, :667-669)
+  float lg[ROUNDS][4];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int c = r * LPI + sub;
+    if (c < NCH) {
+      Io<T>::load_lg4(lg_item + c * 4, prm.scale_weight, lg[r]);
+    } else {
+      lg[r][0] = lg[r][1] = lg[r][2] = lg[r][3] = -INFINITY;
+    }
+    mx = fmaxf(mx, fmaxf(fmaxf(lg[r][0], lg[r][1]), fmaxf(lg[r][2], lg[r][3])));
+  }
+#pragma unroll
+  for (int d = 1; d < LPI; d <<= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, d));
+  float sum = 0.f;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      lg[r][k] = expf(lg[r][k] - mx);  // exp(-inf) = 0 for the padding slots
+      sum += lg[r][k];
+    }
+  }
+#pragma unroll
+  for (int d = 1; d < LPI; d <<= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
+
+  // ---- gather
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  const unsigned step_b = static_cast<unsigned>(M * C) * sizeof(T);  // bytes between horizontally adjacent pixels
+  const char *vbase = reinterpret_cast<const char *>(static_cast<const T *>(prm.value) +
+                                                     (static_cast<long long>(b) * prm.S * M + m) * C + sub * VEC);
+
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    if (r * LPI >= NCH) break;  // uniform
+    // ---- owner: index arithmetic for my chunk. Broadcast payload per point: byte offset of the top-left tap with
+    // the "column step usable" flag in bit 0, byte offset of the bottom-left tap, and the tap weights.
+    unsigned otop[4], obot[4];
+    float tw[4][NW];
+    bool any_ok = false;
+    {
+      const int c = r * LPI + sub;
+      const bool have = c < NCH;
+      const int cc = have ? c : 0;
+      const int H = s_H[cc], W = s_W[cc], start = s_start[cc];
+      float ox[4], oy[4];
+      Io<T>::load_off4(off_item + cc * 8, prm.scale_offset, ox, oy);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int g = k & (G - 1);  // == (point index within level) % G because P % 4 == 0 and G divides 4
+        const PointRec pr = point_record(rp[2 * g], rp[2 * g + 1], ox[k], oy[k], H, W);
+        const bool ok = have && pr.in_range;
+        any_ok |= ok;
+        const int h0 = max(pr.h_low, 0), w0 = max(pr.w_low, 0);
+        const bool t = pr.h_low >= 0, bt = pr.h_low + 1 <= H - 1, lf = pr.w_low >= 0, rt = pr.w_low + 1 <= W - 1;
+        const unsigned top = ok ? static_cast<unsigned>(start + h0 * W + w0) * step_b : 0u;
+        otop[k] = top | ((ok && lf && rt) ? 1u : 0u);
+        obot[k] = top + ((ok && t && bt) ? static_cast<unsigned>(W) * step_b : 0u);
+        const float hh = 1.f - pr.lh, hw = 1.f - pr.lw;
+        const float e = lg[r][k];
+        const float w00 = (ok && t && lf) ? hh * hw * e : 0.f;
+        const float w01 = (ok && t && rt) ? hh * pr.lw * e : 0.f;
+        const float w10 = (ok && bt && lf) ? pr.lh * hw * e : 0.f;
+        const float w11 = (ok && bt && rt) ? pr.lh * pr.lw * e : 0.f;
+        if (MODE == 1) {  // fp16 weights for FHFMA, two per register
+          tw[k][0] = __uint_as_float(f2_to_h2(w00, w01));
+          tw[k][1] = __uint_as_float(f2_to_h2(w10, w11));
+        } else {
+          tw[k][0] = w00, tw[k][1] = w01, tw[k][NW - 2] = w10, tw[k][NW - 1] = w11;
+        }
+      }
+    }
+    const unsigned vm = __ballot_sync(kFullMask, any_ok);
+
+#pragma unroll
+    for (int j = 0; j < LPI; ++j) {
+      if (r * LPI + j >= NCH) break;                // uniform
+      if ((vm & (OWNER0 << j)) == 0u) continue;     // uniform: chunk out of range for every item of the warp
+      const int src = (lane & ~(LPI - 1)) | j;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned ot = __shfl_sync(kFullMask, otop[k], src);
+        const unsigned ob = __shfl_sync(kFullMask, obot[k], src);
+        float w[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = __shfl_sync(kFullMask, tw[k][i], src);
+        // Taps of a point whose neighbour is outside the image alias an in-image tap and carry weight 0; points that
+        // are out of range altogether read the (valid) first bytes of this item's slice with all-zero weights.
+        const unsigned dx = (ot & 1u) ? step_b : 0u;
+        const char *p0 = vbase + (ot & ~1u);
+        const char *p1 = vbase + ob;
+        const uint4 t00 = ldg128(p0), t01 = ldg128(p0 + dx), t10 = ldg128(p1), t11 = ldg128(p1 + dx);
+        if (MODE == 1) {
+          const uint32_t a = __float_as_uint(w[0]), bb = __float_as_uint(w[1]);
+          Io<T>::template fma_tap<MODE>(acc, t00, __uint_as_float(a & 0xffffu));
+          Io<T>::template fma_tap<MODE>(acc, t01, __uint_as_float(a >> 16));
+          Io<T>::template fma_tap<MODE>(acc, t10, __uint_as_float(bb & 0xffffu));
+          Io<T>::template fma_tap<MODE>(acc, t11, __uint_as_float(bb >> 16));
+        } else {
+          Io<T>::template fma_tap<MODE>(acc, t00, w[0]);
+          Io<T>::template fma_tap<MODE>(acc, t01, w[1]);
+          Io<T>::template fma_tap<MODE>(acc, t10, w[NW - 2]);
+          Io<T>::template fma_tap<MODE>(acc, t11, w[NW - 1]);
+        }
+      }
+    }
+  }
+
+  if (active) Io<T>::store(static_cast<T *>(prm.out) + it * C + sub * VEC, acc, sum, prm);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generic fallback: any C / P / G (one thread per output scalar, fp32 math). Correctness path for odd shapes.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T *p, long long i, float s);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float *p, long long i, float) {
+  return __ldg(p + i);
+}
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half *p, long long i, float) {
+  return __half2float(__ldg(p + i));
+}
+template <>
+__device__ __forceinline__ float load_as_float<int8_t>(const int8_t *p, long long i, float s) {
+  return static_cast<float>(__ldg(p + i)) * s;
+}
+template <typename T>
+__device__ __forceinline__ void store_from_float(T *p, long long i, float v, const MsdaParams &prm);
+template <>
+__device__ __forceinline__ void store_from_float<float>(float *p, long long i, float v, const MsdaParams &) {
+  p[i] = v;
+}
+template <>
+__device__ __forceinline__ void store_from_float<__half>(__half *p, long long i, float v, const MsdaParams &) {
+  p[i] = __float2half_rn(v);
+}
+template <>
+__device__ __forceinline__ void store_from_float<int8_t>(int8_t *p, long long i, float v, const MsdaParams &prm) {
+  p[i] = static_cast<int8_t>(to_int8_sat(v * prm.scale_value / prm.scale_out));
+}
+
+template <typename T, typename R>
+__global__ void __launch_bounds__(kThreads) msda_generic_kernel(const MsdaParams prm) {
+  const int M = prm.M, C = prm.C, Q = prm.Q, P = prm.P, G = prm.G, L = prm.L, NP = L * P;
+  const long long n = prm.items * C;
+  const T *value = static_cast<const T *>(prm.value);
+  const T *off = static_cast<const T *>(prm.off);
+  const T *logits = static_cast<const T *>(prm.logits);
+  const R *ref = static_cast<const R *>(prm.ref);
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    const long long it = idx / C;
+    const long long bq = it / M;
+    const int m = static_cast<int>(it - bq * M);
+    const int b = static_cast<int>(bq / Q);
+    float mx = -INFINITY;
+    for (int i = 0; i < NP; ++i) mx = fmaxf(mx, load_as_float<T>(logits, it * NP + i, prm.scale_weight));
+    float acc = 0.f, sum = 0.f;
+    long long start = 0;
+    int k = 0;
+    for (int l = 0; l < L; ++l) {
+      const int H = prm.shapes[2 * l], W = prm.shapes[2 * l + 1];
+      const T *vl = value + ((static_cast<long long>(b) * prm.S + start) * M + m) * C + c;
+      for (int p = 0; p < P; ++p, ++k) {
+        const int g = p % G;
+        const float rx = ref_to_float<R>(ref, bq * 2 * G + 2 * g), ry = ref_to_float<R>(ref, bq * 2 * G + 2 * g + 1);
+        const float ox = load_as_float<T>(off, (it * NP + k) * 2, prm.scale_offset);
+        const float oy = load_as_float<T>(off, (it * NP + k) * 2 + 1, prm.scale_offset);
+        const float e = expf(load_as_float<T>(logits, it * NP + k, prm.scale_weight) - mx);
+        sum += e;
+        const PointRec pr = point_record(rx, ry, ox, oy, H, W);
+        if (!pr.in_range) continue;
+        const int tm = tap_mask_of(pr, H, W);
+        const long long stp = static_cast<long long>(M) * C;
+        const T *t0 = vl + (static_cast<long long>(pr.h_low) * W + pr.w_low) * stp;
+        const float v1 = (tm & 1) ? load_as_float<T>(t0, 0, 1.f) : 0.f;
+        const float v2 = (tm & 2) ? load_as_float<T>(t0, stp, 1.f) : 0.f;
+        const float v3 = (tm & 4) ? load_as_float<T>(t0, W * stp, 1.f) : 0.f;
+        const float v4 = (tm & 8) ? load_as_float<T>(t0, W * stp + stp, 1.f) : 0.f;
+        const float hh = 1.f - pr.lh, hw = 1.f - pr.lw;
+        acc += (hh * hw * v1 + hh * pr.lw * v2 + pr.lh * hw * v3 + pr.lh * pr.lw * v4) * e;
+      }
+      start += static_cast<long long>(H) * W;
+    }
+    store_from_float<T>(static_cast<T *>(prm.out), idx, acc / sum, prm);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Diagnostic kernel: sampling-index records (same device function as the product kernels).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void msda_index_kernel(const int32_t *shapes, const T *ref, const T *off, int B, int M, int L, int Q, int P,
+                                  int G, int4 *rec) {
+  const int NP = L * P;
+  const long long n = static_cast<long long>(B) * Q * M * NP;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(idx % NP);
+    const long long it = idx / NP;
+    const long long bq = it / M;
+    const int l = k / P, g = (k % P) % G;
+    const int H = shapes[2 * l], W = shapes[2 * l + 1];
+    const PointRec pr = point_record(load_as_float<T>(ref, bq * 2 * G + 2 * g, 1.f),
+                                     load_as_float<T>(ref, bq * 2 * G + 2 * g + 1, 1.f),
+                                     load_as_float<T>(off, idx * 2, 1.f), load_as_float<T>(off, idx * 2 + 1, 1.f), H, W);
+    rec[idx] = pr.in_range ? make_int4(1, pr.h_low, pr.w_low, tap_mask_of(pr, H, W)) : make_int4(0, 0, 0, 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------------
+static int validate(const MsdaParams &p) {
+  if (!p.value || !p.shapes || !p.ref || !p.off || !p.logits || !p.out) return B200_ERR_BAD_PARAM;
+  if (p.B <= 0 || p.S <= 0 || p.M <= 0 || p.C <= 0 || p.L <= 0 || p.Q <= 0 || p.P <= 0 || p.G <= 0)
+    return B200_ERR_BAD_PARAM;
+  if (p.L > kMaxLevels) return B200_ERR_UNSUPPORTED;
+  if ((static_cast<long long>(p.S) + 1) * p.M * p.C * 4 >= (1ll << 31)) return B200_ERR_BAD_PARAM;
+  return B200_OK;
+}
+
+template <typename T, typename R, int C, int ROUNDS, int MODE>
+static int launch_gather(const MsdaParams &p, cudaStream_t s) {
+  constexpr int LPI = C / Io<T>::kVec;
+  constexpr int IPB = (32 / LPI) * (kThreads / 32);
+  const long long blocks = (p.items + IPB - 1) / IPB;
+  if (blocks > 0x7fffffffll) return B200_ERR_BAD_PARAM;
+  const size_t smem = static_cast<size_t>(IPB / (p.M < IPB ? p.M : IPB) + 2) * 2 * p.G * sizeof(float);
+  msda_gather_kernel<T, R, C, ROUNDS, MODE><<<static_cast<unsigned>(blocks), kThreads, smem, s>>>(p);
+  return check_launch();
+}
+
+template <typename T, typename R>
+static int launch_generic(const MsdaParams &p, cudaStream_t s) {
+  const long long n = p.items * p.C;
+  const long long blocks = (n + kThreads - 1) / kThreads;
+  msda_generic_kernel<T, R><<<static_cast<unsigned>(blocks < (1 << 20) ? blocks : (1 << 20)), kThreads, 0, s>>>(p);
+  return check_launch();
+}
+
+template <typename T, typename R, int C, int MODE>
+static int dispatch_rounds(const MsdaParams &p, cudaStream_t s) {
+  constexpr int LPI = C / Io<T>::kVec;
+  const int nch = p.L * p.P / 4;
+  const int rounds = (nch + LPI - 1) / LPI;
+  if (rounds <= 1) return launch_gather<T, R, C, 1, MODE>(p, s);
+  if (rounds <= 2) return launch_gather<T, R, C, 2, MODE>(p, s);
+  if (rounds <= 4) return launch_gather<T, R, C, 4, MODE>(p, s);
+  return launch_generic<T, R>(p, s);
+}
+
+template <typename T, typename R, int MODE>
+static int dispatch(const MsdaParams &p, cudaStream_t s) {
+  const int st = validate(p);
+  if (st != B200_OK) return st;
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.value) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p.off) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p.out) % 16 == 0);
+  const bool g_ok = p.G == 1 || p.G == 2 || p.G == 4;
+  if (aligned && p.P % 4 == 0 && g_ok && p.L * p.P / 4 <= kMaxChunks) {
+    // every BEVFormer variant has embed_dims / num_heads = 256 / 8 = 32 channels per head
+    if (p.C == 32) return dispatch_rounds<T, R, 32, MODE>(p, s);
+  }
+  return launch_generic<T, R>(p, s);
+}
+
+static MsdaParams make_params(const void *value, const int32_t *shapes, const void *ref, const void *off,
+                              const void *logits, int B, int S, int M, int C, int L, int Q, int P, int G, void *out) {
+  MsdaParams p{};
+  p.value = value, p.shapes = shapes, p.ref = ref, p.off = off, p.logits = logits, p.out = out;
+  p.B = B, p.S = S, p.M = M, p.C = C, p.L = L, p.Q = Q, p.P = P, p.G = G;
+  p.items = static_cast<long long>(B) * Q * M;
+  p.scale_value = p.scale_offset = p.scale_weight = p.scale_out = 1.f;
+  return p;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_msda_set_f16_mode(int mode) {
+  const int prev = g_f16_mode;
+  g_f16_mode = mode ? 1 : 0;
+  return prev;
+}
+
+int b200_msda_f32(const float *value, const int32_t *spatial_shapes, const float *reference_points,
+                  const float *sampling_offsets, const float *attn_weight, int batch, int spatial_size, int num_heads,
+                  int channels, int num_levels, int num_query, int num_point, int points_per_group, float *out,
+                  void *stream) {
+  const MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                                   spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                                   points_per_group, out);
+  return dispatch<float, float, 0>(p, static_cast<cudaStream_t>(stream));
+}
+
+int b200_msda_f16(const void *value, const int32_t *spatial_shapes, const void *reference_points,
+                  const void *sampling_offsets, const void *attn_weight, int batch, int spatial_size, int num_heads,
+                  int channels, int num_levels, int num_query, int num_point, int points_per_group, void *out,
+                  void *stream) {
+  const MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                                   spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                                   points_per_group, out);
+  return g_f16_mode ? dispatch<__half, __half, 1>(p, static_cast<cudaStream_t>(stream))
+                    : dispatch<__half, __half, 0>(p, static_cast<cudaStream_t>(stream));
+}
+
+int b200_msda_f16_h2(const void *value, const int32_t *spatial_shapes, const void *reference_points,
+                     const void *sampling_offsets, const void *attn_weight, int batch, int spatial_size,
+                     int num_heads, int channels, int num_levels, int num_query, int num_point, int points_per_group,
+                     void *out, void *stream) {
+  if (channels % 2 != 0) return B200_ERR_UNSUPPORTED;  // …Plugin.cpp:240-245
+  return b200_msda_f16(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch, spatial_size,
+                       num_heads, channels, num_levels, num_query, num_point, points_per_group, out, stream);
+}
+
+int b200_msda_i8(const int8_t *value, float scale_value, const int32_t *spatial_shapes, const void *reference_points,
+                 int ref_is_half, const int8_t *sampling_offsets, float scale_offset, const int8_t *attn_weight,
+                 float scale_weight, int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                 int num_query, int num_point, int points_per_group, int8_t *out, float scale_out, void *stream) {
+  if (channels % 4 != 0 || num_point % 4 != 0) return B200_ERR_UNSUPPORTED;  // …Plugin.cpp:151-156
+  if (!(scale_out > 0.f)) return B200_ERR_BAD_PARAM;
+  MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, points_per_group,
+                             out);
+  p.scale_value = scale_value, p.scale_offset = scale_offset, p.scale_weight = scale_weight, p.scale_out = scale_out;
+  p.ref_is_half = ref_is_half;
+  return ref_is_half ? dispatch<int8_t, __half, 0>(p, static_cast<cudaStream_t>(stream))
+                     : dispatch<int8_t, float, 0>(p, static_cast<cudaStream_t>(stream));
+}
+
+int b200_msda_debug_indices(int dtype, const int32_t *spatial_shapes, const void *reference_points,
+                            const void *sampling_offsets, int batch, int num_heads, int num_levels, int num_query,
+                            int num_point, int points_per_group, int32_t *records, void *stream) {
+  if (!spatial_shapes || !reference_points || !sampling_offsets || !records) return B200_ERR_BAD_PARAM;
+  const long long n = static_cast<long long>(batch) * num_query * num_heads * num_levels * num_point;
+  if (n <= 0) return B200_ERR_BAD_PARAM;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256 < (1 << 20) ? (n + 255) / 256 : (1 << 20));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == 0)
+    msda_index_kernel<float><<<blocks, 256, 0, s>>>(spatial_shapes, static_cast<const float *>(reference_points),
+                                                    static_cast<const float *>(sampling_offsets), batch, num_heads,
+                                                    num_levels, num_query, num_point, points_per_group,
+                                                    reinterpret_cast<int4 *>(records));
+  else if (dtype == 1)
+    msda_index_kernel<__half><<<blocks, 256, 0, s>>>(spatial_shapes, static_cast<const __half *>(reference_points),
+                                                     static_cast<const __half *>(sampling_offsets), batch, num_heads,
+                                                     num_levels, num_query, num_point, points_per_group,
+                                                     reinterpret_cast<int4 *>(records));
+  else
+    return B200_ERR_UNSUPPORTED;
+  return check_launch();
+}
+
+}  // extern "C"

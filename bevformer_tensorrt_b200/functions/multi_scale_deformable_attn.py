@@ -1,0 +1,160 @@
+"""Multi-scale deformable attention — host-side mirror of the reference binding
+det2trt/models/functions/multi_scale_deformable_attn.py (:10-217): same module-level names, same positional
+signature, same ONNX symbolic, so SpatialCrossAttentionTRTP / TemporalSelfAttentionTRTP / the decoder's
+CustomMSDeformableAttentionTRTP call it unchanged (spatial_cross_attention.py:692,764-766;
+temporal_self_attention.py:348,447-449; decoder.py:376,460-466).
+
+The reference's forward() expands to sampling locations + softmax and calls mmcv's CUDA op; here forward() hands the
+plugin-signature tensors straight to the fused sm_100a kernel behind the C ABI (include/b200_bev_ops.h). Inference
+only, like the reference (its Function defines no backward).
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+
+
+def _check_inputs(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights):
+    if not value.is_cuda:
+        raise RuntimeError("multi_scale_deformable_attn: value must be a CUDA tensor (no CPU fallback exists)")
+    if value.dim() != 4:
+        raise ValueError("value must be [bs, num_keys, num_heads, channels]")
+    bs, num_keys, num_heads, channels = value.shape
+    num_levels = value_spatial_shapes.shape[0]
+    num_query = sampling_offsets.shape[1]
+    if reference_points.shape[-1] % 2 != 0:
+        raise ValueError("reference_points last dim must hold (x, y) pairs")
+    points_per_group = reference_points.shape[-1] // 2
+    all_points = attention_weights.shape[-1]
+    if all_points % num_levels != 0:
+        raise ValueError("attention_weights last dim must be num_levels * num_points")
+    num_point = all_points // num_levels
+    if sampling_offsets.numel() != bs * num_query * num_heads * all_points * 2:
+        raise ValueError("sampling_offsets does not match [bs, num_query, num_heads, num_levels*num_points*2]")
+    if attention_weights.numel() != bs * num_query * num_heads * all_points:
+        raise ValueError("attention_weights does not match [bs, num_query, num_heads, num_levels*num_points]")
+    if reference_points.numel() != bs * num_query * points_per_group * 2:
+        raise ValueError("reference_points does not match [bs, num_query, 1, 2*points_per_group]")
+    return bs, num_keys, num_heads, channels, num_levels, num_query, num_point, points_per_group
+
+
+def _shapes_i32(value_spatial_shapes, device):
+    # PyTorch callers pass int64 (transformer.py:313); the plugin ABI is int32 (…Plugin.cpp:165-167)
+    return value_spatial_shapes.to(device=device, dtype=torch.int32).contiguous()
+
+
+def _msda_forward(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, use_h2):
+    dims = _check_inputs(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights)
+    bs, _, num_heads, channels, _, num_query, _, _ = dims
+    lib = _lib.load()
+    dt = value.dtype
+    if dt not in (torch.float32, torch.float16):
+        raise _lib.B200OpsError("multi_scale_deformable_attn", 1)
+    value = value.contiguous()
+    shapes = _shapes_i32(value_spatial_shapes, value.device)
+    ref = reference_points.to(dt).contiguous()
+    off = sampling_offsets.to(dt).contiguous()
+    w = attention_weights.to(dt).contiguous()
+    out = torch.empty(bs, num_query, num_heads, channels, dtype=dt, device=value.device)
+    if dt == torch.float32:
+        name = "b200_msda_f32"
+    else:
+        name = "b200_msda_f16_h2" if use_h2 and channels % 2 == 0 else "b200_msda_f16"
+    with torch.cuda.device(value.device):
+        st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
+                                *dims, out.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
+    _lib.check(name, st)
+    return out
+
+
+class _MultiScaleDeformableAttnFunction(Function):
+    @staticmethod
+    def symbolic(g, value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights):
+        return g.op("MultiScaleDeformableAttnTRT", value, value_spatial_shapes, reference_points, sampling_offsets,
+                    attention_weights)  # fmt: skip
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights):
+        """value [bs, num_keys, num_heads, channels]; value_spatial_shapes [num_levels, 2] (h, w);
+        reference_points [bs, num_queries, 1, 2*points_per_group]; sampling_offsets
+        [bs, num_queries, num_heads, num_levels*num_points*2] in pixels, (x, y) innermost; attention_weights
+        [bs, num_queries, num_heads, num_levels*num_points] pre-softmax. Returns [bs, num_queries, num_heads, channels].
+        """
+        return _msda_forward(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, False)
+
+
+class _MultiScaleDeformableAttnFunction2(_MultiScaleDeformableAttnFunction):
+    @staticmethod
+    def symbolic(g, value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights):
+        return g.op("MultiScaleDeformableAttnTRT2", value, value_spatial_shapes, reference_points, sampling_offsets,
+                    attention_weights)  # fmt: skip
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights):
+        return _msda_forward(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, True)
+
+
+_multi_scale_deformable_attn_gpu = _MultiScaleDeformableAttnFunction.apply
+_multi_scale_deformable_attn_gpu2 = _MultiScaleDeformableAttnFunction2.apply
+
+
+def multi_scale_deformable_attn(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights):
+    """Plugin MultiScaleDeformableAttnTRT (FP32 / FP16). Same contract as the reference wrapper (:150-182)."""
+    assert value.is_cuda
+    return _multi_scale_deformable_attn_gpu(value, value_spatial_shapes, reference_points, sampling_offsets,
+                                            attention_weights)  # fmt: skip
+
+
+def multi_scale_deformable_attn2(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights):
+    """Plugin MultiScaleDeformableAttnTRT2 (FP32 / FP16 as half2). Same contract as the reference wrapper (:185-217)."""
+    assert value.is_cuda
+    return _multi_scale_deformable_attn_gpu2(value, value_spatial_shapes, reference_points, sampling_offsets,
+                                             attention_weights)  # fmt: skip
+
+
+def multi_scale_deformable_attn_int8(value_q, scale_value, value_spatial_shapes, reference_points, offsets_q,
+                                     scale_offset, weights_q, scale_weight, scale_out):
+    """INT8 flavour of the plugin (…Plugin.cpp:118-134): int8 value / offsets / logits with per-tensor PTQ scales
+    (real = q * scale), reference points FP16 or FP32, int8 output at ``scale_out``. In PyTorch the reference has no
+    int8 entry (TensorRT supplies the scales through PluginTensorDesc); this mirrors the C launcher's argument list
+    (…Kernel.h:29-38)."""
+    assert value_q.is_cuda and value_q.dtype == torch.int8
+    dims = _check_inputs(value_q, value_spatial_shapes, reference_points, offsets_q, weights_q)
+    bs, _, num_heads, channels, _, num_query, _, _ = dims
+    if reference_points.dtype not in (torch.float16, torch.float32):
+        raise _lib.B200OpsError("multi_scale_deformable_attn_int8", 1)
+    lib = _lib.load()
+    value_q = value_q.contiguous()
+    shapes = _shapes_i32(value_spatial_shapes, value_q.device)
+    ref = reference_points.contiguous()
+    off = offsets_q.contiguous()
+    w = weights_q.contiguous()
+    out = torch.empty(bs, num_query, num_heads, channels, dtype=torch.int8, device=value_q.device)
+    with torch.cuda.device(value_q.device):
+        st = lib.b200_msda_i8(value_q.data_ptr(), float(scale_value), shapes.data_ptr(), ref.data_ptr(),
+                              int(ref.dtype == torch.float16), off.data_ptr(), float(scale_offset), w.data_ptr(),
+                              float(scale_weight), *dims, out.data_ptr(), float(scale_out),
+                              _lib.current_stream_ptr())  # fmt: skip
+    _lib.check("b200_msda_i8", st)
+    return out
+
+
+def msda_sampling_indices(value_spatial_shapes, reference_points, sampling_offsets, num_heads):
+    """Diagnostic: int32 [bs, nq, heads, L*P, 4] records {in_range, h_low, w_low, tap_mask} from the device code."""
+    assert reference_points.is_cuda and reference_points.dtype in (torch.float32, torch.float16)
+    bs, nq = sampling_offsets.shape[:2]
+    L = value_spatial_shapes.shape[0]
+    G = reference_points.shape[-1] // 2
+    NP = sampling_offsets.numel() // (bs * nq * num_heads * 2)
+    shapes = _shapes_i32(value_spatial_shapes, reference_points.device)
+    ref = reference_points.contiguous()
+    off = sampling_offsets.to(ref.dtype).contiguous()
+    rec = torch.empty(bs, nq, num_heads, NP, 4, dtype=torch.int32, device=ref.device)
+    with torch.cuda.device(ref.device):
+        st = _lib.load().b200_msda_debug_indices(int(ref.dtype == torch.float16), shapes.data_ptr(), ref.data_ptr(),
+                                                 off.data_ptr(), bs, num_heads, L, nq, NP // L, G, rec.data_ptr(),
+                                                 _lib.current_stream_ptr())  # fmt: skip
+    _lib.check("b200_msda_debug_indices", st)
+    return rec

@@ -1,0 +1,106 @@
+"""Per-camera sharding of spatial cross-attention's sampling step across GPUs.
+
+The SCA output is a sum over cameras of per-camera MSDA outputs weighted by ``bev_mask[cam, q]``
+(reference: det2trt/models/modules/spatial_cross_attention.py:254-270 — ``slots = (queries * bev_mask).sum(0)``), and
+each camera's MSDA touches only that camera's value stack, so the work splits into independent (camera, query-tile)
+units. Every rank runs the sm_100a MSDA kernel on its units, folds them into a local BEV accumulator ``[nq, heads*ch]``
+and ONE collective (all-reduce, NCCL over NVLink on GPUs / gloo in the CPU tests) produces the summed accumulator.
+6 cameras do not divide 4 or 8 ranks, hence query tiles: the unit count is lcm-friendly (12 units for 4 ranks,
+24 for 8) so every rank gets the same amount of work.
+"""
+import math
+from dataclasses import dataclass
+from typing import Callable, List, Sequence
+
+import torch
+
+
+@dataclass(frozen=True)
+class Unit:
+    cam: int
+    q0: int
+    q1: int
+
+
+def plan_units(num_cams: int, num_query: int, world_size: int, align: int = 8) -> List[List[Unit]]:
+    """Round-robin assignment of (camera, query-tile) units: returns per-rank unit lists, equal counts per rank.
+    Tiles per camera = world_size / gcd(num_cams, world_size); tile edges are multiples of ``align`` queries."""
+    if world_size < 1 or num_cams < 1 or num_query < 1:
+        raise ValueError("world_size, num_cams and num_query must be positive")
+    tiles = world_size // math.gcd(num_cams, world_size)
+    edges = [min(num_query, ((num_query * t // tiles + align - 1) // align) * align) for t in range(tiles)] + [num_query]
+    units = [Unit(c, edges[t], edges[t + 1]) for c in range(num_cams) for t in range(tiles) if edges[t + 1] > edges[t]]
+    per_rank: List[List[Unit]] = [[] for _ in range(world_size)]
+    # camera-major order keeps one camera's tiles on as few ranks as possible: rank r takes a contiguous run
+    n = len(units)
+    for r in range(world_size):
+        per_rank[r] = units[n * r // world_size : n * (r + 1) // world_size]
+    return per_rank
+
+
+def merge_units(units: Sequence[Unit]) -> List[Unit]:
+    """Coalesces adjacent query tiles of the same camera (fewer, larger kernel launches)."""
+    out: List[Unit] = []
+    for u in sorted(units, key=lambda x: (x.cam, x.q0)):
+        if out and out[-1].cam == u.cam and out[-1].q1 == u.q0:
+            out[-1] = Unit(u.cam, out[-1].q0, u.q1)
+        else:
+            out.append(u)
+    return out
+
+
+def group_cameras(units: Sequence[Unit]):
+    """Batches consecutive cameras that cover the same query range into one launch: (cam0, cam1, q0, q1) tuples."""
+    groups = []
+    for u in merge_units(units):
+        if groups and groups[-1][1] == u.cam and groups[-1][2:] == (u.q0, u.q1):
+            groups[-1] = (groups[-1][0], u.cam + 1, u.q0, u.q1)
+        else:
+            groups.append((u.cam, u.cam + 1, u.q0, u.q1))
+    return groups
+
+
+class ShardedSCASampler:
+    """Holds one rank's slice of the SCA sampling inputs and produces the all-reduced BEV accumulator.
+
+    ``msda`` is the operator to run per unit (the product passes ``multi_scale_deformable_attn``; the CPU tests pass a
+    checker so the host-side plumbing — planning, slicing, masking, the collective — is covered without a GPU).
+    """
+
+    def __init__(self, units: Sequence[Unit], num_query: int, msda: Callable, group=None,
+                 accum_dtype: torch.dtype = torch.float32):  # fmt: skip
+        self.units = merge_units(units)
+        self.num_query = num_query
+        self.msda = msda
+        self.group = group
+        self.accum_dtype = accum_dtype
+        self.local = []  # per launch group: (value[c,S,M,C], ref[c,q,1,2G], off[c,q,M,*], logits[c,q,M,*], mask[c,q,1])
+        self.groups = []
+        self.shapes = None
+        self.accum = None
+
+    def load(self, value, shapes, ref, off, logits, bev_mask, device):
+        """Copies this rank's units out of full-size host tensors (a real model produces them in place)."""
+        self.shapes = shapes.to(device)
+        self.local = []
+        self.groups = group_cameras(self.units)  # (cam0, cam1, q0, q1): consecutive cameras sharing a query range
+        for c0, c1, q0, q1 in self.groups:
+            sl = slice(q0, q1)
+            self.local.append(tuple(t.to(device).contiguous() for t in (
+                value[c0:c1], ref[c0:c1, sl], off[c0:c1, sl], logits[c0:c1, sl], bev_mask[c0:c1, sl])))  # fmt: skip
+        M, C = value.shape[2], value.shape[3]
+        self.accum = torch.zeros(self.num_query, M * C, dtype=self.accum_dtype, device=device)
+        return self
+
+    def step(self, reduce: bool = True):
+        """One SCA sampling step on this rank: kernels for the local units, masked camera-sum, one all-reduce."""
+        import torch.distributed as dist
+
+        self.accum.zero_()
+        for (c0, c1, q0, q1), (v, r, o, w, mask) in zip(self.groups, self.local):
+            out = self.msda(v, self.shapes, r, o, w)  # [cams, q, M, C]
+            weighted = out.reshape(c1 - c0, q1 - q0, -1).to(self.accum_dtype) * mask.to(self.accum_dtype)
+            self.accum[q0:q1] += weighted.sum(0)
+        if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.accum, op=dist.ReduceOp.SUM, group=self.group)
+        return self.accum

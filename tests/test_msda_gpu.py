@@ -1,0 +1,315 @@
+"""GPU parity tests for multi-scale deformable attention (run on the B200 box: pytest -m gpu).
+
+Bars (BASELINE.json north_star): sampling-index arithmetic bit-exact; values within 1e-3 max-abs (FP16) and 2e-2
+(INT8, after multiplying by scale_out); FP32 is held to 1e-5 (the reference's own FP32 op-test bar is mean-abs 1e-5,
+test_multi_scale_deformable_attn.py:139-140 — max-abs is stricter).
+Checkers: tests/golden (reference Python), oracle/msda_oracle.c (CPU restatement), oracle/_ref (the reference's CUDA
+kernels on the same GPU).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import bevformer_tensorrt_b200 as bt
+from bevformer_tensorrt_b200 import _lib
+from bevformer_tensorrt_b200.functions.multi_scale_deformable_attn import msda_sampling_indices
+from bevformer_tensorrt_b200.workloads import CONFIGS, MSDAConfig, make_msda_inputs, quantize_per_tensor
+from oracle import REF_LIB
+from oracle import msda as omsda
+from tests.helpers import golden_msda_cases, load_golden_msda
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+FP16_TOL = 1e-3  # north_star
+INT8_TOL = 2e-2  # north_star
+
+SMALL = [
+    ("small_sca", "U", 11),
+    ("small_sca", "edge", 12),
+    ("tiny_sca", "U", 13),
+    ("cpu_plumbing", "U", 14),
+]
+EXTRA = {
+    "tsa_like": MSDAConfig("tsa_like", 2, 1000, 8, 32, ((30, 30),), 4, 1),
+    "decoder_like": MSDAConfig("decoder_like", 1, 900, 8, 32, ((50, 50),), 4, 1),
+    "g2": MSDAConfig("g2", 2, 129, 8, 32, ((9, 11), (5, 6)), 8, 2),
+    "ragged_tail": MSDAConfig("ragged_tail", 1, 37, 5, 32, ((8, 8), (4, 4)), 4, 1),  # items not a multiple of a block
+    "one_pixel": MSDAConfig("one_pixel", 1, 64, 8, 32, ((1, 1), (1, 7), (7, 1)), 4, 4),
+    "generic_c20": MSDAConfig("generic_c20", 1, 61, 3, 20, ((7, 9), (4, 5)), 3, 1),  # falls to the generic kernel
+    "generic_g3": MSDAConfig("generic_g3", 1, 50, 4, 32, ((6, 6),), 12, 3),
+    "many_points": MSDAConfig("many_points", 1, 40, 8, 32, ((10, 12), (5, 6), (3, 3), (2, 2)), 16, 4),
+}
+
+
+def _cfg(name):
+    return CONFIGS.get(name) or EXTRA[name]
+
+
+def _cuda(ts):
+    return [t.cuda() for t in ts]
+
+
+def _oracle_f32(inputs):
+    return omsda.msda_f32(*(t.float().numpy() for t in inputs))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors produced by the reference's own Python code
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", golden_msda_cases())
+def test_fp32_matches_reference_golden(path):
+    cfg, inputs, want = load_golden_msda(path)
+    got = bt.multi_scale_deformable_attn(*_cuda(inputs)).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 2e-5  # golden goes through grid_sample's normalise/un-normalise round trip
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU oracle, seeded inputs
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,dist,seed", SMALL + [(n, "U", 20 + i) for i, n in enumerate(EXTRA)]
+                         + [(n, "edge", 40 + i) for i, n in enumerate(EXTRA)])  # fmt: skip
+def test_fp32_matches_oracle(name, dist, seed):
+    inputs = make_msda_inputs(_cfg(name), dist, seed, torch.float32)
+    want = _oracle_f32(inputs)
+    for fn in (bt.multi_scale_deformable_attn, bt.multi_scale_deformable_attn2):
+        got = fn(*_cuda(inputs)).cpu().numpy()
+        assert np.abs(got - want).max() < FP32_TOL, (name, dist, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name,dist,seed", SMALL + [("tsa_like", "U", 31), ("g2", "edge", 32),
+                                                    ("generic_c20", "U", 33), ("many_points", "U", 34)])  # fmt: skip
+def test_fp16_matches_oracle(name, dist, seed, mode):
+    inputs = make_msda_inputs(_cfg(name), dist, seed, torch.float16)
+    want = _oracle_f32(inputs)  # fp32 formulas on the fp16-rounded inputs
+    prev = _lib.load().b200_msda_set_f16_mode(mode)
+    try:
+        for fn in (bt.multi_scale_deformable_attn, bt.multi_scale_deformable_attn2):
+            out = fn(*_cuda(inputs))
+            assert out.dtype == torch.float16
+            err = np.abs(out.float().cpu().numpy() - want).max()
+            assert err < FP16_TOL, (name, dist, mode, err)
+    finally:
+        _lib.load().b200_msda_set_f16_mode(prev)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("name,dist,seed", [("small_sca", "edge", 51), ("small_sca", "U", 52), ("one_pixel", "edge", 53),
+                                            ("tsa_like", "edge", 54), ("tiny_sca", "G", 55)])  # fmt: skip
+def test_sampling_indices_bit_exact(name, dist, seed, dtype):
+    cfg = _cfg(name)
+    value, shapes, ref, off, logits = make_msda_inputs(cfg, dist, seed, dtype)
+    _, idx = omsda.msda_f32(value.float().numpy(), shapes.numpy(), ref.float().numpy(), off.float().numpy(),
+                            logits.float().numpy(), return_index=True)  # fmt: skip
+    rec = msda_sampling_indices(shapes, ref.cuda(), off.cuda(), cfg.num_heads).cpu().numpy()
+    want = np.stack([idx["in_range"], idx["h_low"], idx["w_low"], idx["tap_mask"]], -1)
+    assert rec.shape == want.shape
+    assert (rec == want).all(), f"{(rec != want).any(-1).sum()} of {want[..., 0].size} records differ"
+    assert want[..., 0].any() and not want[..., 0].all() or dist == "U"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# INT8
+# ---------------------------------------------------------------------------------------------------------------
+def _quantised(cfg, dist, seed, ref_dtype):
+    value, shapes, ref, off, logits = make_msda_inputs(cfg, dist, seed, torch.float32)
+    vq, sv = quantize_per_tensor(value)
+    oq, so = quantize_per_tensor(off)
+    wq, sw = quantize_per_tensor(logits)
+    ref = ref.to(ref_dtype)
+    real = omsda.msda_f32(vq.float().numpy() * sv, shapes.numpy(), ref.float().numpy(), oq.float().numpy() * so,
+                          wq.float().numpy() * sw)  # fmt: skip
+    sout = float(np.abs(real).max()) / 127.0
+    return (vq, sv, shapes, ref, oq, so, wq, sw, sout), real
+
+
+@pytest.mark.parametrize("ref_dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("name,dist,seed", [("small_sca", "U", 61), ("small_sca", "edge", 62), ("tiny_sca", "U", 63),
+                                            ("tsa_like", "U", 64), ("many_points", "U", 65)])  # fmt: skip
+def test_int8_matches_dequant_oracle(name, dist, seed, ref_dtype):
+    (vq, sv, shapes, ref, oq, so, wq, sw, sout), real = _quantised(_cfg(name), dist, seed, ref_dtype)
+    got = bt.multi_scale_deformable_attn_int8(vq.cuda(), sv, shapes, ref.cuda(), oq.cuda(), so, wq.cuda(), sw, sout)
+    assert got.dtype == torch.int8
+    got = got.cpu().numpy()
+    # (1) north_star bar: dequantised output vs the fp32 formulas on dequantised inputs
+    assert np.abs(got.astype(np.float32) * sout - real).max() < INT8_TOL
+    # (2) against the oracle's own requantisation: identical up to 1 LSB on rounding ties
+    want_q = omsda.msda_i8_dequant(vq.numpy(), sv, shapes.numpy(), ref.float().numpy(), oq.numpy(), so, wq.numpy(), sw,
+                                   sout)  # fmt: skip
+    diff = np.abs(got.astype(np.int32) - want_q.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3, (diff.max(), (diff != 0).mean())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own CUDA kernels on this GPU
+# ---------------------------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref not built (needs /root/reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("name,dist,seed", [("small_sca", "edge", 71), ("tiny_sca", "U", 72), ("tsa_like", "U", 73)])
+def test_fp32_matches_reference_kernel(name, dist, seed):
+    inputs = _cuda(make_msda_inputs(_cfg(name), dist, seed, torch.float32))
+    want = omsda.RefKernels().msda(*inputs, variant="f32")
+    got = bt.multi_scale_deformable_attn(*inputs)
+    torch.cuda.synchronize()
+    assert (got - want).abs().max().item() < FP32_TOL
+
+
+@needs_ref
+def test_base_shapes_fp32_against_reference_kernel_full_size():
+    """BASELINE configs[2] at full size, every output element, GPU vs GPU."""
+    inputs = _cuda(make_msda_inputs(CONFIGS["base_sca"], "U", 0, torch.float32))
+    want = omsda.RefKernels().msda(*inputs, variant="f32")
+    got = bt.multi_scale_deformable_attn(*inputs)
+    torch.cuda.synchronize()
+    assert got.shape == (6, 40000, 8, 32)
+    assert (got - want).abs().max().item() < FP32_TOL
+
+
+@needs_ref
+@pytest.mark.parametrize("dist", ["U", "G"])
+def test_base_shapes_fp16_within_tolerance_of_fp32_reference_kernel(dist):
+    """FP16 I/O at full size vs the reference FP32 kernel run on the same (fp16-rounded) inputs; also reports how far
+    the reference's own __half / __half2 kernels are from that truth (they do the coordinate math in half)."""
+    h = make_msda_inputs(CONFIGS["base_sca"], dist, 1, torch.float16)
+    hin = _cuda(h)
+    fin = [t.float() if t.is_floating_point() else t for t in hin]
+    rk = omsda.RefKernels()
+    truth = rk.msda(*fin, variant="f32")
+    for mode in (0, 1):
+        prev = _lib.load().b200_msda_set_f16_mode(mode)
+        try:
+            got = bt.multi_scale_deformable_attn(*hin).float()
+        finally:
+            _lib.load().b200_msda_set_f16_mode(prev)
+        err = (got - truth).abs().max().item()
+        print(f"\n[base {dist}] ours fp16 mode {mode}: max-abs vs fp32 reference kernel = {err:.3e}")
+        assert err < FP16_TOL
+    for variant in ("f16", "f16_h2"):
+        e = (rk.msda(*hin, variant=variant).float() - truth).abs().max().item()
+        print(f"[base {dist}] reference {variant} kernel: max-abs vs its own fp32 kernel = {e:.3e}")
+
+
+@needs_ref
+@pytest.mark.parametrize("ref_dtype", [torch.float32, torch.float16])
+def test_int8_vs_reference_int8_kernel(ref_dtype):
+    """Informational + sanity: the reference INT8 kernels quantise intermediates, so they differ from the
+    in-register-dequant definition by O(1 LSB); both must sit within the INT8 bar of the fp32 truth."""
+    (vq, sv, shapes, ref, oq, so, wq, sw, sout), real = _quantised(_cfg("small_sca"), "U", 81, ref_dtype)
+    args = (vq.cuda(), sv, shapes.cuda(), ref.cuda(), oq.cuda(), so, wq.cuda(), sw, sout)
+    theirs = omsda.RefKernels().msda_i8(*args).cpu().numpy().astype(np.float32) * sout
+    ours = bt.multi_scale_deformable_attn_int8(*args).cpu().numpy().astype(np.float32) * sout
+    e_ours, e_theirs = np.abs(ours - real).max(), np.abs(theirs - real).max()
+    print(f"\n[int8 {ref_dtype}] ours {e_ours:.4f}  reference kernel {e_theirs:.4f}  (scale_out {sout:.4f})")
+    assert e_ours < INT8_TOL
+    assert e_ours <= e_theirs + 1e-6  # dequantising in registers can only be closer to the fp32 truth
+    if ref_dtype == torch.float32:  # the CPU emulation of the quantised-intermediate kernel pins oracle <-> _ref
+        emu = omsda.msda_i8_refemu(vq.numpy(), sv, shapes.numpy(), ref.float().numpy(), oq.numpy(), so, wq.numpy(), sw,
+                                   sout).astype(np.float32) * sout  # fmt: skip
+        d = np.abs(emu - theirs) / sout
+        assert d.max() <= 1.0 and (d != 0).mean() < 0.02, (d.max(), (d != 0).mean())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# size-independent properties at full BASELINE size
+# ---------------------------------------------------------------------------------------------------------------
+def test_base_shapes_properties_fp32():
+    value, shapes, ref, off, logits = _cuda(make_msda_inputs(CONFIGS["base_sca"], "U", 5, torch.float32))
+    f = bt.multi_scale_deformable_attn
+    out = f(value, shapes, ref, off, logits)
+    # softmax shift invariance
+    out_shift = f(value, shapes, ref, off, logits + 3.0)
+    assert (out - out_shift).abs().max().item() < 5e-6
+    # linearity in value
+    v2 = torch.randn_like(value)
+    lin = f(2.0 * value + v2, shapes, ref, off, logits)
+    assert (lin - (2.0 * out + f(v2, shapes, ref, off, logits))).abs().max().item() < 2e-5
+    # a constant image sampled strictly inside returns the constant: shrink refs/offsets so no tap leaves the image
+    ones = torch.ones_like(value)
+    inner_ref = ref * 0.5 + 0.25
+    small_off = off.clamp(-1.0, 1.0)
+    const = f(ones, shapes, inner_ref, small_off, logits)
+    assert (const - 1.0).abs().max().item() < 1e-5
+    # everything out of range -> exact zeros
+    far = f(value, shapes, ref + 5.0, off, logits)
+    assert far.abs().max().item() == 0.0
+
+
+def test_base_shapes_fp16_vs_fp32_kernel_full_size():
+    h = make_msda_inputs(CONFIGS["base_sca"], "U", 6, torch.float16)
+    hin = _cuda(h)
+    fin = [t.float() if t.is_floating_point() else t for t in hin]
+    truth = bt.multi_scale_deformable_attn(*fin)
+    for mode in (0, 1):
+        prev = _lib.load().b200_msda_set_f16_mode(mode)
+        try:
+            got = bt.multi_scale_deformable_attn(*hin).float()
+        finally:
+            _lib.load().b200_msda_set_f16_mode(prev)
+        assert (got - truth).abs().max().item() < FP16_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# boundary behaviour
+# ---------------------------------------------------------------------------------------------------------------
+def test_plugin_enqueue_entry_matches_function():
+    cfg = _cfg("small_sca")
+    value, shapes, ref, off, logits = _cuda(make_msda_inputs(cfg, "U", 91, torch.float16))
+    want = bt.multi_scale_deformable_attn(value, shapes, ref, off, logits)
+    lib = _lib.load()
+
+    def desc(t, ttype, scale=1.0):
+        d = _lib.TensorDesc()
+        d.dims.nbDims = t.dim()
+        for i, s in enumerate(t.shape):
+            d.dims.d[i] = s
+        d.type, d.format, d.scale = ttype, 0, scale
+        return d
+
+    out = torch.empty_like(want)
+    ins = [value, shapes, ref, off, logits]
+    in_desc = (_lib.TensorDesc * 5)(desc(value, 1), desc(shapes, 3), desc(ref, 1), desc(off, 1), desc(logits, 1))
+    out_desc = (_lib.TensorDesc * 1)(desc(out, 1))
+    in_ptrs = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ins])
+    out_ptrs = (ctypes.c_void_p * 1)(out.data_ptr())
+    for pos in range(6):
+        io = (_lib.TensorDesc * 6)(*in_desc, out_desc[0])
+        assert lib.b200_msda_supports_format(pos, io, 5, 1) == 1
+    st = lib.b200_msda_enqueue(in_desc, out_desc, in_ptrs, out_ptrs, None, _lib.current_stream_ptr(), 1)
+    assert st == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    in_desc[0].type = 3  # int32 value: unsupported dtype -> 1, like the reference's enqueue
+    assert lib.b200_msda_enqueue(in_desc, out_desc, in_ptrs, out_ptrs, None, _lib.current_stream_ptr(), 0) == 1
+
+
+def test_error_behaviour():
+    cfg = _cfg("small_sca")
+    value, shapes, ref, off, logits = make_msda_inputs(cfg, "U", 92, torch.float32)
+    with pytest.raises(AssertionError):
+        bt.multi_scale_deformable_attn(value, shapes, ref, off, logits)  # CPU tensor: `assert value.is_cuda`
+    cu = _cuda([value, shapes, ref, off, logits])
+    with pytest.raises(_lib.B200OpsError):
+        bt.multi_scale_deformable_attn(cu[0].double(), *cu[1:])
+    with pytest.raises(ValueError):
+        bt.multi_scale_deformable_attn(cu[0], cu[1], cu[2], cu[3][..., :-2], cu[4])
+    lib = _lib.load()
+    assert lib.b200_msda_f32(None, None, None, None, None, 1, 1, 1, 32, 1, 1, 4, 1, None, None) == 2
+    n0 = _lib.launch_count()
+    bt.multi_scale_deformable_attn(*cu)
+    assert _lib.launch_count() == n0 + 1
+
+
+def test_noncontiguous_and_int64_shapes():
+    cfg = _cfg("small_sca")
+    value, shapes, ref, off, logits = _cuda(make_msda_inputs(cfg, "U", 93, torch.float32))
+    want = bt.multi_scale_deformable_attn(value, shapes, ref, off, logits)
+    v_nc = value.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+    got = bt.multi_scale_deformable_attn(v_nc, shapes.long(), ref, off, logits)
+    assert torch.equal(got, want)
