@@ -4,12 +4,26 @@ modulated deformable conv) as hand-written sm_100a CUDA behind the operator inte
 Importing the package loads lib/libb200_bev_ops.so (built in-tree by ``python -m bevformer_tensorrt_b200.build``) and
 fails loudly if it is missing — there is no CPU or PyTorch fallback on this path.
 """
+import os as _os
+import sys as _sys
+
 from . import _lib
 
-_lib.load()
+# Eager load: a missing or stale library is an ImportError at `import bevformer_tensorrt_b200`, not a late surprise.
+# The only exemption is the build step itself (python -m bevformer_tensorrt_b200.build / __graft_entry__.build()),
+# which has to import this package's build module before the library exists.
+_building = _os.environ.get("B200_BEV_OPS_BUILDING") == "1" or any(
+    a == "bevformer_tensorrt_b200.build" for a in getattr(_sys, "orig_argv", [])
+)
+if not _building:
+    _lib.load()
 
 from .functions import (  # noqa: E402
     TRT_FUNCTIONS,
+    grid_sampler,
+    grid_sampler2,
+    grid_sampler_chw2,
+    grid_sampler_int8,
     multi_scale_deformable_attn,
     multi_scale_deformable_attn2,
     multi_scale_deformable_attn_int8,
@@ -17,6 +31,10 @@ from .functions import (  # noqa: E402
 
 __all__ = [
     "TRT_FUNCTIONS",
+    "grid_sampler",
+    "grid_sampler2",
+    "grid_sampler_chw2",
+    "grid_sampler_int8",
     "multi_scale_deformable_attn",
     "multi_scale_deformable_attn2",
     "multi_scale_deformable_attn_int8",

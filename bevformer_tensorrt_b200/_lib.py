@@ -13,6 +13,7 @@ B200_OK = 0
 STATUS = {0: "ok", 1: "unsupported dtype/format/shape", 2: "bad parameter", 3: "CUDA launch error"}
 
 _vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_ip = ctypes.POINTER(ctypes.c_int)
 
 
 class B200OpsError(RuntimeError):
@@ -47,6 +48,10 @@ SIGNATURES = {
     "b200_msda_enqueue": (_i, [ctypes.POINTER(TensorDesc), ctypes.POINTER(TensorDesc), ctypes.POINTER(_vp),
                                ctypes.POINTER(_vp), _vp, _vp, _i]),
     "b200_msda_supports_format": (_i, [_i, ctypes.POINTER(TensorDesc), _i, _i]),
+    "b200_grid_sample_f32": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
+    "b200_grid_sample_f16": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
+    "b200_grid_sample_f16_chw2": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
+    "b200_grid_sample_i8_chw4": (_i, [_vp, _f, _vp, _f, _vp, _f, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
 }  # fmt: skip
 
 _lib = None
@@ -62,7 +67,11 @@ def load() -> ctypes.CDLL:
             )
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:  # header/library mismatch: the .so is older than the sources
+                raise ImportError(f"{LIB_PATH} lacks `{name}`: stale build, rerun "
+                                  "`python -m bevformer_tensorrt_b200.build --force`") from e
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib

@@ -1,0 +1,397 @@
+// grid_sampler.cu — GridSampler2DTRT / GridSampler3DTRT for B200 (sm_100a).
+//
+// Replaces the reference launchers grid_sample<float|__half|__half2> and grid_sample_int8
+// (TensorRT/plugin/grid_sampler/gridSamplerKernel.cu:1933-2043) and their kernels (:666-1923).
+// Semantics = the reference FP32 kernel = ATen grid_sample with two twists: the grid is
+// channel-first [N, 2|3, ...] and spans [-10, 10] (gridSamplerKernel.cu:82-92, :694-698).
+//
+// The reference runs one thread per output pixel that walks all C channels with a read-modify-write on the output
+// per tap (:725-739). Here a thread owns (pixel, slice of channel packets): the source index, tap offsets, weights and
+// validity are computed once in fp32 registers, then each packet costs 4 independent loads + 4 FMAs + one store;
+// consecutive threads are consecutive output pixels of the same channel, so loads are as coalesced as the sampling
+// grid is smooth and stores are fully coalesced. FP16 and INT8 inputs are converted in registers (fp32 math), INT8
+// output is requantised once (T2int8). The reference's __half kernels compute coordinates in half precision and its
+// INT8 kernel leaves out-of-image taps uninitialised (:1140-1176); neither is reproduced.
+#include <climits>
+
+#include "common.cuh"
+
+namespace b200 {
+
+struct GsParams {
+  const void *in;
+  const void *grid;
+  void *out;
+  int N, C, CP;       // CP = channel packets (C, ceil(C/2), ceil(C/4))
+  int Di, Hi, Wi;     // input spatial (Di = 1 for 2-D)
+  int Do, Ho, Wo;     // output spatial
+  int interp, padding, align;
+  int slices, cps;    // channel slices per pixel, packets per slice
+  float scale_i, scale_g, scale_o;
+};
+
+// ---- coordinate helpers: fp32, op-for-op the reference's (and ATen's) formulas -----------------------------------
+__device__ __forceinline__ float gs_unnormalize(float coord, int size, bool align) {
+  // no FMA contraction: the reference forms (coord+10)/2, size/10 and the product as separately rounded fp32 ops
+  const float half = __fmul_rn(__fadd_rn(coord, 10.f), 0.5f);
+  if (align) return __fmul_rn(half, __fdiv_rn(static_cast<float>(size - 1), 10.f));
+  return __fadd_rn(__fmul_rn(half, __fdiv_rn(static_cast<float>(size), 10.f)), -0.5f);
+}
+__device__ __forceinline__ float gs_clip(float in, int limit) {
+  return fminf(static_cast<float>(limit - 1), fmaxf(in, 0.f));
+}
+__device__ __forceinline__ float gs_reflect(float in, int twice_low, int twice_high) {
+  if (twice_low == twice_high) return 0.f;
+  const float mn = __fmul_rn(static_cast<float>(twice_low), 0.5f);
+  const float span = __fmul_rn(static_cast<float>(twice_high - twice_low), 0.5f);
+  in = fabsf(__fsub_rn(in, mn));
+  const float extra = fmodf(in, span);
+  const int flips = static_cast<int>(floorf(__fdiv_rn(in, span)));
+  return (flips % 2 == 0) ? __fadd_rn(extra, mn) : __fadd_rn(__fsub_rn(span, extra), mn);
+}
+__device__ __forceinline__ float gs_safe(float x) {
+  if (x > static_cast<float>(INT_MAX - 1) || x < static_cast<float>(INT_MIN) || !isfinite(x)) return -100.f;
+  return x;
+}
+__device__ __forceinline__ float gs_compute_coordinates(float coord, int size, int padding, bool align) {
+  if (padding == 1) {
+    coord = gs_clip(coord, size);
+  } else if (padding == 2) {
+    coord = align ? gs_reflect(coord, 0, 2 * (size - 1)) : gs_reflect(coord, -1, 2 * size - 1);
+    coord = gs_clip(coord, size);
+  }
+  return gs_safe(coord);
+}
+__device__ __forceinline__ float gs_source_index(float coord, int size, int padding, bool align) {
+  return gs_compute_coordinates(gs_unnormalize(coord, size, align), size, padding, align);
+}
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__device__ __forceinline__ void cubic_coeffs(float (&c)[4], float t) {
+  const float A = -0.75f;
+  c[0] = cubic2(t + 1.f, A);
+  c[1] = cubic1(t, A);
+  const float x2 = 1.f - t;
+  c[2] = cubic1(x2, A);
+  c[3] = cubic2(x2 + 1.f, A);
+}
+
+// ---- packet I/O ---------------------------------------------------------------------------------------------------
+// A packet is the unit stored per (channel group, pixel): float, __half, __half2 (kCHW2) or 4 x int8 (kCHW4).
+enum { kF32 = 0, kF16 = 1, kF16x2 = 2, kI8x4 = 3 };
+
+template <int K>
+struct Pk;
+template <>
+struct Pk<kF32> {
+  using T = float;
+  static constexpr int W = 1;
+  __device__ static void load(const T *p, float (&v)[1], float) { v[0] = __ldg(p); }
+  __device__ static void store(T *p, const float (&v)[1], float) { *p = v[0]; }
+  __device__ static void grid_xy(const void *g, long long plane, long long pix, long long n, float, float &x, float &y,
+                                 float &z, bool has_z) {
+    const T *gp = static_cast<const T *>(g) + n * (has_z ? 3 : 2) * plane + pix;
+    x = __ldg(gp), y = __ldg(gp + plane), z = has_z ? __ldg(gp + 2 * plane) : 0.f;
+  }
+};
+template <>
+struct Pk<kF16> {
+  using T = __half;
+  static constexpr int W = 1;
+  __device__ static void load(const T *p, float (&v)[1], float) { v[0] = __half2float(__ldg(p)); }
+  __device__ static void store(T *p, const float (&v)[1], float) { *p = __float2half_rn(v[0]); }
+  __device__ static void grid_xy(const void *g, long long plane, long long pix, long long n, float, float &x, float &y,
+                                 float &z, bool has_z) {
+    const T *gp = static_cast<const T *>(g) + n * (has_z ? 3 : 2) * plane + pix;
+    x = __half2float(__ldg(gp)), y = __half2float(__ldg(gp + plane));
+    z = has_z ? __half2float(__ldg(gp + 2 * plane)) : 0.f;
+  }
+};
+template <>
+struct Pk<kF16x2> {  // kCHW2: [N, ceil(C/2), H, W, 2]; the 2-channel grid is one (x, y) pair per pixel (:946-961)
+  using T = uint32_t;
+  static constexpr int W = 2;
+  __device__ static void load(const T *p, float (&v)[2], float) {
+    const float2 f = h2_to_f2(__ldg(p));
+    v[0] = f.x, v[1] = f.y;
+  }
+  __device__ static void store(T *p, const float (&v)[2], float) { *p = f2_to_h2(v[0], v[1]); }
+  __device__ static void grid_xy(const void *g, long long plane, long long pix, long long n, float, float &x, float &y,
+                                 float &z, bool) {
+    const float2 f = h2_to_f2(__ldg(static_cast<const T *>(g) + n * plane + pix));
+    x = f.x, y = f.y, z = 0.f;
+  }
+};
+template <>
+struct Pk<kI8x4> {  // kCHW4: [N, ceil(C/4), H, W, 4]; grid = (x, y, pad, pad) int8 per pixel (:1088-1103)
+  using T = uint32_t;
+  static constexpr int W = 4;
+  __device__ static void load(const T *p, float (&v)[4], float s) {
+    const uint32_t u = __ldg(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = static_cast<float>(static_cast<int8_t>(u >> (8 * i))) * s;
+  }
+  __device__ static void store(T *p, const float (&v)[4], float inv_so) {
+    uint32_t u = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u |= (static_cast<uint32_t>(to_int8_sat(v[i] * inv_so)) & 0xffu) << (8 * i);
+    *p = u;
+  }
+  __device__ static void grid_xy(const void *g, long long plane, long long pix, long long n, float sg, float &x,
+                                 float &y, float &z, bool) {
+    const uint32_t u = __ldg(static_cast<const T *>(g) + n * plane + pix);
+    x = static_cast<float>(static_cast<int8_t>(u)) * sg, y = static_cast<float>(static_cast<int8_t>(u >> 8)) * sg;
+    z = 0.f;
+  }
+};
+
+// ---- 2-D kernel -----------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) grid_sample_2d_kernel(const GsParams p) {
+  using P = Pk<K>;
+  using T = typename P::T;
+  constexpr int W = P::W;
+  const long long plane_o = static_cast<long long>(p.Ho) * p.Wo;
+  const long long plane_i = static_cast<long long>(p.Hi) * p.Wi;
+  const long long total = static_cast<long long>(p.N) * p.slices * plane_o;
+  const bool align = p.align != 0;
+  // INT8 output requantisation is a true division in the reference's fp32 oracle form; one reciprocal here differs by
+  // at most an ulp before rounding to int8.
+  const float so = K == kI8x4 ? 1.f / p.scale_o : 1.f;
+
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = idx % plane_o;
+    const int s = static_cast<int>((idx / plane_o) % p.slices);
+    const long long n = idx / (plane_o * p.slices);
+    float gx, gy, gz;
+    P::grid_xy(p.grid, plane_o, pix, n, p.scale_g, gx, gy, gz, false);
+
+    const int cp0 = s * p.cps, cp1 = min(p.CP, cp0 + p.cps);
+    const T *in_n = static_cast<const T *>(p.in) + (n * p.CP + cp0) * plane_i;
+    T *out_p = static_cast<T *>(p.out) + (n * p.CP + cp0) * plane_o + pix;
+
+    if (p.interp == 0) {  // bilinear (:700-740)
+      const float ix = gs_source_index(gx, p.Wi, p.padding, align);
+      const float iy = gs_source_index(gy, p.Hi, p.padding, align);
+      const int ix_nw = static_cast<int>(floorf(ix)), iy_nw = static_cast<int>(floorf(iy));
+      const int ix_se = ix_nw + 1, iy_se = iy_nw + 1;
+      const float fx1 = __fsub_rn(static_cast<float>(ix_se), ix), fx0 = __fsub_rn(ix, static_cast<float>(ix_nw));
+      const float fy1 = __fsub_rn(static_cast<float>(iy_se), iy), fy0 = __fsub_rn(iy, static_cast<float>(iy_nw));
+      const bool x0 = ix_nw >= 0 && ix_nw < p.Wi, x1 = ix_se >= 0 && ix_se < p.Wi;
+      const bool y0 = iy_nw >= 0 && iy_nw < p.Hi, y1 = iy_se >= 0 && iy_se < p.Hi;
+      const float w_nw = (x0 && y0) ? fx1 * fy1 : 0.f, w_ne = (x1 && y0) ? fx0 * fy1 : 0.f;
+      const float w_sw = (x0 && y1) ? fx1 * fy0 : 0.f, w_se = (x1 && y1) ? fx0 * fy0 : 0.f;
+      // out-of-image taps carry weight 0 and alias an in-image address (clamped), so loads are unconditional
+      const int cx0 = min(max(ix_nw, 0), p.Wi - 1), cx1 = min(max(ix_se, 0), p.Wi - 1);
+      const int cy0 = min(max(iy_nw, 0), p.Hi - 1), cy1 = min(max(iy_se, 0), p.Hi - 1);
+      const int o_nw = cy0 * p.Wi + cx0, o_ne = cy0 * p.Wi + cx1, o_sw = cy1 * p.Wi + cx0, o_se = cy1 * p.Wi + cx1;
+      const T *ip = in_n;
+      T *op = out_p;
+#pragma unroll 4
+      for (int cp = cp0; cp < cp1; ++cp, ip += plane_i, op += plane_o) {
+        float a[W], b[W], c[W], d[W], o[W];
+        P::load(ip + o_nw, a, p.scale_i), P::load(ip + o_ne, b, p.scale_i);
+        P::load(ip + o_sw, c, p.scale_i), P::load(ip + o_se, d, p.scale_i);
+#pragma unroll
+        for (int i = 0; i < W; ++i) o[i] = fmaf(d[i], w_se, fmaf(c[i], w_sw, fmaf(b[i], w_ne, a[i] * w_nw)));
+        P::store(op, o, so);
+      }
+    } else if (p.interp == 1) {  // nearest (:741-756): ::round, half away from zero
+      const float ix = gs_source_index(gx, p.Wi, p.padding, align);
+      const float iy = gs_source_index(gy, p.Hi, p.padding, align);
+      const int ixn = static_cast<int>(roundf(ix)), iyn = static_cast<int>(roundf(iy));
+      const bool ok = ixn >= 0 && ixn < p.Wi && iyn >= 0 && iyn < p.Hi;
+      const int o_n = ok ? iyn * p.Wi + ixn : 0;
+      const T *ip = in_n;
+      T *op = out_p;
+      for (int cp = cp0; cp < cp1; ++cp, ip += plane_i, op += plane_o) {
+        float a[W];
+        P::load(ip + o_n, a, p.scale_i);
+#pragma unroll
+        for (int i = 0; i < W; ++i) a[i] = ok ? a[i] : 0.f;
+        P::store(op, a, so);
+      }
+    } else {  // bicubic (:757-792)
+      const float ix = gs_unnormalize(gx, p.Wi, align), iy = gs_unnormalize(gy, p.Hi, align);
+      const float ix_nw = floorf(ix), iy_nw = floorf(iy);
+      float cx[4], cy[4];
+      cubic_coeffs(cx, ix - ix_nw);
+      cubic_coeffs(cy, iy - iy_nw);
+      int xo[4], yo[4];  // column / row offsets, -1 when outside (get_value_bounded :615-629)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int xi = static_cast<int>(gs_compute_coordinates(ix_nw - 1.f + i, p.Wi, p.padding, align));
+        const int yi = static_cast<int>(gs_compute_coordinates(iy_nw - 1.f + i, p.Hi, p.padding, align));
+        xo[i] = (xi >= 0 && xi < p.Wi) ? xi : -1;
+        yo[i] = (yi >= 0 && yi < p.Hi) ? yi * p.Wi : -1;
+      }
+      const T *ip = in_n;
+      T *op = out_p;
+      for (int cp = cp0; cp < cp1; ++cp, ip += plane_i, op += plane_o) {
+        float o[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) o[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float row[W];
+#pragma unroll
+          for (int i = 0; i < W; ++i) row[i] = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[W];
+            const bool ok = xo[q] >= 0 && yo[r] >= 0;
+            P::load(ip + (ok ? yo[r] + xo[q] : 0), v, p.scale_i);
+#pragma unroll
+            for (int i = 0; i < W; ++i) row[i] = fmaf(ok ? v[i] : 0.f, cx[q], row[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < W; ++i) o[i] = fmaf(row[i], cy[r], o[i]);
+        }
+        P::store(op, o, so);
+      }
+    }
+  }
+}
+
+// ---- 3-D kernel (GridSampler3DTRT, :1271-1923): trilinear / nearest, fp32 / fp16 kLINEAR ----------------------------
+template <int K>
+__global__ void __launch_bounds__(256) grid_sample_3d_kernel(const GsParams p) {
+  using P = Pk<K>;
+  using T = typename P::T;
+  const long long plane_o = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  const long long plane_i = static_cast<long long>(p.Di) * p.Hi * p.Wi;
+  const long long total = static_cast<long long>(p.N) * p.slices * plane_o;
+  const bool align = p.align != 0;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = idx % plane_o;
+    const int s = static_cast<int>((idx / plane_o) % p.slices);
+    const long long n = idx / (plane_o * p.slices);
+    float gx, gy, gz;
+    P::grid_xy(p.grid, plane_o, pix, n, 1.f, gx, gy, gz, true);
+    const float ix = gs_source_index(gx, p.Wi, p.padding, align);
+    const float iy = gs_source_index(gy, p.Hi, p.padding, align);
+    const float iz = gs_source_index(gz, p.Di, p.padding, align);
+    const int cp0 = s * p.cps, cp1 = min(p.CP, cp0 + p.cps);
+    const T *ip = static_cast<const T *>(p.in) + (n * p.CP + cp0) * plane_i;
+    T *op = static_cast<T *>(p.out) + (n * p.CP + cp0) * plane_o + pix;
+    if (p.interp == 0) {
+      const int x0 = static_cast<int>(floorf(ix)), y0 = static_cast<int>(floorf(iy)), z0 = static_cast<int>(floorf(iz));
+      const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
+      int off[8];
+      float wt[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int dx = t & 1, dy = (t >> 1) & 1, dz = t >> 2;
+        const int x = x0 + dx, y = y0 + dy, z = z0 + dz;
+        const bool ok = x >= 0 && x < p.Wi && y >= 0 && y < p.Hi && z >= 0 && z < p.Di;
+        // weight of a corner = product over axes of (1 - f) for the low side and f for the high side, written as the
+        // reference does: (x_high - ix) etc. (:1330-1337)
+        const float wx = dx ? fx : (static_cast<float>(x0 + 1) - ix);
+        const float wy = dy ? fy : (static_cast<float>(y0 + 1) - iy);
+        const float wz = dz ? fz : (static_cast<float>(z0 + 1) - iz);
+        wt[t] = ok ? wx * wy * wz : 0.f;
+        off[t] = ok ? (z * p.Hi + y) * p.Wi + x : 0;
+      }
+      for (int cp = cp0; cp < cp1; ++cp, ip += plane_i, op += plane_o) {
+        float o[1] = {0.f};
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float v[1];
+          P::load(ip + off[t], v, 1.f);
+          o[0] = fmaf(v[0], wt[t], o[0]);
+        }
+        P::store(op, o, 1.f);
+      }
+    } else {
+      const int x = static_cast<int>(roundf(ix)), y = static_cast<int>(roundf(iy)), z = static_cast<int>(roundf(iz));
+      const bool ok = x >= 0 && x < p.Wi && y >= 0 && y < p.Hi && z >= 0 && z < p.Di;
+      const int o_n = ok ? (z * p.Hi + y) * p.Wi + x : 0;
+      for (int cp = cp0; cp < cp1; ++cp, ip += plane_i, op += plane_o) {
+        float v[1];
+        P::load(ip + o_n, v, 1.f);
+        v[0] = ok ? v[0] : 0.f;
+        P::store(op, v, 1.f);
+      }
+    }
+  }
+}
+
+// ---- host -----------------------------------------------------------------------------------------------------------
+template <int K>
+static int launch_gs(void *out, const void *in, const void *grid, const int *od, const int *id, const int *gd, int nb,
+                     int interp, int padding, int align, float si, float sg, float so, cudaStream_t s) {
+  if (!out || !in || !grid || !od || !id || !gd) return B200_ERR_BAD_PARAM;
+  if (nb != 4 && nb != 5) return B200_ERR_UNSUPPORTED;  // the reference printf()s and returns (:1959-1961)
+  if (interp < 0 || interp > 2 || padding < 0 || padding > 2) return B200_ERR_BAD_PARAM;
+  for (int i = 0; i < nb; ++i)
+    if (id[i] <= 0 || gd[i] <= 0 || od[i] <= 0) return B200_ERR_BAD_PARAM;
+  if (gd[0] != id[0] || gd[1] != nb - 2) return B200_ERR_BAD_PARAM;
+  constexpr int W = Pk<K>::W;
+  GsParams p{};
+  p.in = in, p.grid = grid, p.out = out;
+  p.N = id[0], p.C = id[1], p.CP = (id[1] + W - 1) / W;
+  p.interp = interp, p.padding = padding, p.align = align;
+  p.scale_i = si, p.scale_g = sg, p.scale_o = so;
+  if (nb == 4) {
+    p.Di = p.Do = 1, p.Hi = id[2], p.Wi = id[3], p.Ho = gd[2], p.Wo = gd[3];
+  } else {
+    if (K == kF16x2 || K == kI8x4 || interp == 2) return B200_ERR_UNSUPPORTED;  // 3-D: linear layouts, no bicubic
+    p.Di = id[2], p.Hi = id[3], p.Wi = id[4], p.Do = gd[2], p.Ho = gd[3], p.Wo = gd[4];
+  }
+  const long long plane_i = static_cast<long long>(p.Di) * p.Hi * p.Wi;
+  const long long plane_o = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  if (plane_i >= (1ll << 31) || plane_o >= (1ll << 31)) return B200_ERR_BAD_PARAM;
+  // enough (pixel, slice) threads to fill 148 SMs a few times over, at most 16 packets per thread
+  const long long pixels = static_cast<long long>(p.N) * plane_o;
+  int slices = 1;
+  while (slices < p.CP && (pixels * slices < 148ll * 2048 * 4 || (p.CP + slices - 1) / slices > 16)) slices <<= 1;
+  p.cps = (p.CP + slices - 1) / slices;
+  p.slices = (p.CP + p.cps - 1) / p.cps;
+  const long long total = pixels * p.slices;
+  const unsigned blocks = static_cast<unsigned>(total / 256 + 1 < (1 << 22) ? total / 256 + 1 : (1 << 22));
+  if (nb == 4)
+    grid_sample_2d_kernel<K><<<blocks, 256, 0, s>>>(p);
+  else
+    grid_sample_3d_kernel<(K == kF16 ? kF16 : kF32)><<<blocks, 256, 0, s>>>(p);
+  return check_launch();
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_grid_sample_f32(float *output, const float *input, const float *grid, const int *output_dims,
+                         const int *input_dims, const int *grid_dims, int nb_dims, int interp, int padding,
+                         int align_corners, void *stream) {
+  return launch_gs<kF32>(output, input, grid, output_dims, input_dims, grid_dims, nb_dims, interp, padding,
+                         align_corners, 1.f, 1.f, 1.f, static_cast<cudaStream_t>(stream));
+}
+
+int b200_grid_sample_f16(void *output, const void *input, const void *grid, const int *output_dims,
+                         const int *input_dims, const int *grid_dims, int nb_dims, int interp, int padding,
+                         int align_corners, void *stream) {
+  return launch_gs<kF16>(output, input, grid, output_dims, input_dims, grid_dims, nb_dims, interp, padding,
+                         align_corners, 1.f, 1.f, 1.f, static_cast<cudaStream_t>(stream));
+}
+
+int b200_grid_sample_f16_chw2(void *output, const void *input, const void *grid, const int *output_dims,
+                              const int *input_dims, const int *grid_dims, int nb_dims, int interp, int padding,
+                              int align_corners, void *stream) {
+  return launch_gs<kF16x2>(output, input, grid, output_dims, input_dims, grid_dims, nb_dims, interp, padding,
+                           align_corners, 1.f, 1.f, 1.f, static_cast<cudaStream_t>(stream));
+}
+
+int b200_grid_sample_i8_chw4(int8_t *output, float scale_o, const int8_t *input, float scale_i, const int8_t *grid,
+                             float scale_g, const int *output_dims, const int *input_dims, const int *grid_dims,
+                             int nb_dims, int interp, int padding, int align_corners, void *stream) {
+  if (!(scale_o > 0.f)) return B200_ERR_BAD_PARAM;
+  if (nb_dims != 4) return B200_ERR_UNSUPPORTED;  // the reference: "input and grid dims should be 4" (:2040-2042)
+  return launch_gs<kI8x4>(output, input, grid, output_dims, input_dims, grid_dims, nb_dims, interp, padding,
+                          align_corners, scale_i, scale_g, scale_o, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -25,7 +25,7 @@ namespace b200 {
 constexpr int kMaxLevels = 16;
 constexpr int kThreads = 256;
 
-static int g_f16_mode = 1;
+static int g_f16_mode = 0;  // exact by default; 1 = mixed FHFMA (opt-in, see Io<__half, 1>)
 
 struct MsdaParams {
   const void *value;
@@ -75,86 +75,111 @@ __device__ __forceinline__ int tap_mask_of(const PointRec &r, int H, int W) {
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Per-dtype I/O
+// Per-dtype I/O. Every lane moves 16 bytes of channels per tap: 4 floats, 8 halves or 16 int8.
+//   Wt  = number of 32-bit registers that carry the four tap weights of a point from the owner lane:
+//         4 (fp32 weights) or 2 (fp16 pairs, for the FHFMA paths).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T>
+__device__ __forceinline__ float2 ffma2(float2 a, float w, float2 c) {
+  // Blackwell packed fp32 FMA (fma.rn.f32x2 -> SASS FFMA2): two IEEE fp32 FMAs per issue slot
+  unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rc = *reinterpret_cast<unsigned long long *>(&c),
+                     rd;
+  const float2 w2 = make_float2(w, w);
+  const unsigned long long rw = *reinterpret_cast<const unsigned long long *>(&w2);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rw), "l"(rc));
+  return *reinterpret_cast<float2 *>(&rd);
+}
+
+template <typename T, int MODE>
 struct Io;
 
-template <>
-struct Io<float> {
-  static constexpr int kVec = 4;
-  __device__ static void load_off4(const float *p, float s, float (&ox)[4], float (&oy)[4]) {
+template <int MODE>
+struct Io<float, MODE> {
+  static constexpr int kVec = 4, kWt = 4;
+  __device__ static void load_off4(const float *p, float, float (&ox)[4], float (&oy)[4]) {
     const uint4 a = ldg128_stream(p), b = ldg128_stream(p + 4);
     ox[0] = __uint_as_float(a.x), oy[0] = __uint_as_float(a.y), ox[1] = __uint_as_float(a.z),
     oy[1] = __uint_as_float(a.w);
     ox[2] = __uint_as_float(b.x), oy[2] = __uint_as_float(b.y), ox[3] = __uint_as_float(b.z),
     oy[3] = __uint_as_float(b.w);
   }
-  __device__ static void load_lg4(const float *p, float s, float (&lg)[4]) {
+  __device__ static void load_lg4(const float *p, float, float (&lg)[4]) {
     const uint4 a = ldg128_stream(p);
     lg[0] = __uint_as_float(a.x), lg[1] = __uint_as_float(a.y), lg[2] = __uint_as_float(a.z),
     lg[3] = __uint_as_float(a.w);
   }
-  template <int MODE>
-  __device__ static void fma_tap(float (&acc)[4], const uint4 &t, float w) {
-    acc[0] = fmaf(w, __uint_as_float(t.x), acc[0]);
-    acc[1] = fmaf(w, __uint_as_float(t.y), acc[1]);
-    acc[2] = fmaf(w, __uint_as_float(t.z), acc[2]);
-    acc[3] = fmaf(w, __uint_as_float(t.w), acc[3]);
+  __device__ static void pack_w(float (&o)[4], float w00, float w01, float w10, float w11) {
+    o[0] = w00, o[1] = w01, o[2] = w10, o[3] = w11;
   }
-  __device__ static void store(float *p, const float (&acc)[4], float sum, const MsdaParams &) {
-    uint4 o;
-    o.x = __float_as_uint(acc[0] / sum), o.y = __float_as_uint(acc[1] / sum);
-    o.z = __float_as_uint(acc[2] / sum), o.w = __float_as_uint(acc[3] / sum);
-    stg128_stream(p, o);
+  __device__ static void fma_point(float (&acc)[4], const uint4 (&t)[4], const float (&w)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 *a2 = reinterpret_cast<float2 *>(acc);
+      a2[0] = ffma2(make_float2(__uint_as_float(t[k].x), __uint_as_float(t[k].y)), w[k], a2[0]);
+      a2[1] = ffma2(make_float2(__uint_as_float(t[k].z), __uint_as_float(t[k].w)), w[k], a2[1]);
+    }
+  }
+  __device__ static void store(float *p, const float (&acc)[4], float inv_sum, const MsdaParams &) {
+    stg128_stream(p, make_uint4(__float_as_uint(acc[0] * inv_sum), __float_as_uint(acc[1] * inv_sum),
+                                __float_as_uint(acc[2] * inv_sum), __float_as_uint(acc[3] * inv_sum)));
   }
 };
 
-template <>
-struct Io<__half> {
-  static constexpr int kVec = 8;
-  __device__ static void load_off4(const __half *p, float s, float (&ox)[4], float (&oy)[4]) {
+// MODE 0: exact — taps widened to fp32 (HADD2.F32), fp32 weights, FFMA2.
+// MODE 1: mixed — fp16 weights, FHFMA (fp16 x fp16 + fp32 -> fp32, one rounding). Faster, but the 2^-11 relative
+//         rounding of the weights costs up to ~3e-4 absolute on O(1) outputs: opt-in only (b200_msda_set_f16_mode).
+template <int MODE>
+struct Io<__half, MODE> {
+  static constexpr int kVec = 8, kWt = MODE == 1 ? 2 : 4;
+  __device__ static void load_off4(const __half *p, float, float (&ox)[4], float (&oy)[4]) {
     const uint4 a = ldg128_stream(p);
     const float2 p0 = h2_to_f2(a.x), p1 = h2_to_f2(a.y), p2 = h2_to_f2(a.z), p3 = h2_to_f2(a.w);
     ox[0] = p0.x, oy[0] = p0.y, ox[1] = p1.x, oy[1] = p1.y, ox[2] = p2.x, oy[2] = p2.y, ox[3] = p3.x, oy[3] = p3.y;
   }
-  __device__ static void load_lg4(const __half *p, float s, float (&lg)[4]) {
+  __device__ static void load_lg4(const __half *p, float, float (&lg)[4]) {
     const uint2 a = ldg64_stream(p);
     const float2 p0 = h2_to_f2(a.x), p1 = h2_to_f2(a.y);
     lg[0] = p0.x, lg[1] = p0.y, lg[2] = p1.x, lg[3] = p1.y;
   }
-  // MODE 0: exact (tap -> fp32, FFMA with the fp32 weight). MODE 1: the weight arrives as fp16 bits in the low half
-  // of `wbits` and the product is formed by FHFMA (fp16 x fp16 + fp32, single rounding into the fp32 accumulator).
-  template <int MODE>
-  __device__ static void fma_tap(float (&acc)[8], const uint4 &t, float w) {
-    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
-    if (MODE == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 v = h2_to_f2(u[i]);
-        acc[2 * i] = fmaf(w, v.x, acc[2 * i]);
-        acc[2 * i + 1] = fmaf(w, v.y, acc[2 * i + 1]);
-      }
+  __device__ static void pack_w(float (&o)[kWt], float w00, float w01, float w10, float w11) {
+    if (MODE == 1) {
+      o[0] = __uint_as_float(f2_to_h2(w00, w01)), o[1] = __uint_as_float(f2_to_h2(w10, w11));
     } else {
-      const unsigned short wh = static_cast<unsigned short>(__float_as_uint(w) & 0xffffu);
+      o[0] = w00, o[1] = w01, o[kWt - 2] = w10, o[kWt - 1] = w11;
+    }
+  }
+  __device__ static void fma_point(float (&acc)[8], const uint4 (&t)[4], const float (&w)[kWt]) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[2 * i] = fma_f32_f16(static_cast<unsigned short>(u[i] & 0xffffu), wh, acc[2 * i]);
-        acc[2 * i + 1] = fma_f32_f16(static_cast<unsigned short>(u[i] >> 16), wh, acc[2 * i + 1]);
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t u[4] = {t[k].x, t[k].y, t[k].z, t[k].w};
+      if (MODE == 1) {
+        const uint32_t wp = __float_as_uint(w[k >> 1]);
+        const unsigned short wh = static_cast<unsigned short>((k & 1) ? (wp >> 16) : (wp & 0xffffu));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] = fma_f32_f16(static_cast<unsigned short>(u[i] & 0xffffu), wh, acc[2 * i]);
+          acc[2 * i + 1] = fma_f32_f16(static_cast<unsigned short>(u[i] >> 16), wh, acc[2 * i + 1]);
+        }
+      } else {
+        float2 *a2 = reinterpret_cast<float2 *>(acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a2[i] = ffma2(h2_to_f2(u[i]), w[k < kWt ? k : 0], a2[i]);
       }
     }
   }
-  __device__ static void store(__half *p, const float (&acc)[8], float sum, const MsdaParams &) {
-    uint4 o;
-    o.x = f2_to_h2(acc[0] / sum, acc[1] / sum), o.y = f2_to_h2(acc[2] / sum, acc[3] / sum);
-    o.z = f2_to_h2(acc[4] / sum, acc[5] / sum), o.w = f2_to_h2(acc[6] / sum, acc[7] / sum);
-    stg128_stream(p, o);
+  __device__ static void store(__half *p, const float (&acc)[8], float inv_sum, const MsdaParams &) {
+    stg128_stream(p, make_uint4(f2_to_h2(acc[0] * inv_sum, acc[1] * inv_sum), f2_to_h2(acc[2] * inv_sum, acc[3] * inv_sum),
+                                f2_to_h2(acc[4] * inv_sum, acc[5] * inv_sum),
+                                f2_to_h2(acc[6] * inv_sum, acc[7] * inv_sum)));
   }
 };
 
-template <>
-struct Io<int8_t> {
-  static constexpr int kVec = 16;
+// INT8: taps are dequantised in registers. int8 -> fp16 is exact (|q| <= 128): flip the sign bit, splice each byte
+// under the exponent byte 0x64 (= 1024 + byte as fp16) with PRMT, subtract 1152 with one packed HADD2 per pair. The
+// product with the fp16 tap weight is accumulated in fp32 by FHFMA; the fp16 weight rounding (2^-11 relative) is two
+// orders of magnitude below the INT8 output step. scale_value is applied once, at the requantisation.
+template <int MODE>
+struct Io<int8_t, MODE> {
+  static constexpr int kVec = 16, kWt = 2;
   __device__ static float deq(uint32_t word, int byte, float s) {
     return static_cast<float>(static_cast<int8_t>(word >> (8 * byte))) * s;
   }
@@ -168,29 +193,40 @@ struct Io<int8_t> {
     const uint32_t a = ldg32_stream(p);
     lg[0] = deq(a, 0, s), lg[1] = deq(a, 1, s), lg[2] = deq(a, 2, s), lg[3] = deq(a, 3, s);
   }
-  template <int MODE>
-  __device__ static void fma_tap(float (&acc)[16], const uint4 &t, float w) {
-    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+  __device__ static void pack_w(float (&o)[2], float w00, float w01, float w10, float w11) {
+    o[0] = __uint_as_float(f2_to_h2(w00, w01)), o[1] = __uint_as_float(f2_to_h2(w10, w11));
+  }
+  __device__ static void fma_point(float (&acc)[16], const uint4 (&t)[4], const float (&w)[2]) {
+    const __half2 bias = __floats2half2_rn(1152.f, 1152.f);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t wp = __float_as_uint(w[k >> 1]);
+      const unsigned short wh = static_cast<unsigned short>((k & 1) ? (wp >> 16) : (wp & 0xffffu));
+      const uint32_t u[4] = {t[k].x, t[k].y, t[k].z, t[k].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v = static_cast<float>(static_cast<int8_t>(u[i] >> (8 * j)));
-        acc[4 * i + j] = fmaf(w, v, acc[4 * i + j]);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t x = u[i] ^ 0x80808080u;
+        uint32_t lo = __byte_perm(x, 0x64646464u, 0x4140), hi = __byte_perm(x, 0x64646464u, 0x4342);
+        const __half2 a = __hsub2(*reinterpret_cast<__half2 *>(&lo), bias);
+        const __half2 b = __hsub2(*reinterpret_cast<__half2 *>(&hi), bias);
+        const uint32_t ua = *reinterpret_cast<const uint32_t *>(&a), ub = *reinterpret_cast<const uint32_t *>(&b);
+        acc[4 * i + 0] = fma_f32_f16(static_cast<unsigned short>(ua & 0xffffu), wh, acc[4 * i + 0]);
+        acc[4 * i + 1] = fma_f32_f16(static_cast<unsigned short>(ua >> 16), wh, acc[4 * i + 1]);
+        acc[4 * i + 2] = fma_f32_f16(static_cast<unsigned short>(ub & 0xffffu), wh, acc[4 * i + 2]);
+        acc[4 * i + 3] = fma_f32_f16(static_cast<unsigned short>(ub >> 16), wh, acc[4 * i + 3]);
       }
     }
   }
-  __device__ static void store(int8_t *p, const float (&acc)[16], float sum, const MsdaParams &prm) {
+  __device__ static void store(int8_t *p, const float (&acc)[16], float inv_sum, const MsdaParams &prm) {
     // real = acc * scale_value / sum ; q = T2int8(real / scale_out)
+    const float mul = prm.scale_value * inv_sum / prm.scale_out;
     uint32_t o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t word = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float real = acc[4 * i + j] * prm.scale_value / sum;
-        word |= (static_cast<uint32_t>(to_int8_sat(real / prm.scale_out)) & 0xffu) << (8 * j);
-      }
+      for (int j = 0; j < 4; ++j)
+        word |= (static_cast<uint32_t>(to_int8_sat(acc[4 * i + j] * mul)) & 0xffu) << (8 * j);
       o[i] = word;
     }
     stg128_stream(p, make_uint4(o[0], o[1], o[2], o[3]));
@@ -217,11 +253,12 @@ constexpr int kMaxChunks = 64;
 
 template <typename T, typename R, int C, int ROUNDS, int MODE>
 __global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams prm) {
-  constexpr int VEC = Io<T>::kVec;
+  using IO = Io<T, MODE>;
+  constexpr int VEC = IO::kVec;
   constexpr int LPI = C / VEC;
   constexpr int IPW = 32 / LPI;
   constexpr int IPB = IPW * (kThreads / 32);
-  constexpr int NW = MODE == 1 ? 2 : 4;  // weight registers broadcast per point (fp16 pairs in mixed mode)
+  constexpr int NW = IO::kWt;
   // lanes whose sub-index is 0 (one per item of the warp); shifted by j it selects the owner lanes j
   constexpr unsigned OWNER0 = LPI == 1 ? 0xffffffffu
                               : LPI == 2 ? 0x55555555u
@@ -266,15 +303,44 @@ __global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams 
   const float *rp = s_ref + (bq - bq0) * 2 * G;
   const T *off_item = static_cast<const T *>(prm.off) + it * NP * 2;
   const T *lg_item = static_cast<const T *>(prm.logits) + it * NP;
+  T *out_item = static_cast<T *>(prm.out) + it * C + sub * VEC;
 
-  // ---- softmax statistics over the item's NP logits (…Kernel.cu:642-648, :667-669)
+  // ---- phase A: sampling positions of the points this lane owns (chunk c = r*LPI + sub), the bit-exact part
+  float him[ROUNDS][4], wim[ROUNDS][4];
+  unsigned inr = 0;  // bit r*4+k: point in range (…Kernel.cu:674)
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int c = r * LPI + sub;
+    const bool have = c < NCH;
+    const int cc = have ? c : 0;
+    const int H = s_H[cc], W = s_W[cc];
+    float ox[4], oy[4];
+    IO::load_off4(off_item + cc * 8, prm.scale_offset, ox, oy);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = k & (G - 1);  // == (point index within its level) % G, because P % 4 == 0 and G divides 4
+      wim[r][k] = __fadd_rn(__fmaf_rn(rp[2 * g], static_cast<float>(W), ox[k]), -0.5f);
+      him[r][k] = __fadd_rn(__fmaf_rn(rp[2 * g + 1], static_cast<float>(H), oy[k]), -0.5f);
+      const bool ok = have && him[r][k] > -1.f && wim[r][k] > -1.f && him[r][k] < static_cast<float>(H) &&
+                      wim[r][k] < static_cast<float>(W);
+      inr |= ok ? (1u << (r * 4 + k)) : 0u;
+    }
+  }
+  // Nothing of this warp's items lands inside any image (a camera that does not see these BEV queries): the result
+  // is exactly 0 (= 0 / sum), and logits are never read.
+  if (__ballot_sync(kFullMask, inr != 0u) == 0u) {
+    if (active) stg128_stream(out_item, make_uint4(0u, 0u, 0u, 0u));
+    return;
+  }
+
+  // ---- phase B: softmax statistics over the item's NP logits (…Kernel.cu:642-648, :667-669)
   float lg[ROUNDS][4];
   float mx = -INFINITY;
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
     const int c = r * LPI + sub;
     if (c < NCH) {
-      Io<T>::load_lg4(lg_item + c * 4, prm.scale_weight, lg[r]);
+      IO::load_lg4(lg_item + c * 4, prm.scale_weight, lg[r]);
     } else {
       lg[r][0] = lg[r][1] = lg[r][2] = lg[r][3] = -INFINITY;
     }
@@ -294,7 +360,7 @@ __global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams 
 #pragma unroll
   for (int d = 1; d < LPI; d <<= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
 
-  // ---- gather
+  // ---- phase C: gather
   float acc[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
@@ -305,49 +371,37 @@ __global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams 
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
     if (r * LPI >= NCH) break;  // uniform
-    // ---- owner: index arithmetic for my chunk. Broadcast payload per point: byte offset of the top-left tap with
-    // the "column step usable" flag in bit 0, byte offset of the bottom-left tap, and the tap weights.
+    // owner: per point, the byte offset of the top-left tap (bit 0 = "column step usable"), the byte offset of the
+    // bottom-left tap, and the four tap weights = bilinear weight x softmax numerator x tap validity.
     unsigned otop[4], obot[4];
     float tw[4][NW];
-    bool any_ok = false;
     {
       const int c = r * LPI + sub;
-      const bool have = c < NCH;
-      const int cc = have ? c : 0;
+      const int cc = c < NCH ? c : 0;
       const int H = s_H[cc], W = s_W[cc], start = s_start[cc];
-      float ox[4], oy[4];
-      Io<T>::load_off4(off_item + cc * 8, prm.scale_offset, ox, oy);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int g = k & (G - 1);  // == (point index within level) % G because P % 4 == 0 and G divides 4
-        const PointRec pr = point_record(rp[2 * g], rp[2 * g + 1], ox[k], oy[k], H, W);
-        const bool ok = have && pr.in_range;
-        any_ok |= ok;
-        const int h0 = max(pr.h_low, 0), w0 = max(pr.w_low, 0);
-        const bool t = pr.h_low >= 0, bt = pr.h_low + 1 <= H - 1, lf = pr.w_low >= 0, rt = pr.w_low + 1 <= W - 1;
+        const bool ok = (inr >> (r * 4 + k)) & 1u;
+        const float hf = floorf(him[r][k]), wf = floorf(wim[r][k]);
+        const int h_low = ok ? static_cast<int>(hf) : 0, w_low = ok ? static_cast<int>(wf) : 0;
+        const float lh = __fsub_rn(him[r][k], hf), lw = __fsub_rn(wim[r][k], wf);
+        const int h0 = max(h_low, 0), w0 = max(w_low, 0);
+        const bool t = h_low >= 0, bt = h_low + 1 <= H - 1, lf = w_low >= 0, rt = w_low + 1 <= W - 1;
         const unsigned top = ok ? static_cast<unsigned>(start + h0 * W + w0) * step_b : 0u;
         otop[k] = top | ((ok && lf && rt) ? 1u : 0u);
         obot[k] = top + ((ok && t && bt) ? static_cast<unsigned>(W) * step_b : 0u);
-        const float hh = 1.f - pr.lh, hw = 1.f - pr.lw;
+        const float hh = 1.f - lh, hw = 1.f - lw;
         const float e = lg[r][k];
-        const float w00 = (ok && t && lf) ? hh * hw * e : 0.f;
-        const float w01 = (ok && t && rt) ? hh * pr.lw * e : 0.f;
-        const float w10 = (ok && bt && lf) ? pr.lh * hw * e : 0.f;
-        const float w11 = (ok && bt && rt) ? pr.lh * pr.lw * e : 0.f;
-        if (MODE == 1) {  // fp16 weights for FHFMA, two per register
-          tw[k][0] = __uint_as_float(f2_to_h2(w00, w01));
-          tw[k][1] = __uint_as_float(f2_to_h2(w10, w11));
-        } else {
-          tw[k][0] = w00, tw[k][1] = w01, tw[k][NW - 2] = w10, tw[k][NW - 1] = w11;
-        }
+        IO::pack_w(tw[k], (ok && t && lf) ? hh * hw * e : 0.f, (ok && t && rt) ? hh * lw * e : 0.f,
+                   (ok && bt && lf) ? lh * hw * e : 0.f, (ok && bt && rt) ? lh * lw * e : 0.f);
       }
     }
-    const unsigned vm = __ballot_sync(kFullMask, any_ok);
+    const unsigned vm = __ballot_sync(kFullMask, ((inr >> (r * 4)) & 0xfu) != 0u);
 
 #pragma unroll
     for (int j = 0; j < LPI; ++j) {
-      if (r * LPI + j >= NCH) break;                // uniform
-      if ((vm & (OWNER0 << j)) == 0u) continue;     // uniform: chunk out of range for every item of the warp
+      if (r * LPI + j >= NCH) break;             // uniform
+      if ((vm & (OWNER0 << j)) == 0u) continue;  // uniform: chunk out of range for every item of the warp
       const int src = (lane & ~(LPI - 1)) | j;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -361,24 +415,13 @@ __global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams 
         const unsigned dx = (ot & 1u) ? step_b : 0u;
         const char *p0 = vbase + (ot & ~1u);
         const char *p1 = vbase + ob;
-        const uint4 t00 = ldg128(p0), t01 = ldg128(p0 + dx), t10 = ldg128(p1), t11 = ldg128(p1 + dx);
-        if (MODE == 1) {
-          const uint32_t a = __float_as_uint(w[0]), bb = __float_as_uint(w[1]);
-          Io<T>::template fma_tap<MODE>(acc, t00, __uint_as_float(a & 0xffffu));
-          Io<T>::template fma_tap<MODE>(acc, t01, __uint_as_float(a >> 16));
-          Io<T>::template fma_tap<MODE>(acc, t10, __uint_as_float(bb & 0xffffu));
-          Io<T>::template fma_tap<MODE>(acc, t11, __uint_as_float(bb >> 16));
-        } else {
-          Io<T>::template fma_tap<MODE>(acc, t00, w[0]);
-          Io<T>::template fma_tap<MODE>(acc, t01, w[1]);
-          Io<T>::template fma_tap<MODE>(acc, t10, w[NW - 2]);
-          Io<T>::template fma_tap<MODE>(acc, t11, w[NW - 1]);
-        }
+        const uint4 t[4] = {ldg128(p0), ldg128(p0 + dx), ldg128(p1), ldg128(p1 + dx)};
+        IO::fma_point(acc, t, w);
       }
     }
   }
 
-  if (active) Io<T>::store(static_cast<T *>(prm.out) + it * C + sub * VEC, acc, sum, prm);
+  if (active) IO::store(out_item, acc, 1.f / sum, prm);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -497,7 +540,7 @@ static int validate(const MsdaParams &p) {
 
 template <typename T, typename R, int C, int ROUNDS, int MODE>
 static int launch_gather(const MsdaParams &p, cudaStream_t s) {
-  constexpr int LPI = C / Io<T>::kVec;
+  constexpr int LPI = C / Io<T, 0>::kVec;
   constexpr int IPB = (32 / LPI) * (kThreads / 32);
   const long long blocks = (p.items + IPB - 1) / IPB;
   if (blocks > 0x7fffffffll) return B200_ERR_BAD_PARAM;
@@ -516,7 +559,7 @@ static int launch_generic(const MsdaParams &p, cudaStream_t s) {
 
 template <typename T, typename R, int C, int MODE>
 static int dispatch_rounds(const MsdaParams &p, cudaStream_t s) {
-  constexpr int LPI = C / Io<T>::kVec;
+  constexpr int LPI = C / Io<T, 0>::kVec;
   const int nch = p.L * p.P / 4;
   const int rounds = (nch + LPI - 1) / LPI;
   if (rounds <= 1) return launch_gather<T, R, C, 1, MODE>(p, s);

@@ -7,7 +7,7 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/${TAG}_smi.csv 2>&1
 python -c "import os; print('cpus', os.cpu_count())" >> $OUT/${TAG}_smi.csv
 lscpu | grep -E "Model name|^CPU\(s\)" >> $OUT/${TAG}_smi.csv
-( time python -m pytest tests -m gpu -q -x -s 2>&1 | tail -60 ) > $OUT/${TAG}_pytest.log 2>&1
+( time python -m pytest tests -m gpu -q -s 2>&1 | tail -80 ) > $OUT/${TAG}_pytest.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1
 python bench.py --steps 100 --warmup 10 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 python bench.py --steps 100 --warmup 10 --dist G --no-secondary --no-cpu-baseline > $OUT/${TAG}_bench_G.json 2>> $OUT/${TAG}_bench.err

@@ -36,3 +36,21 @@ def load_golden_msda(path):
         else:
             raise RuntimeError(f"{path}: seeded CPU generator no longer reproduces the golden inputs")
     return cfg, inputs, z["out"]
+
+
+def make_grid_sampler_inputs(N, C, Hi, Wi, Ho, Wo, seed=0, depth=None, span=15.0):
+    """input ~ N(0,1); grid = a regular sweep over [-span, span] (1.5x beyond the image, as the reference test's
+    linspace(-15, 15), test_grid_sampler.py:29-36) plus N(0, 0.5) jitter, channel-first [N, 2|3, ...]."""
+    g = torch.Generator().manual_seed(seed)
+    if depth is None:
+        inp = torch.randn(N, C, Hi, Wi, generator=g)
+        ys, xs = torch.meshgrid(torch.linspace(-span, span, Ho), torch.linspace(-span, span, Wo), indexing="ij")
+        grid = torch.stack([xs, ys], 0)[None].repeat(N, 1, 1, 1)
+    else:
+        Di, Do = depth
+        inp = torch.randn(N, C, Di, Hi, Wi, generator=g)
+        zs, ys, xs = torch.meshgrid(torch.linspace(-span, span, Do), torch.linspace(-span, span, Ho),
+                                    torch.linspace(-span, span, Wo), indexing="ij")  # fmt: skip
+        grid = torch.stack([xs, ys, zs], 0)[None].repeat(N, 1, 1, 1, 1)
+    grid = grid + 0.5 * torch.randn(grid.shape, generator=g)
+    return inp, grid.contiguous()

@@ -1,0 +1,152 @@
+"""GPU parity tests for the grid sampler (pytest -m gpu). Checkers: oracle/grid_sampler_oracle.c (the reference FP32
+kernel restated), golden vectors from the reference Python binding, and oracle/_ref (the reference's CUDA kernels).
+Tolerances: FP32 1e-5; FP16 1e-3 + output rounding slack for |out| > 2 (bicubic overshoots); INT8 2e-2-style bound in
+units of the output scale."""
+import itertools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import bevformer_tensorrt_b200 as bt
+from bevformer_tensorrt_b200.functions.grid_sampler import pack_chw, unpack_chw
+from bevformer_tensorrt_b200.workloads import quantize_per_tensor
+from oracle import REF_LIB
+from oracle import grid_sampler as ogs
+from tests.helpers import GOLDEN, make_grid_sampler_inputs
+
+pytestmark = pytest.mark.gpu
+
+MODES = list(itertools.product(["bilinear", "nearest", "bicubic"], ["zeros", "border", "reflection"], [False, True]))
+IM = {"bilinear": 0, "nearest": 1, "bicubic": 2}
+PM = {"zeros": 0, "border": 1, "reflection": 2}
+
+
+@pytest.mark.parametrize("interp,pad,align", MODES)
+def test_fp32_matches_oracle_all_modes(interp, pad, align):
+    inp, grid = make_grid_sampler_inputs(2, 7, 11, 13, 23, 19, seed=5)
+    want = ogs.grid_sample_2d(inp.numpy(), grid.numpy(), IM[interp], PM[pad], align)
+    for fn in (bt.grid_sampler, bt.grid_sampler2):
+        got = fn(inp.cuda(), grid.cuda(), interp, pad, align).cpu().numpy()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() < 1e-5, (interp, pad, align, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("interp,pad,align", MODES)
+def test_fp32_matches_reference_golden(interp, pad, align):
+    z = np.load(os.path.join(GOLDEN, "grid_sampler_ref.npz"))
+    inp, grid = make_grid_sampler_inputs(2, 6, 11, 13, 17, 19, seed=3)
+    got = bt.grid_sampler(inp.cuda(), grid.cuda(), interp, pad, align).cpu().numpy()
+    d = np.abs(got - z[f"{interp}_{pad}_{int(align)}"])
+    if interp == "nearest":
+        assert (d > 1e-6).mean() < 0.01
+    else:
+        assert d.max() < 3e-5
+
+
+@pytest.mark.parametrize("interp,pad,align", [("bilinear", "zeros", False), ("bilinear", "border", True),
+                                               ("nearest", "reflection", False), ("bicubic", "zeros", False)])  # fmt: skip
+def test_fp16_and_chw2_match_oracle(interp, pad, align):
+    inp, grid = make_grid_sampler_inputs(2, 7, 12, 14, 20, 22, seed=6)
+    inp, grid = inp.half(), grid.half()
+    want = ogs.grid_sample_2d(inp.float().numpy(), grid.float().numpy(), IM[interp], PM[pad], align)
+    tol = 1e-3 + np.abs(want).max() * 2.0**-11  # fp16 output rounding grows with |out| (bicubic overshoot)
+    got = bt.grid_sampler(inp.cuda(), grid.cuda(), interp, pad, align)
+    assert got.dtype == torch.float16
+    assert np.abs(got.float().cpu().numpy() - want).max() < tol
+    # kCHW2 packed layout (…TRT2)
+    g2 = grid.permute(0, 2, 3, 1).unsqueeze(1).contiguous()  # [N,1,Ho,Wo,2] = (x, y)
+    out2 = bt.grid_sampler_chw2(pack_chw(inp, 2).cuda(), g2.cuda(), inp.shape[1], interp, pad, align)
+    got2 = unpack_chw(out2.cpu(), inp.shape[1])
+    assert torch.equal(got2, got.cpu())
+
+
+@pytest.mark.parametrize("interp,pad,align", [("bilinear", "zeros", False), ("nearest", "border", False),
+                                               ("bicubic", "reflection", True)])  # fmt: skip
+def test_int8_chw4_matches_dequant_oracle(interp, pad, align):
+    inp, grid = make_grid_sampler_inputs(2, 10, 12, 14, 20, 22, seed=7, span=12.0)
+    iq, si = quantize_per_tensor(inp)
+    gq, sg = quantize_per_tensor(grid)
+    real = ogs.grid_sample_2d(iq.float().numpy() * si, gq.float().numpy() * sg, IM[interp], PM[pad], align)
+    so = float(np.abs(real).max()) / 127.0
+    g4 = torch.zeros(grid.shape[0], 1, grid.shape[2], grid.shape[3], 4, dtype=torch.int8)
+    g4[:, 0, :, :, 0], g4[:, 0, :, :, 1] = gq[:, 0], gq[:, 1]
+    out4 = bt.grid_sampler_int8(pack_chw(iq, 4).cuda(), si, g4.cuda(), sg, so, inp.shape[1], interp, pad, align)
+    got = unpack_chw(out4.cpu(), inp.shape[1]).float().numpy() * so
+    assert np.abs(got - real).max() <= 0.5 * so + 1e-6  # one requantisation: at most half an output step
+
+
+def test_sampling_indices_bit_exact_via_nearest():
+    """Nearest mode on an index-valued image returns the sampled flat index itself: the device's source-index
+    arithmetic is compared bit-exactly with the oracle's (and thereby the reference kernel's formulas)."""
+    Hi, Wi = 37, 41
+    img = torch.arange(Hi * Wi, dtype=torch.float32).view(1, 1, Hi, Wi) + 1.0
+    _, grid = make_grid_sampler_inputs(1, 1, Hi, Wi, 64, 64, seed=8, span=11.0)
+    for pad, align in itertools.product(["zeros", "border", "reflection"], [False, True]):
+        want = ogs.grid_sample_2d(img.numpy(), grid.numpy(), 1, PM[pad], align)
+        got = bt.grid_sampler(img.cuda(), grid.cuda(), "nearest", pad, align).cpu().numpy()
+        assert np.array_equal(got, want), (pad, align)
+
+
+def test_3d_matches_reference_golden():
+    z = np.load(os.path.join(GOLDEN, "grid_sampler_ref.npz"))
+    inp3, grid3 = make_grid_sampler_inputs(1, 3, 5, 6, 7, 8, seed=4, depth=(4, 5))
+    for interp, pad, align in itertools.product(["bilinear", "nearest"], ["zeros", "border", "reflection"], [False, True]):
+        got = bt.grid_sampler(inp3.cuda(), grid3.cuda(), interp, pad, align).cpu().numpy()
+        d = np.abs(got - z[f"3d_{interp}_{pad}_{int(align)}"])
+        if interp == "nearest":
+            assert (d > 1e-6).mean() < 0.02
+        else:
+            assert d.max() < 3e-5, (interp, pad, align, d.max())
+
+
+def test_base_shape_identity_and_shift_properties():
+    """BEVFormer-base prev-BEV warp shape [1,256,200,200]: an identity grid reproduces the input exactly; a one-pixel
+    shift grid reproduces the shifted input (zeros padding)."""
+    H = W = 200
+    x = torch.randn(1, 256, H, W, device="cuda")
+    xs = (torch.arange(W, device="cuda", dtype=torch.float32) + 0.5) / W * 20 - 10
+    ys = (torch.arange(H, device="cuda", dtype=torch.float32) + 0.5) / H * 20 - 10
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    grid = torch.stack([gx, gy], 0)[None].contiguous()
+    out = bt.grid_sampler(x, grid, "bilinear", "zeros", False)
+    assert (out - x).abs().max().item() < 2e-5
+    grid_s = grid.clone()
+    grid_s[:, 0] += 20.0 / W  # sample one pixel to the right
+    out_s = bt.grid_sampler(x, grid_s, "bilinear", "zeros", False)
+    assert (out_s[..., :-1] - x[..., 1:]).abs().max().item() < 2e-4
+    assert out_s[..., -1].abs().max().item() < 2e-4 + 0.0  # weight of the out-of-image tap ~1 -> zeros padding
+    outh = bt.grid_sampler(x.half(), grid.half(), "bilinear", "zeros", False)
+    assert (outh.float() - x.half().float()).abs().max().item() < 4e-3  # fp16 grid quantisation moves samples
+
+
+needs_ref = pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("interp,pad,align", MODES)
+def test_fp32_matches_reference_kernel(interp, pad, align):
+    import ctypes
+
+    inp, grid = make_grid_sampler_inputs(2, 5, 17, 19, 33, 31, seed=9)
+    inp, grid = inp.cuda(), grid.cuda()
+    lib = ctypes.CDLL(REF_LIB)
+    out = torch.empty(2, 5, 33, 31, device="cuda")
+    dims = lambda t: (ctypes.c_int * 4)(*t.shape)  # noqa: E731
+    lib.ref_grid_sample(0, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(inp.data_ptr()),
+                        ctypes.c_void_p(grid.data_ptr()), dims(out), dims(inp), dims(grid), 4, IM[interp], PM[pad],
+                        int(align), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))  # fmt: skip
+    torch.cuda.synchronize()
+    got = bt.grid_sampler(inp, grid, interp, pad, align)
+    assert (got - out).abs().max().item() < 1e-5, (interp, pad, align)
+
+
+def test_error_behaviour():
+    inp, grid = make_grid_sampler_inputs(1, 2, 4, 4, 5, 5)
+    with pytest.raises(RuntimeError):
+        bt.grid_sampler(inp, grid, "bilinear", "zeros", False)  # CPU tensor
+    with pytest.raises(KeyError):
+        bt.grid_sampler(inp.cuda(), grid.cuda(), "lanczos", "zeros", False)
+    with pytest.raises(ValueError):
+        bt.grid_sampler(inp.cuda(), grid.cuda()[:, :1], "bilinear", "zeros", False)

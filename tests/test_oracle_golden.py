@@ -33,3 +33,40 @@ def test_index_records_are_consistent():
     assert (idx["h_low"][inr] >= -1).all() and (idx["h_low"][inr] <= H - 1).all()
     assert (idx["w_low"][inr] >= -1).all() and (idx["w_low"][inr] <= W - 1).all()
     assert (idx["tap_mask"][~inr] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# grid sampler
+# ---------------------------------------------------------------------------------------------------------------
+import itertools  # noqa: E402
+import os  # noqa: E402
+
+from oracle import grid_sampler as ogs  # noqa: E402
+from tests.helpers import GOLDEN, make_grid_sampler_inputs  # noqa: E402
+
+_GS_MODES = list(itertools.product(["bilinear", "nearest", "bicubic"], ["zeros", "border", "reflection"], [False, True]))
+_IM = {"bilinear": 0, "nearest": 1, "bicubic": 2}
+_PM = {"zeros": 0, "border": 1, "reflection": 2}
+
+
+@pytest.mark.parametrize("interp,pad,align", _GS_MODES)
+def test_grid_sampler_c_oracle_matches_reference_python(interp, pad, align):
+    z = np.load(os.path.join(GOLDEN, "grid_sampler_ref.npz"))
+    inp, grid = make_grid_sampler_inputs(2, 6, 11, 13, 17, 19, seed=3)
+    want = z[f"{interp}_{pad}_{int(align)}"]
+    got = ogs.grid_sample_2d(inp.numpy(), grid.numpy(), _IM[interp], _PM[pad], align)
+    d = np.abs(got - want)
+    if interp == "nearest":
+        # kernel: ::round (half away from zero) on an index un-normalised from [-10,10]; binding: nearbyint on /10 then
+        # [-1,1]. They may pick different pixels exactly at half-way points (reference test delta 0.1, :146-147).
+        assert (d > 1e-6).mean() < 0.01
+    else:
+        assert d.max() < 3e-5, d.max()
+
+
+def test_grid_sampler_torch_port_matches_reference_python():
+    z = np.load(os.path.join(GOLDEN, "grid_sampler_ref.npz"))
+    inp, grid = make_grid_sampler_inputs(2, 6, 11, 13, 17, 19, seed=3)
+    for interp, pad, align in _GS_MODES:
+        got = ogs.grid_sampler_torch_port(inp, grid, _IM[interp], _PM[pad], align).numpy()
+        assert np.array_equal(got, z[f"{interp}_{pad}_{int(align)}"])
