@@ -1,0 +1,158 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/b200_bev_ops.h declares
+(no compute calls without a GPU), argument validation, the registry, workload generators, and that the product package
+never imports oracle/."""
+import ast
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import bevformer_tensorrt_b200 as bt
+from bevformer_tensorrt_b200 import _lib
+from bevformer_tensorrt_b200.workloads import (CONFIGS, bev_reference_points_cam, camera_ring_lidar2img,
+                                               make_msda_inputs, quantize_per_tensor)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200_bev_ops.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b200_bev_ops.h but not exported"
+    # and every symbol the Python binding uses is declared in the header
+    assert set(_lib.SIGNATURES) <= set(syms), set(_lib.SIGNATURES) - set(syms)
+
+
+def test_version_status_and_argument_validation_without_gpu():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.b200_bev_ops_version()
+    assert lib.b200_status_string(0) == b"ok" and lib.b200_status_string(2) == b"bad parameter"
+    # null pointers / bad dims are rejected before any CUDA call
+    assert lib.b200_msda_f32(None, None, None, None, None, 1, 1, 1, 32, 1, 1, 4, 1, None, None) == 2
+    assert lib.b200_msda_i8(None, 1.0, None, None, 0, None, 1.0, None, 1.0, 1, 1, 1, 30, 1, 1, 4, 1, None, 1.0, None) == 1
+    assert lib.b200_msda_i8(None, 1.0, None, None, 0, None, 1.0, None, 1.0, 1, 1, 1, 32, 1, 1, 4, 1, None, 0.0, None) == 2
+    dims = (ctypes.c_int * 4)(1, 1, 1, 1)
+    assert lib.b200_grid_sample_f32(None, None, None, dims, dims, dims, 4, 0, 0, 0, None) == 2
+    assert lib.b200_msda_enqueue(None, None, None, None, None, None, 0) == 2
+    assert lib.b200_msda_supports_format(0, None, 5, 1) == 0
+
+
+def test_supports_format_mirror():
+    lib = _lib.load()
+
+    def desc(shape, t, fmt=0):
+        d = _lib.TensorDesc()
+        d.dims.nbDims = len(shape)
+        for i, s in enumerate(shape):
+            d.dims.d[i] = s
+        d.type, d.format, d.scale = t, fmt, 1.0
+        return d
+
+    def io(vt, rt, ch=32, pts=32):
+        return (_lib.TensorDesc * 6)(desc((6, 100, 8, ch), vt), desc((4, 2), 3), desc((6, 10, 1, 8), rt),
+                                     desc((6, 10, 8, 2 * pts), vt), desc((6, 10, 8, pts), vt), desc((6, 10, 8, ch), vt))
+
+    for pos in range(6):
+        assert lib.b200_msda_supports_format(pos, io(0, 0), 5, 1) == 1
+        assert lib.b200_msda_supports_format(pos, io(1, 1), 5, 1) == 1
+        assert lib.b200_msda_supports_format(pos, io(2, 1), 5, 1) == 1  # int8 value, fp16 ref points
+        assert lib.b200_msda_supports_format(pos, io(2, 0), 5, 1) == 1  # int8 value, fp32 ref points
+    assert lib.b200_msda_supports_format(2, io(1, 0), 5, 1) == 0  # fp16 value needs fp16 ref points
+    assert lib.b200_msda_supports_format(0, io(2, 1, ch=30), 5, 1) == 0  # int8 needs channels % 4 == 0
+    assert lib.b200_msda_supports_format(0, io(2, 1, pts=12), 5, 1) == 0  # 12/4 levels = 3 points: % 4 != 0
+    assert lib.b200_msda_supports_format(1, io(0, 0), 5, 1) == 1 and lib.b200_msda_supports_format(6, io(0, 0), 5, 1) == 0
+
+
+def test_registry_and_names():
+    for name in ("multi_scale_deformable_attn", "multi_scale_deformable_attn2", "grid_sampler", "grid_sampler2"):
+        assert bt.TRT_FUNCTIONS.get(name) is getattr(bt, name)
+    with pytest.raises(KeyError):
+        bt.TRT_FUNCTIONS.register_module(module=bt.grid_sampler)
+    with pytest.raises(TypeError):
+        bt.TRT_FUNCTIONS.register_module(force=1, module=bt.grid_sampler)
+
+    @bt.TRT_FUNCTIONS.register_module(name="_tmp_fn")
+    def f():
+        return 1
+
+    assert "_tmp_fn" in bt.TRT_FUNCTIONS and bt.TRT_FUNCTIONS.get("_tmp_fn") is f
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    cfg = CONFIGS["cpu_plumbing"]
+    ins = make_msda_inputs(cfg, "U", 0)
+    with pytest.raises(AssertionError):
+        bt.multi_scale_deformable_attn(*ins)
+    with pytest.raises(RuntimeError):
+        bt.grid_sampler(torch.zeros(1, 1, 2, 2), torch.zeros(1, 2, 2, 2), "bilinear", "zeros", False)
+
+
+def test_onnx_symbolic_names_are_the_reference_plugin_names():
+    import importlib
+
+    gs = importlib.import_module("bevformer_tensorrt_b200.functions.grid_sampler")
+    m = importlib.import_module("bevformer_tensorrt_b200.functions.multi_scale_deformable_attn")
+
+    class G:
+        def op(self, name, *a, **k):
+            return name, a, k
+
+    assert m._MultiScaleDeformableAttnFunction.symbolic(G(), 1, 2, 3, 4, 5)[0] == "MultiScaleDeformableAttnTRT"
+    assert m._MultiScaleDeformableAttnFunction2.symbolic(G(), 1, 2, 3, 4, 5)[0] == "MultiScaleDeformableAttnTRT2"
+    n, a, k = gs._GridSampler2D.symbolic(G(), 1, 2, 0, 1, True)
+    assert n == "GridSampler2DTRT" and k == {"interpolation_mode_i": 0, "padding_mode_i": 1, "align_corners_i": True}
+    assert gs._GridSampler3D2.symbolic(G(), 1, 2, 0, 0, False)[0] == "GridSampler3DTRT2"
+
+
+def test_workload_generators():
+    cfg = CONFIGS["base_sca"]
+    assert cfg.spatial_size == 30825 and cfg.algorithmic_bytes(2) == 590054432
+    assert cfg.algorithmic_bytes(1, 2) == 296947232
+    assert CONFIGS["tiny_sca"].algorithmic_bytes(2) == 14832000 + 8
+    uv, mask = bev_reference_points_cam((50, 50), camera_ring_lidar2img(6))
+    assert uv.shape == (6, 2500, 4, 2) and mask.shape == (6, 2500, 1)
+    seen = (mask > 0).float().sum(0)
+    assert 0.9 < seen.mean() < 2.1  # about one or two cameras see a BEV pillar
+    assert torch.allclose(mask.sum(0)[seen > 0], torch.ones_like(mask.sum(0)[seen > 0]))
+    a = make_msda_inputs(CONFIGS["tiny_sca"], "G", 5, torch.float16)
+    b = make_msda_inputs(CONFIGS["tiny_sca"], "G", 5, torch.float16)
+    assert all(torch.equal(x, y) for x, y in zip(a, b)) and torch.isfinite(a[2].float()).all()
+    q, s = quantize_per_tensor(torch.tensor([-2.0, 0.5, 1.0]))
+    assert q.tolist() == [-127, 32, 64] and abs(s - 2 / 127) < 1e-9
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "bevformer_tensorrt_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                tree = ast.parse(open(os.path.join(dirpath, f)).read())
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom) and node.module:
+                        names = [node.module]
+                    assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (f, names)
+            if f.endswith((".cu", ".cuh", ".h", ".cpp")):
+                for line in open(os.path.join(dirpath, f)):
+                    if line.lstrip().startswith("#include") or "dlopen" in line:
+                        assert "oracle" not in line, (f, line)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError, match="no CPU/PyTorch fallback"):
+        _lib.load()
