@@ -24,6 +24,8 @@ from .functions import (  # noqa: E402
     grid_sampler2,
     grid_sampler_chw2,
     grid_sampler_int8,
+    modulated_deformable_conv2d,
+    modulated_deformable_conv2d2,
     multi_scale_deformable_attn,
     multi_scale_deformable_attn2,
     multi_scale_deformable_attn_int8,
@@ -35,6 +37,8 @@ __all__ = [
     "grid_sampler2",
     "grid_sampler_chw2",
     "grid_sampler_int8",
+    "modulated_deformable_conv2d",
+    "modulated_deformable_conv2d2",
     "multi_scale_deformable_attn",
     "multi_scale_deformable_attn2",
     "multi_scale_deformable_attn_int8",

@@ -24,6 +24,7 @@ namespace b200 {
 
 constexpr int kMaxLevels = 16;
 constexpr int kThreads = 256;
+constexpr int kMinBlocks = 3;  // registers capped at 85: 24 resident warps per SM
 
 static int g_f16_mode = 0;  // exact by default; 1 = mixed FHFMA (opt-in, see Io<__half, 1>)
 
@@ -244,6 +245,41 @@ __device__ __forceinline__ float ref_to_float<__half>(const __half *p, long long
   return __half2float(__ldg(p + i));
 }
 
+// Reference points of one (batch, query) for the four points of a chunk: point k of a chunk uses group k % G
+// (G in {1,2,4}; P % 4 == 0), so px[k], py[k] are filled once and indexed with compile-time k (no local memory).
+template <typename R>
+__device__ __forceinline__ void load_ref(const R *p, int G, float (&px)[4], float (&py)[4]);
+template <>
+__device__ __forceinline__ void load_ref<__half>(const __half *p, int G, float (&px)[4], float (&py)[4]) {
+  if (G == 4) {
+    const uint4 a = ldg128(p);
+    const float2 f0 = h2_to_f2(a.x), f1 = h2_to_f2(a.y), f2 = h2_to_f2(a.z), f3 = h2_to_f2(a.w);
+    px[0] = f0.x, py[0] = f0.y, px[1] = f1.x, py[1] = f1.y, px[2] = f2.x, py[2] = f2.y, px[3] = f3.x, py[3] = f3.y;
+  } else if (G == 2) {
+    const uint2 a = ldg64(p);
+    const float2 f0 = h2_to_f2(a.x), f1 = h2_to_f2(a.y);
+    px[0] = px[2] = f0.x, py[0] = py[2] = f0.y, px[1] = px[3] = f1.x, py[1] = py[3] = f1.y;
+  } else {
+    const float2 f0 = h2_to_f2(ldg32(p));
+    px[0] = px[1] = px[2] = px[3] = f0.x, py[0] = py[1] = py[2] = py[3] = f0.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_ref<float>(const float *p, int G, float (&px)[4], float (&py)[4]) {
+  if (G == 4) {
+    const uint4 a = ldg128(p), b = ldg128(p + 4);
+    px[0] = __uint_as_float(a.x), py[0] = __uint_as_float(a.y), px[1] = __uint_as_float(a.z), py[1] = __uint_as_float(a.w);
+    px[2] = __uint_as_float(b.x), py[2] = __uint_as_float(b.y), px[3] = __uint_as_float(b.z), py[3] = __uint_as_float(b.w);
+  } else if (G == 2) {
+    const uint4 a = ldg128(p);
+    px[0] = px[2] = __uint_as_float(a.x), py[0] = py[2] = __uint_as_float(a.y);
+    px[1] = px[3] = __uint_as_float(a.z), py[1] = py[3] = __uint_as_float(a.w);
+  } else {
+    const uint2 a = ldg64(p);
+    px[0] = px[1] = px[2] = px[3] = __uint_as_float(a.x), py[0] = py[1] = py[2] = py[3] = __uint_as_float(a.y);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Main kernel. T = storage type of value/offsets/logits/out, R = storage type of reference points.
 // Requirements checked on the host: LPI = C*sizeof(T)/16 in {1,2,4,8,16,32}, P % 4 == 0, G in {1,2,4},
@@ -252,7 +288,7 @@ __device__ __forceinline__ float ref_to_float<__half>(const __half *p, long long
 constexpr int kMaxChunks = 64;
 
 template <typename T, typename R, int C, int ROUNDS, int MODE>
-__global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams prm) {
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 1 ? 2 : kMinBlocks) msda_gather_kernel(const MsdaParams prm) {
   using IO = Io<T, MODE>;
   constexpr int VEC = IO::kVec;
   constexpr int LPI = C / VEC;
@@ -267,30 +303,10 @@ __global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams 
                               : LPI == 16 ? 0x00010001u
                                           : 0x00000001u;
 
-  extern __shared__ float s_ref[];  // [(b,q) of this block][2G]
-  // per chunk of 4 points: the level it samples (all four share it because P % 4 == 0)
-  __shared__ int s_H[kMaxChunks], s_W[kMaxChunks], s_start[kMaxChunks];
-
   const int M = prm.M, Q = prm.Q, P = prm.P, G = prm.G, L = prm.L;
   const int NP = L * P, NCH = NP >> 2, CPL = P >> 2;  // chunks (4 points) in total / per level
-  const long long item0 = static_cast<long long>(blockIdx.x) * IPB;
-  const long long item_last = min(prm.items, item0 + IPB) - 1;
-  const long long bq0 = item0 / M;
-
-  if (threadIdx.x < NCH) {
-    const int l = threadIdx.x / CPL;
-    int st = 0;
-    for (int i = 0; i < l; ++i) st += prm.shapes[2 * i] * prm.shapes[2 * i + 1];
-    s_H[threadIdx.x] = prm.shapes[2 * l];
-    s_W[threadIdx.x] = prm.shapes[2 * l + 1];
-    s_start[threadIdx.x] = st;
-  }
-  {
-    const int n = static_cast<int>(item_last / M - bq0 + 1) * 2 * G;
-    const R *rp = static_cast<const R *>(prm.ref);
-    for (int i = threadIdx.x; i < n; i += kThreads) s_ref[i] = ref_to_float<R>(rp, bq0 * 2 * G + i);
-  }
-  __syncthreads();
+  constexpr int IPB_ = IPB;
+  const long long item0 = static_cast<long long>(blockIdx.x) * IPB_;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % LPI;
@@ -300,10 +316,34 @@ __global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams 
   const long long bq = it / M;
   const int m = static_cast<int>(it - bq * M);
   const int b = static_cast<int>(bq / Q);
-  const float *rp = s_ref + (bq - bq0) * 2 * G;
   const T *off_item = static_cast<const T *>(prm.off) + it * NP * 2;
   const T *lg_item = static_cast<const T *>(prm.logits) + it * NP;
   T *out_item = static_cast<T *>(prm.out) + it * C + sub * VEC;
+
+  // Level table, per warp and without any block barrier: lane l < L holds (H_l, W_l) and the exclusive prefix sum of
+  // H*W (the level's first pixel); consumers fetch their level's entry with shuffles. All global loads of the prologue
+  // (shapes, reference points, offsets) are independent, so a warp pays one memory latency before it can decide whether
+  // anything it owns is visible at all.
+  int lvH = 1, lvW = 1;
+  if (lane < L) {
+    const int2 hw = __ldg(reinterpret_cast<const int2 *>(prm.shapes) + lane);
+    lvH = hw.x, lvW = hw.y;
+  }
+  int lvStart;
+  {
+    const int area = lane < L ? lvH * lvW : 0;
+    int incl = area;
+#pragma unroll
+    for (int d = 1; d < kMaxLevels; d <<= 1) {
+      const int t = __shfl_up_sync(kFullMask, incl, d);
+      if (lane >= d) incl += t;
+    }
+    lvStart = incl - area;
+  }
+  // Reference points of this item's (batch, query): 2G values, the same for every head (and every lane group that
+  // shares the query) — a broadcast load.
+  float rpx[4], rpy[4];
+  load_ref<R>(static_cast<const R *>(prm.ref) + bq * 2 * G, G, rpx, rpy);
 
   // ---- phase A: sampling positions of the points this lane owns (chunk c = r*LPI + sub), the bit-exact part
   float him[ROUNDS][4], wim[ROUNDS][4];
@@ -313,14 +353,14 @@ __global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams 
     const int c = r * LPI + sub;
     const bool have = c < NCH;
     const int cc = have ? c : 0;
-    const int H = s_H[cc], W = s_W[cc];
+    const int lv = cc / CPL;
+    const int H = __shfl_sync(kFullMask, lvH, lv), W = __shfl_sync(kFullMask, lvW, lv);
     float ox[4], oy[4];
     IO::load_off4(off_item + cc * 8, prm.scale_offset, ox, oy);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int g = k & (G - 1);  // == (point index within its level) % G, because P % 4 == 0 and G divides 4
-      wim[r][k] = __fadd_rn(__fmaf_rn(rp[2 * g], static_cast<float>(W), ox[k]), -0.5f);
-      him[r][k] = __fadd_rn(__fmaf_rn(rp[2 * g + 1], static_cast<float>(H), oy[k]), -0.5f);
+      wim[r][k] = __fadd_rn(__fmaf_rn(rpx[k], static_cast<float>(W), ox[k]), -0.5f);
+      him[r][k] = __fadd_rn(__fmaf_rn(rpy[k], static_cast<float>(H), oy[k]), -0.5f);
       const bool ok = have && him[r][k] > -1.f && wim[r][k] > -1.f && him[r][k] < static_cast<float>(H) &&
                       wim[r][k] < static_cast<float>(W);
       inr |= ok ? (1u << (r * 4 + k)) : 0u;
@@ -378,7 +418,9 @@ __global__ void __launch_bounds__(kThreads) msda_gather_kernel(const MsdaParams 
     {
       const int c = r * LPI + sub;
       const int cc = c < NCH ? c : 0;
-      const int H = s_H[cc], W = s_W[cc], start = s_start[cc];
+      const int lv = cc / CPL;
+      const int H = __shfl_sync(kFullMask, lvH, lv), W = __shfl_sync(kFullMask, lvW, lv);
+      const int start = __shfl_sync(kFullMask, lvStart, lv);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const bool ok = (inr >> (r * 4 + k)) & 1u;
@@ -544,8 +586,7 @@ static int launch_gather(const MsdaParams &p, cudaStream_t s) {
   constexpr int IPB = (32 / LPI) * (kThreads / 32);
   const long long blocks = (p.items + IPB - 1) / IPB;
   if (blocks > 0x7fffffffll) return B200_ERR_BAD_PARAM;
-  const size_t smem = static_cast<size_t>(IPB / (p.M < IPB ? p.M : IPB) + 2) * 2 * p.G * sizeof(float);
-  msda_gather_kernel<T, R, C, ROUNDS, MODE><<<static_cast<unsigned>(blocks), kThreads, smem, s>>>(p);
+  msda_gather_kernel<T, R, C, ROUNDS, MODE><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(p);
   return check_launch();
 }
 
@@ -577,7 +618,8 @@ static int dispatch(const MsdaParams &p, cudaStream_t s) {
                        (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p.out) % 16 == 0);
   const bool g_ok = p.G == 1 || p.G == 2 || p.G == 4;
-  if (aligned && p.P % 4 == 0 && g_ok && p.L * p.P / 4 <= kMaxChunks) {
+  const bool ref_aligned = reinterpret_cast<uintptr_t>(p.ref) % 16 == 0 && reinterpret_cast<uintptr_t>(p.shapes) % 8 == 0;
+  if (aligned && ref_aligned && p.P % 4 == 0 && g_ok && p.L * p.P / 4 <= kMaxChunks) {
     // every BEVFormer variant has embed_dims / num_heads = 256 / 8 = 32 channels per head
     if (p.C == 32) return dispatch_rounds<T, R, 32, MODE>(p, s);
   }

@@ -1,0 +1,82 @@
+"""Modulated deformable convolution (DCNv2) — host-side mirror of the reference binding
+det2trt/models/functions/modulated_deformable_conv2d.py (:13-291): ``modulated_deformable_conv2d(input, offset, mask,
+weight, bias=None, stride=1, padding=0, dilation=1, groups=1, deform_groups=1)`` and its twin
+``modulated_deformable_conv2d2`` (plugin …TRT2), same ONNX symbolic attributes, used by DCNv2P
+(det2trt/models/modules/cnn/dcn.py:70-86: ``offset = cat(o1, o2)``, ``mask = sigmoid(mask)``).
+
+The reference's forward calls mmcv's ``modulated_deform_conv_forward`` (:84-104); here it calls the sm_100a path behind
+the C ABI. Inference only."""
+import torch
+from torch.autograd import Function
+from torch.nn.modules.utils import _pair
+
+from .. import _lib
+
+
+def _forward(input, offset, mask, weight, bias, stride, padding, dilation, groups, deform_groups):
+    if not input.is_cuda:
+        raise RuntimeError("modulated_deformable_conv2d: input must be a CUDA tensor (no CPU fallback exists)")
+    if input.dim() != 4 or weight.dim() != 4:
+        raise ValueError("input must be [N,C,H,W] and weight [Co, C/groups, kh, kw]")
+    dt = input.dtype
+    if dt not in (torch.float32, torch.float16):
+        raise _lib.B200OpsError("modulated_deformable_conv2d", 1)
+    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
+    n, c, h, w = input.shape
+    co, cig, kh, kw = weight.shape
+    if cig * groups != c:
+        raise ValueError("weight.shape[1] * groups must equal the input channels")
+    ho = (h + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    wo = (w + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    if tuple(offset.shape) != (n, deform_groups * 2 * kh * kw, ho, wo):
+        raise ValueError(f"offset must be {(n, deform_groups * 2 * kh * kw, ho, wo)}, got {tuple(offset.shape)}")
+    if tuple(mask.shape) != (n, deform_groups * kh * kw, ho, wo):
+        raise ValueError(f"mask must be {(n, deform_groups * kh * kw, ho, wo)}, got {tuple(mask.shape)}")
+    lib = _lib.load()
+    input, offset, mask, weight = (t.to(dt).contiguous() for t in (input, offset, mask, weight))
+    bias_t = bias.to(dt).contiguous() if bias is not None else None
+    ws_bytes = lib.b200_dcn_workspace_size(int(dt == torch.float16), n, c, h, w, kw, kh, sw, sh, pw, ph, dw, dh)
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=input.device)
+    out = torch.empty(n, co, ho, wo, dtype=dt, device=input.device)
+    name = "b200_dcn_f32" if dt == torch.float32 else "b200_dcn_f16"
+    with torch.cuda.device(input.device):
+        st = getattr(lib, name)(input.data_ptr(), weight.data_ptr(), bias_t.data_ptr() if bias_t is not None else None,
+                                offset.data_ptr(), mask.data_ptr(), out.data_ptr(), workspace.data_ptr(), n, c, h, w,
+                                co, kw, kh, sw, sh, pw, ph, dw, dh, groups, deform_groups, min(n, 32), None,
+                                _lib.current_stream_ptr())  # fmt: skip
+    _lib.check(name, st)
+    return out
+
+
+def _make(op_name):
+    class _ModulatedDeformableConv2dFunction(Function):
+        @staticmethod
+        def symbolic(g, input, offset, mask, weight, bias, stride, padding, dilation, groups, deform_groups):
+            inputs = [input, offset, mask, weight] + ([bias] if bias is not None else [])
+            return g.op(op_name, *inputs, stride_i=_pair(stride), padding_i=_pair(padding), dilation_i=_pair(dilation),
+                        groups_i=groups, deform_groups_i=deform_groups)  # fmt: skip
+
+        @staticmethod
+        def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                    deform_groups=1):  # fmt: skip
+            return _forward(input, offset, mask, weight, bias, stride, padding, dilation, groups, deform_groups)
+
+    return _ModulatedDeformableConv2dFunction
+
+
+_ModulatedDeformableConv2dFunction = _make("ModulatedDeformableConv2dTRT")
+_ModulatedDeformableConv2dFunction2 = _make("ModulatedDeformableConv2dTRT2")
+
+
+def modulated_deformable_conv2d(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                                deform_groups=1):
+    """Plugin ModulatedDeformableConv2dTRT (FP32 / FP16). Same contract as the reference wrapper (:208-248)."""
+    return _ModulatedDeformableConv2dFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation,
+                                                    groups, deform_groups)  # fmt: skip
+
+
+def modulated_deformable_conv2d2(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                                 deform_groups=1):
+    """Plugin ModulatedDeformableConv2dTRT2 (FP16 as half2). Same contract as the reference wrapper (:251-291)."""
+    return _ModulatedDeformableConv2dFunction2.apply(input, offset, mask, weight, bias, stride, padding, dilation,
+                                                     groups, deform_groups)  # fmt: skip

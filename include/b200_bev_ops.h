@@ -16,6 +16,7 @@
 #ifndef B200_BEV_OPS_H
 #define B200_BEV_OPS_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -156,6 +157,39 @@ int b200_grid_sample_f16_chw2(void *output, const void *input, const void *grid,
 int b200_grid_sample_i8_chw4(int8_t *output, float scale_o, const int8_t *input, float scale_i, const int8_t *grid,
                              float scale_g, const int *output_dims, const int *input_dims, const int *grid_dims,
                              int nb_dims, int interp, int padding, int align_corners, void *stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Modulated deformable convolution, DCNv2 (plugins ModulatedDeformableConv2dTRT / …TRT2)
+ *
+ *   input  [batch, channels, height, width]
+ *   weight [channels_out, channels/group, kernel_h, kernel_w]     bias [channels_out] or NULL
+ *   offset [batch, deformable_group*2*kernel_h*kernel_w, Ho, Wo]  per tap: dh then dw (mmcv order,
+ *                                                                 modulatedDeformableConv2dKernel.cu:297-301)
+ *   mask   [batch, deformable_group*kernel_h*kernel_w, Ho, Wo]    already sigmoid-ed
+ *   output [batch, channels_out, Ho, Wo],  Ho = (height + 2*pad_h - (dilation_h*(kernel_h-1)+1))/stride_h + 1
+ *   workspace: device scratch of b200_dcn_workspace_size(...) bytes (the plugin's getWorkspaceSize,
+ *              …Conv2dPlugin.cpp:73-115, should return this instead of its single-image column size).
+ *   cublas_handle: a cublasHandle_t (as TensorRT passes through attachToContext, …Conv2dPlugin.cpp:286-290) or NULL
+ *              to use the library's own handle.
+ * Argument order = the reference launcher ModulatedDeformConvForwardCUDAKernel<T> (…Conv2dKernel.h:11-19).
+ * FP16 accumulates the GEMM in FP32 (the reference accumulates in FP16, common/cuda_helper.cu:101-110).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t b200_dcn_workspace_size(int dtype /* 0 f32, 1 f16 */, int batch, int channels, int height, int width,
+                               int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h,
+                               int dilation_w, int dilation_h);
+
+/* replaces ModulatedDeformConvForwardCUDAKernel<float> — …Conv2dKernel.cu:695-760 */
+int b200_dcn_f32(const float *input, const float *weight, const float *bias, const float *offset, const float *mask,
+                 float *output, void *workspace, int batch, int channels, int height, int width, int channels_out,
+                 int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                 int dilation_h, int group, int deformable_group, int im2col_step, void *cublas_handle, void *stream);
+
+/* replaces ModulatedDeformConvForwardCUDAKernel<__half> / <__half2> — …Conv2dKernel.cu:762-895 (kLINEAR tensors) */
+int b200_dcn_f16(const void *input, const void *weight, const void *bias, const void *offset, const void *mask,
+                 void *output, void *workspace, int batch, int channels, int height, int width, int channels_out,
+                 int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                 int dilation_h, int group, int deformable_group, int im2col_step, void *cublas_handle, void *stream);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -54,3 +54,30 @@ def make_grid_sampler_inputs(N, C, Hi, Wi, Ho, Wo, seed=0, depth=None, span=15.0
         grid = torch.stack([xs, ys, zs], 0)[None].repeat(N, 1, 1, 1, 1)
     grid = grid + 0.5 * torch.randn(grid.shape, generator=g)
     return inp, grid.contiguous()
+
+
+DCN_CASES = {
+    # name: (N, Ci, H, W, Co, kh, kw, stride, padding, dilation, groups, deform_groups)
+    "k3_s1_p1_g2_dg2": (2, 16, 13, 17, 12, 3, 3, 1, 1, 1, 2, 2),  # the reference op test's structure, reduced
+    "k3_s2_p1_g1_dg1": (2, 8, 14, 15, 6, 3, 3, 2, 1, 1, 1, 1),
+    "k3_s1_p2_d2_g1_dg4": (1, 16, 12, 12, 8, 3, 3, 1, 2, 2, 1, 4),
+    "k1_s1_p0_g1_dg1": (2, 8, 9, 9, 8, 1, 1, 1, 0, 1, 1, 1),
+    "k3x5_s1_p1_g1_dg1": (1, 4, 11, 13, 4, 3, 5, 1, 1, 1, 1, 1),
+    "backbone_like": (2, 64, 29, 50, 64, 3, 3, 1, 1, 1, 1, 1),  # BEVFormer R101 stage shapes, channels reduced
+}
+
+
+def make_dcn_inputs(case, seed=0, dtype=torch.float32):
+    N, Ci, H, W, Co, kh, kw, s, p, d, g, dg = DCN_CASES[case]
+    gen = torch.Generator().manual_seed(seed)
+    Ho = (H + 2 * p - (d * (kh - 1) + 1)) // s + 1
+    Wo = (W + 2 * p - (d * (kw - 1) + 1)) // s + 1
+    x = torch.randn(N, Ci, H, W, generator=gen)
+    off = torch.randn(N, dg * 2 * kh * kw, Ho, Wo, generator=gen) * 1.5
+    mask = torch.sigmoid(torch.randn(N, dg * kh * kw, Ho, Wo, generator=gen))  # dcn.py:74
+    w = torch.randn(Co, Ci // g, kh, kw, generator=gen) / (Ci // g * kh * kw) ** 0.5
+    b = torch.randn(Co, generator=gen)
+    kwargs = dict(stride=s, padding=p, dilation=d, groups=g, deform_groups=dg)
+    if torch.__version__ and kh != kw:
+        pass
+    return x.to(dtype), off.to(dtype), mask.to(dtype), w.to(dtype), b.to(dtype), kwargs

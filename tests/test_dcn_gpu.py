@@ -1,0 +1,107 @@
+"""GPU parity tests for DCNv2 (pytest -m gpu). Checkers: oracle/dcn (reference im2col restated + fp64-accumulated GEMM),
+torchvision.ops.deform_conv2d on the GPU at larger sizes, and the reference's own CUDA launcher in oracle/_ref.
+Tolerances: FP32 1e-4 relative to max|out| (GEMM summation order); FP16 5e-3 absolute on O(1) outputs (the reference's
+own FP16 bar is mean-abs 0.05, test_modulated_deformable_conv2d.py:100-103)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import bevformer_tensorrt_b200 as bt
+from bevformer_tensorrt_b200 import _lib
+from oracle import REF_LIB
+from oracle import dcn as odcn
+from tests.helpers import DCN_CASES, make_dcn_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _call(fn, x, off, mask, w, b, kw):
+    return fn(x.cuda(), off.cuda(), mask.cuda(), w.cuda(), b.cuda() if b is not None else None, kw["stride"],
+              kw["padding"], kw["dilation"], kw["groups"], kw["deform_groups"])  # fmt: skip
+
+
+@pytest.mark.parametrize("case", list(DCN_CASES))
+def test_fp32_matches_oracle(case):
+    x, off, mask, w, b, kw = make_dcn_inputs(case)
+    want = odcn.modulated_deformable_conv2d(x.numpy(), off.numpy(), mask.numpy(), w.numpy(), b.numpy(), **kw)
+    for fn in (bt.modulated_deformable_conv2d, bt.modulated_deformable_conv2d2):
+        got = _call(fn, x, off, mask, w, b, kw).cpu().numpy()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max()), (case, np.abs(got - want).max())
+    nb = _call(bt.modulated_deformable_conv2d, x, off, mask, w, None, kw).cpu().numpy()  # bias optional (4 inputs)
+    assert np.abs(nb - (want - b.numpy()[None, :, None, None])).max() < 2e-4 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("case", ["k3_s1_p1_g2_dg2", "backbone_like", "k3_s2_p1_g1_dg1"])
+def test_fp16_matches_oracle(case):
+    x, off, mask, w, b, kw = make_dcn_inputs(case, dtype=torch.float16)
+    want = odcn.modulated_deformable_conv2d(*(t.float().numpy() for t in (x, off, mask, w, b)), **kw)
+    got = _call(bt.modulated_deformable_conv2d, x, off, mask, w, b, kw)
+    assert got.dtype == torch.float16
+    err = np.abs(got.float().cpu().numpy() - want).max()
+    assert err < 5e-3 * max(1.0, np.abs(want).max()), (case, err)
+
+
+def test_im2col_indices_bit_exact_through_identity_weights():
+    """With a 1x1 kernel, identity weights and mask 1 the op returns the bilinear sample itself; integer-valued offsets
+    then return exact pixels of an index image, so the device's h_im/w_im/floor arithmetic is compared bit-exactly."""
+    C, H, W = 4, 19, 23
+    img = torch.arange(H * W, dtype=torch.float32).view(1, 1, H, W).repeat(1, C, 1, 1) + 1.0
+    g = torch.Generator().manual_seed(5)
+    off = torch.randint(-6, 7, (1, 2, H, W), generator=g).float()
+    mask = torch.ones(1, 1, H, W)
+    w = torch.eye(C).view(C, C, 1, 1)
+    want = odcn.modulated_deformable_conv2d(img.numpy(), off.numpy(), mask.numpy(), w.numpy(), None)
+    got = bt.modulated_deformable_conv2d(img.cuda(), off.cuda(), mask.cuda(), w.cuda(), None).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_base_backbone_shape_against_torchvision_gpu():
+    """BEVFormer-base R101 stage-3 DCN shape [6,256,58,100] 3x3, FP32, vs torchvision on the same GPU."""
+    import torchvision
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(6, 256, 58, 100, device="cuda", generator=g)
+    off = torch.randn(6, 18, 58, 100, device="cuda", generator=g) * 2
+    mask = torch.sigmoid(torch.randn(6, 9, 58, 100, device="cuda", generator=g))
+    w = torch.randn(256, 256, 3, 3, device="cuda", generator=g) / 48.0
+    b = torch.randn(256, device="cuda", generator=g)
+    want = torchvision.ops.deform_conv2d(x, off, w, b, padding=1, mask=mask)
+    got = bt.modulated_deformable_conv2d(x, off, mask, w, b, 1, 1, 1, 1, 1)
+    assert (got - want).abs().max().item() < 2e-3  # both sides may use TF32-free fp32 GEMMs with different orders
+    goth = bt.modulated_deformable_conv2d(x.half(), off.half(), mask.half(), w.half(), b.half(), 1, 1, 1, 1, 1)
+    assert (goth.float() - want).abs().max().item() < 3e-2
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["k3_s1_p1_g2_dg2", "backbone_like"])
+def test_fp32_matches_reference_launcher(case):
+    x, off, mask, w, b, kw = make_dcn_inputs(case)
+    N, Ci, H, W, Co, kh, kwid, s, p, d, g, dg = DCN_CASES[case]
+    xs = [t.cuda() for t in (x, off, mask, w, b)]
+    Ho, Wo = odcn.out_size(H, W, kh, kwid, s, p, d)
+    out = torch.empty(N, Co, Ho, Wo, device="cuda")
+    ws = torch.empty(Ci * kh * kwid * Ho * Wo + 64, device="cuda")
+    lib = ctypes.CDLL(REF_LIB)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    lib.ref_dcn(0, P(xs[0]), P(xs[3]), P(xs[4]), P(xs[1]), P(xs[2]), P(out), P(ws), N, Ci, H, W, Co, kwid, kh, s, s, p,
+                p, d, d, g, dg, min(N, 32), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = _call(bt.modulated_deformable_conv2d, x, off, mask, w, b, kw)
+    assert (got - out).abs().max().item() < 1e-4 * max(1.0, out.abs().max().item())
+
+
+def test_error_behaviour():
+    x, off, mask, w, b, kw = make_dcn_inputs("k3_s2_p1_g1_dg1")
+    with pytest.raises(RuntimeError):
+        bt.modulated_deformable_conv2d(x, off, mask, w, b, 2, 1, 1, 1, 1)
+    with pytest.raises(ValueError):
+        bt.modulated_deformable_conv2d(x.cuda(), off.cuda()[:, :-1], mask.cuda(), w.cuda(), b.cuda(), 2, 1, 1, 1, 1)
+    lib = _lib.load()
+    # channels not divisible by groups: the reference exit(1)s, here status 1
+    assert lib.b200_dcn_f32(1, 1, None, 1, 1, 1, 1, 1, 6, 4, 4, 4, 3, 3, 1, 1, 1, 1, 1, 1, 4, 1, 1, None, None) == 1
+    assert lib.b200_dcn_f32(None, None, None, None, None, None, None, 1, 4, 4, 4, 4, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                            None, None) == 2

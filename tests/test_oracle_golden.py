@@ -70,3 +70,24 @@ def test_grid_sampler_torch_port_matches_reference_python():
     for interp, pad, align in _GS_MODES:
         got = ogs.grid_sampler_torch_port(inp, grid, _IM[interp], _PM[pad], align).numpy()
         assert np.array_equal(got, z[f"{interp}_{pad}_{int(align)}"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DCNv2: mmcv (the reference binding's forward) is absent, so the oracle is pinned to torchvision's independent
+# implementation of the same definition (same offset channel order: 2*(i*kw+j) = dh, +1 = dw).
+# ---------------------------------------------------------------------------------------------------------------
+from oracle import dcn as odcn  # noqa: E402
+from tests.helpers import make_dcn_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ["k3_s1_p1_g2_dg2", "k3_s2_p1_g1_dg1", "k3_s1_p2_d2_g1_dg4", "k1_s1_p0_g1_dg1",
+                                  "k3x5_s1_p1_g1_dg1"])  # fmt: skip
+def test_dcn_oracle_matches_torchvision(case):
+    import torchvision
+
+    x, off, mask, w, b, kw = make_dcn_inputs(case)
+    want = torchvision.ops.deform_conv2d(x, off, w, b, stride=kw["stride"], padding=kw["padding"],
+                                         dilation=kw["dilation"], mask=mask).numpy()  # fmt: skip
+    got = odcn.modulated_deformable_conv2d(x.numpy(), off.numpy(), mask.numpy(), w.numpy(), b.numpy(), **kw)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max())
