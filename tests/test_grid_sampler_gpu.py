@@ -117,8 +117,12 @@ def test_base_shape_identity_and_shift_properties():
     out_s = bt.grid_sampler(x, grid_s, "bilinear", "zeros", False)
     assert (out_s[..., :-1] - x[..., 1:]).abs().max().item() < 5e-4
     assert out_s[..., -1].abs().max().item() < 5e-4  # weight of the out-of-image tap ~1 -> zeros padding
-    outh = bt.grid_sampler(x.half(), grid.half(), "bilinear", "zeros", False)
-    assert (outh.float() - x.half().float()).abs().max().item() < 4e-3  # fp16 grid quantisation moves samples
+    # FP16 storage: an fp16 grid near +-10 has a resolution of 2^-7 (~0.08 px here), so compare with the oracle on the
+    # fp16-rounded grid instead of with the un-warped image
+    xh, gh = x[:, :8].half(), grid.half()
+    want = ogs.grid_sample_2d(xh.float().cpu().numpy(), gh.float().cpu().numpy(), 0, 0, False)
+    outh = bt.grid_sampler(xh, gh, "bilinear", "zeros", False)
+    assert np.abs(outh.float().cpu().numpy() - want).max() < 1e-3 + np.abs(want).max() * 2.0**-11
 
 
 needs_ref = pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref not built")
