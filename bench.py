@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample-cams", type=int, default=1)
     ap.add_argument("--cpu-repeats", type=int, default=2)
+    ap.add_argument("--chunks", type=int, default=4, help="N>1: query chunks whose all-reduce overlaps the next chunk")
+    ap.add_argument("--unfused", action="store_true", help="N>1: plugin op + torch camera-sum instead of the fused kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other distribution / INT8) legs")
     return ap.parse_args()
@@ -302,7 +304,7 @@ def run_multi(args, cfg, peak, peak_src):
 
     import bevformer_tensorrt_b200 as bt
     from bevformer_tensorrt_b200 import _lib
-    from bevformer_tensorrt_b200.sharding import ShardedSCASampler, plan_units
+    from bevformer_tensorrt_b200.sharding import ShardedSCASampler, plan_chunk_bounds, plan_chunked
     from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img, make_msda_inputs
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -312,8 +314,10 @@ def run_multi(args, cfg, peak, peak_src):
     td = torch.float16 if args.dtype != "f32" else torch.float32
     value, shapes, ref, off, logits = make_msda_inputs(cfg, args.dist, 0, td)
     _, bev_mask = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(cfg.batch))
-    plan = plan_units(cfg.batch, cfg.num_query, world)
-    sampler = ShardedSCASampler(plan[rank], cfg.num_query, bt.multi_scale_deformable_attn).load(
+    plan = plan_chunked(cfg.batch, cfg.num_query, world, args.chunks)
+    sampler = ShardedSCASampler([chunk[rank] for chunk in plan], cfg.num_query, bt.multi_scale_deformable_attn,
+                                fused_sca=None if args.unfused else bt.multi_scale_deformable_attn_sca,
+                                chunk_bounds=plan_chunk_bounds(plan)).load(
         value, shapes, ref, off, logits, bev_mask.to(td), torch.device("cuda", local))
     del value, ref, off, logits
 
@@ -368,8 +372,9 @@ def run_multi(args, cfg, peak, peak_src):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 storage, f32 index math + accumulate" if eb == 2 else "f32", "data": "synthetic",
             "config": {"workload": f"{WORKLOAD}: MSDA 200x200 BEV, 6 cams, 4 levels, 8 heads x 32 ch, 4x8 points, "
-                                   "sharded per (camera, query tile); bev_mask camera-sum; one NCCL all-reduce of the "
-                                   "fp32 BEV accumulator [40000,256]",
+                                   "sharded per (camera, query tile); bev_mask camera-sum fused into the kernel; NCCL "
+                                   f"all-reduce of the fp32 BEV accumulator [40000,256] in {len(plan)} query chunks, each "
+                                   "overlapped with the next chunk's kernels",
                        "distribution": args.dist, "parallelism": f"camera-shard x{world}",
                        "l2": "no flush: per-rank inputs exceed L2 only for N<=4; value stack is L2-resident by design"},
             "gpu_launches": int(launches), "clocks": clk.summary(),

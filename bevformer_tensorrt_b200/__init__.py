@@ -29,6 +29,7 @@ from .functions import (  # noqa: E402
     multi_scale_deformable_attn,
     multi_scale_deformable_attn2,
     multi_scale_deformable_attn_int8,
+    multi_scale_deformable_attn_sca,
 )
 
 __all__ = [
@@ -42,5 +43,6 @@ __all__ = [
     "multi_scale_deformable_attn",
     "multi_scale_deformable_attn2",
     "multi_scale_deformable_attn_int8",
+    "multi_scale_deformable_attn_sca",
 ]
 __version__ = "0.1.0"

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libb200_bev_ops.so")
+# B200_BEV_OPS_LIB lets A/B experiments load an alternative build of the same ABI (scripts/ab_build.sh)
+LIB_PATH = os.environ.get("B200_BEV_OPS_LIB") or os.path.join(_PKG, "lib", "libb200_bev_ops.so")
 
 B200_OK = 0
 STATUS = {0: "ok", 1: "unsupported dtype/format/shape", 2: "bad parameter", 3: "CUDA launch error"}
@@ -43,6 +44,8 @@ SIGNATURES = {
     "b200_msda_f16": (_i, [_vp] * 5 + _MSDA_DIMS + [_vp, _vp]),
     "b200_msda_f16_h2": (_i, [_vp] * 5 + _MSDA_DIMS + [_vp, _vp]),
     "b200_msda_i8": (_i, [_vp, _f, _vp, _vp, _i, _vp, _f, _vp, _f] + _MSDA_DIMS + [_vp, _f, _vp]),
+    "b200_msda_sca_f32": (_i, [_vp] * 6 + _MSDA_DIMS + [_vp, _vp]),
+    "b200_msda_sca_f16": (_i, [_vp] * 6 + _MSDA_DIMS + [_vp, _vp]),
     "b200_msda_debug_indices": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200_msda_set_f16_mode": (_i, [_i]),
     "b200_msda_enqueue": (_i, [ctypes.POINTER(TensorDesc), ctypes.POINTER(TensorDesc), ctypes.POINTER(_vp),

@@ -6,8 +6,8 @@
 //
 // Work decomposition (the reference uses one thread per output scalar, re-reading all logits/offsets per channel):
 //   item            = one (batch, query, head): NP = L*P sampling points, C channels.
-//   lane group      = LPI = C*sizeof(T)/16 lanes own one item; every lane holds 16 bytes of channels, so each
-//                     bilinear tap of an item is ONE 128-bit load per lane and a warp covers 32/LPI items.
+//   lane group      = LPI = C/VEC lanes own one item (VEC = 4 fp32, 8 fp16, 8 int8 channels per lane), so each
+//                     bilinear tap of an item is ONE vector load per lane (128-bit; 64-bit for int8) and a warp covers 32/LPI items.
 //   point ownership = offsets/logits are read exactly once with vector loads: chunk c (4 consecutive points) of an
 //                     item belongs to lane c % LPI of its group. The owner evaluates the index arithmetic once
 //                     (fp32, bit-exact with the reference), folds softmax numerator x bilinear weight x tap validity
@@ -24,7 +24,10 @@ namespace b200 {
 
 constexpr int kMaxLevels = 16;
 constexpr int kThreads = 256;
-constexpr int kMinBlocks = 3;  // registers capped at 85: 24 resident warps per SM
+#ifndef B200_MSDA_MIN_BLOCKS
+#define B200_MSDA_MIN_BLOCKS 3
+#endif
+constexpr int kMinBlocks = B200_MSDA_MIN_BLOCKS;  // 3: registers capped at 85, 24 resident warps per SM
 
 static int g_f16_mode = 0;  // exact by default; 1 = mixed FHFMA (opt-in, see Io<__half, 1>)
 
@@ -38,6 +41,9 @@ struct MsdaParams {
   int B, S, M, C, L, Q, P, G;
   long long items;
   int ref_is_half;  // int8 path: dtype of reference_points
+  // fused spatial-cross-attention epilogue (EPI = 1): accum[q, m*C + c] += bev_mask[b, q] * out[b, q, m, c]
+  const float *mask;
+  float *accum;
   float scale_value, scale_offset, scale_weight, scale_out;
 };
 
@@ -76,7 +82,7 @@ __device__ __forceinline__ int tap_mask_of(const PointRec &r, int H, int W) {
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Per-dtype I/O. Every lane moves 16 bytes of channels per tap: 4 floats, 8 halves or 16 int8.
+// Per-dtype I/O. A lane moves one vector of channels per tap: 4 floats / 8 halves (16 B) or 8 int8 (8 B).
 //   Wt  = number of 32-bit registers that carry the four tap weights of a point from the owner lane:
 //         4 (fp32 weights) or 2 (fp16 pairs, for the FHFMA paths).
 // ---------------------------------------------------------------------------------------------------------------
@@ -96,6 +102,9 @@ struct Io;
 template <int MODE>
 struct Io<float, MODE> {
   static constexpr int kVec = 4, kWt = 4;
+  using Tap = uint4;
+  __device__ static Tap ld(const char *p) { return ldg128(p); }
+  __device__ static void store_zero(float *p) { stg128_stream(p, make_uint4(0u, 0u, 0u, 0u)); }
   __device__ static void load_off4(const float *p, float, float (&ox)[4], float (&oy)[4]) {
     const uint4 a = ldg128_stream(p), b = ldg128_stream(p + 4);
     ox[0] = __uint_as_float(a.x), oy[0] = __uint_as_float(a.y), ox[1] = __uint_as_float(a.z),
@@ -111,7 +120,7 @@ struct Io<float, MODE> {
   __device__ static void pack_w(float (&o)[4], float w00, float w01, float w10, float w11) {
     o[0] = w00, o[1] = w01, o[2] = w10, o[3] = w11;
   }
-  __device__ static void fma_point(float (&acc)[4], const uint4 (&t)[4], const float (&w)[4]) {
+  __device__ static void fma_point(float (&acc)[4], const Tap (&t)[4], const float (&w)[4]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float2 *a2 = reinterpret_cast<float2 *>(acc);
@@ -131,6 +140,9 @@ struct Io<float, MODE> {
 template <int MODE>
 struct Io<__half, MODE> {
   static constexpr int kVec = 8, kWt = MODE == 1 ? 2 : 4;
+  using Tap = uint4;
+  __device__ static Tap ld(const char *p) { return ldg128(p); }
+  __device__ static void store_zero(__half *p) { stg128_stream(p, make_uint4(0u, 0u, 0u, 0u)); }
   __device__ static void load_off4(const __half *p, float, float (&ox)[4], float (&oy)[4]) {
     const uint4 a = ldg128_stream(p);
     const float2 p0 = h2_to_f2(a.x), p1 = h2_to_f2(a.y), p2 = h2_to_f2(a.z), p3 = h2_to_f2(a.w);
@@ -148,7 +160,7 @@ struct Io<__half, MODE> {
       o[0] = w00, o[1] = w01, o[kWt - 2] = w10, o[kWt - 1] = w11;
     }
   }
-  __device__ static void fma_point(float (&acc)[8], const uint4 (&t)[4], const float (&w)[kWt]) {
+  __device__ static void fma_point(float (&acc)[8], const Tap (&t)[4], const float (&w)[kWt]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t u[4] = {t[k].x, t[k].y, t[k].z, t[k].w};
@@ -174,13 +186,19 @@ struct Io<__half, MODE> {
   }
 };
 
-// INT8: taps are dequantised in registers. int8 -> fp16 is exact (|q| <= 128): flip the sign bit, splice each byte
-// under the exponent byte 0x64 (= 1024 + byte as fp16) with PRMT, subtract 1152 with one packed HADD2 per pair. The
-// product with the fp16 tap weight is accumulated in fp32 by FHFMA; the fp16 weight rounding (2^-11 relative) is two
-// orders of magnitude below the INT8 output step. scale_value is applied once, at the requantisation.
+// INT8: 8 channels (8 bytes) per lane, 4 lanes per item like FP16 — same ownership structure, half the tap bytes.
+// Taps are dequantised in registers. int8 -> fp16 is exact (|q| <= 128): flip the sign bit, splice each byte under the
+// exponent byte 0x64 (= 1024 + byte as fp16) with PRMT, subtract 1152 with one packed HADD2 per pair. The product with
+// the fp16 tap weight is accumulated in fp32 by FHFMA; the fp16 weight rounding (2^-11 relative) is two orders of
+// magnitude below the INT8 output step. scale_value is applied once, at the requantisation.
 template <int MODE>
 struct Io<int8_t, MODE> {
-  static constexpr int kVec = 16, kWt = 2;
+  static constexpr int kVec = 8, kWt = 2;
+  using Tap = uint2;
+  __device__ static Tap ld(const char *p) { return ldg64(p); }
+  __device__ static void store_zero(int8_t *p) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(0u), "r"(0u) : "memory");
+  }
   __device__ static float deq(uint32_t word, int byte, float s) {
     return static_cast<float>(static_cast<int8_t>(word >> (8 * byte))) * s;
   }
@@ -197,15 +215,15 @@ struct Io<int8_t, MODE> {
   __device__ static void pack_w(float (&o)[2], float w00, float w01, float w10, float w11) {
     o[0] = __uint_as_float(f2_to_h2(w00, w01)), o[1] = __uint_as_float(f2_to_h2(w10, w11));
   }
-  __device__ static void fma_point(float (&acc)[16], const uint4 (&t)[4], const float (&w)[2]) {
+  __device__ static void fma_point(float (&acc)[8], const Tap (&t)[4], const float (&w)[2]) {
     const __half2 bias = __floats2half2_rn(1152.f, 1152.f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t wp = __float_as_uint(w[k >> 1]);
       const unsigned short wh = static_cast<unsigned short>((k & 1) ? (wp >> 16) : (wp & 0xffffu));
-      const uint32_t u[4] = {t[k].x, t[k].y, t[k].z, t[k].w};
+      const uint32_t u[2] = {t[k].x, t[k].y};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         const uint32_t x = u[i] ^ 0x80808080u;
         uint32_t lo = __byte_perm(x, 0x64646464u, 0x4140), hi = __byte_perm(x, 0x64646464u, 0x4342);
         const __half2 a = __hsub2(*reinterpret_cast<__half2 *>(&lo), bias);
@@ -218,19 +236,19 @@ struct Io<int8_t, MODE> {
       }
     }
   }
-  __device__ static void store(int8_t *p, const float (&acc)[16], float inv_sum, const MsdaParams &prm) {
+  __device__ static void store(int8_t *p, const float (&acc)[8], float inv_sum, const MsdaParams &prm) {
     // real = acc * scale_value / sum ; q = T2int8(real / scale_out)
     const float mul = prm.scale_value * inv_sum / prm.scale_out;
-    uint32_t o[4];
+    uint32_t o[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       uint32_t word = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         word |= (static_cast<uint32_t>(to_int8_sat(acc[4 * i + j] * mul)) & 0xffu) << (8 * j);
       o[i] = word;
     }
-    stg128_stream(p, make_uint4(o[0], o[1], o[2], o[3]));
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(o[0]), "r"(o[1]) : "memory");
   }
 };
 
@@ -287,8 +305,8 @@ __device__ __forceinline__ void load_ref<float>(const float *p, int G, float (&p
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxChunks = 64;
 
-template <typename T, typename R, int C, int ROUNDS, int MODE>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 1 ? 2 : kMinBlocks) msda_gather_kernel(const MsdaParams prm) {
+template <typename T, typename R, int C, int ROUNDS, int MODE, int EPI>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const MsdaParams prm) {
   using IO = Io<T, MODE>;
   constexpr int VEC = IO::kVec;
   constexpr int LPI = C / VEC;
@@ -369,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 1 ? 2 : kMinBlocks) msd
   // Nothing of this warp's items lands inside any image (a camera that does not see these BEV queries): the result
   // is exactly 0 (= 0 / sum), and logits are never read.
   if (__ballot_sync(kFullMask, inr != 0u) == 0u) {
-    if (active) stg128_stream(out_item, make_uint4(0u, 0u, 0u, 0u));
+    if (EPI == 0 && active) IO::store_zero(out_item);  // the fused epilogue adds nothing for invisible items
     return;
   }
 
@@ -457,13 +475,32 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 1 ? 2 : kMinBlocks) msd
         const unsigned dx = (ot & 1u) ? step_b : 0u;
         const char *p0 = vbase + (ot & ~1u);
         const char *p1 = vbase + ob;
-        const uint4 t[4] = {ldg128(p0), ldg128(p0 + dx), ldg128(p1), ldg128(p1 + dx)};
+        const typename IO::Tap t[4] = {IO::ld(p0), IO::ld(p0 + dx), IO::ld(p1), IO::ld(p1 + dx)};
         IO::fma_point(acc, t, w);
       }
     }
   }
 
-  if (active) IO::store(out_item, acc, 1.f / sum, prm);
+  if (EPI == 0) {
+    if (active) IO::store(out_item, acc, 1.f / sum, prm);
+  } else {
+    // Fused SCA epilogue (reference: slots = (queries * bev_mask).sum(0), spatial_cross_attention.py:270): the
+    // per-camera output never goes to memory; visible items add their bev_mask-weighted result into the fp32 BEV
+    // accumulator with vector reductions (at most one add per camera that sees the query).
+    unsigned any = inr;
+#pragma unroll
+    for (int d = 1; d < LPI; d <<= 1) any |= __shfl_xor_sync(kFullMask, any, d);
+    const float mk = __ldg(prm.mask + bq);
+    if (active && any != 0u && mk != 0.f) {
+      const float sc = mk / sum;
+      float *dst = prm.accum + ((bq - static_cast<long long>(b) * Q) * M + m) * C + sub * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + i), "f"(acc[i] * sc),
+                     "f"(acc[i + 1] * sc), "f"(acc[i + 2] * sc), "f"(acc[i + 3] * sc)
+                     : "memory");
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -572,7 +609,8 @@ __global__ void msda_index_kernel(const int32_t *shapes, const T *ref, const T *
 // Host side
 // ---------------------------------------------------------------------------------------------------------------
 static int validate(const MsdaParams &p) {
-  if (!p.value || !p.shapes || !p.ref || !p.off || !p.logits || !p.out) return B200_ERR_BAD_PARAM;
+  if (!p.value || !p.shapes || !p.ref || !p.off || !p.logits || !(p.out || (p.accum && p.mask)))
+    return B200_ERR_BAD_PARAM;
   if (p.B <= 0 || p.S <= 0 || p.M <= 0 || p.C <= 0 || p.L <= 0 || p.Q <= 0 || p.P <= 0 || p.G <= 0)
     return B200_ERR_BAD_PARAM;
   if (p.L > kMaxLevels) return B200_ERR_UNSUPPORTED;
@@ -580,13 +618,13 @@ static int validate(const MsdaParams &p) {
   return B200_OK;
 }
 
-template <typename T, typename R, int C, int ROUNDS, int MODE>
+template <typename T, typename R, int C, int ROUNDS, int MODE, int EPI>
 static int launch_gather(const MsdaParams &p, cudaStream_t s) {
   constexpr int LPI = C / Io<T, 0>::kVec;
   constexpr int IPB = (32 / LPI) * (kThreads / 32);
   const long long blocks = (p.items + IPB - 1) / IPB;
   if (blocks > 0x7fffffffll) return B200_ERR_BAD_PARAM;
-  msda_gather_kernel<T, R, C, ROUNDS, MODE><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(p);
+  msda_gather_kernel<T, R, C, ROUNDS, MODE, EPI><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(p);
   return check_launch();
 }
 
@@ -598,32 +636,33 @@ static int launch_generic(const MsdaParams &p, cudaStream_t s) {
   return check_launch();
 }
 
-template <typename T, typename R, int C, int MODE>
+template <typename T, typename R, int C, int MODE, int EPI>
 static int dispatch_rounds(const MsdaParams &p, cudaStream_t s) {
   constexpr int LPI = C / Io<T, 0>::kVec;
   const int nch = p.L * p.P / 4;
   const int rounds = (nch + LPI - 1) / LPI;
-  if (rounds <= 1) return launch_gather<T, R, C, 1, MODE>(p, s);
-  if (rounds <= 2) return launch_gather<T, R, C, 2, MODE>(p, s);
-  if (rounds <= 4) return launch_gather<T, R, C, 4, MODE>(p, s);
-  return launch_generic<T, R>(p, s);
+  if (rounds <= 1) return launch_gather<T, R, C, 1, MODE, EPI>(p, s);
+  if (rounds <= 2) return launch_gather<T, R, C, 2, MODE, EPI>(p, s);
+  if (EPI == 0 && rounds <= 4) return launch_gather<T, R, C, 4, MODE, 0>(p, s);
+  return EPI == 0 ? launch_generic<T, R>(p, s) : B200_ERR_UNSUPPORTED;
 }
 
-template <typename T, typename R, int MODE>
+template <typename T, typename R, int MODE, int EPI = 0>
 static int dispatch(const MsdaParams &p, cudaStream_t s) {
   const int st = validate(p);
   if (st != B200_OK) return st;
   const bool aligned = (reinterpret_cast<uintptr_t>(p.value) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p.off) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0) &&
-                       (reinterpret_cast<uintptr_t>(p.out) % 16 == 0);
+                       (reinterpret_cast<uintptr_t>(p.out) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p.accum) % 16 == 0);
   const bool g_ok = p.G == 1 || p.G == 2 || p.G == 4;
   const bool ref_aligned = reinterpret_cast<uintptr_t>(p.ref) % 16 == 0 && reinterpret_cast<uintptr_t>(p.shapes) % 8 == 0;
   if (aligned && ref_aligned && p.P % 4 == 0 && g_ok && p.L * p.P / 4 <= kMaxChunks) {
     // every BEVFormer variant has embed_dims / num_heads = 256 / 8 = 32 channels per head
-    if (p.C == 32) return dispatch_rounds<T, R, 32, MODE>(p, s);
+    if (p.C == 32) return dispatch_rounds<T, R, 32, MODE, EPI>(p, s);
   }
-  return launch_generic<T, R>(p, s);
+  return EPI == 0 ? launch_generic<T, R>(p, s) : B200_ERR_UNSUPPORTED;
 }
 
 static MsdaParams make_params(const void *value, const int32_t *shapes, const void *ref, const void *off,
@@ -691,6 +730,28 @@ int b200_msda_i8(const int8_t *value, float scale_value, const int32_t *spatial_
   p.ref_is_half = ref_is_half;
   return ref_is_half ? dispatch<int8_t, __half, 0>(p, static_cast<cudaStream_t>(stream))
                      : dispatch<int8_t, float, 0>(p, static_cast<cudaStream_t>(stream));
+}
+
+int b200_msda_sca_f32(const float *value, const int32_t *spatial_shapes, const float *reference_points,
+                      const float *sampling_offsets, const float *attn_weight, const float *bev_mask, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                      int points_per_group, float *accum, void *stream) {
+  MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, points_per_group,
+                             nullptr);
+  p.mask = bev_mask, p.accum = accum;
+  return dispatch<float, float, 0, 1>(p, static_cast<cudaStream_t>(stream));
+}
+
+int b200_msda_sca_f16(const void *value, const int32_t *spatial_shapes, const void *reference_points,
+                      const void *sampling_offsets, const void *attn_weight, const float *bev_mask, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                      int points_per_group, float *accum, void *stream) {
+  MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, points_per_group,
+                             nullptr);
+  p.mask = bev_mask, p.accum = accum;
+  return dispatch<__half, __half, 0, 1>(p, static_cast<cudaStream_t>(stream));
 }
 
 int b200_msda_debug_indices(int dtype, const int32_t *spatial_shapes, const void *reference_points,

@@ -7,6 +7,7 @@ from .multi_scale_deformable_attn import (
     multi_scale_deformable_attn,
     multi_scale_deformable_attn2,
     multi_scale_deformable_attn_int8,
+    multi_scale_deformable_attn_sca,
 )
 
 TRT_FUNCTIONS.register_module(module=grid_sampler)
@@ -20,3 +21,4 @@ TRT_FUNCTIONS.register_module(module=modulated_deformable_conv2d2)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn2)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_int8)
+TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_sca)

@@ -141,6 +141,38 @@ def multi_scale_deformable_attn_int8(value_q, scale_value, value_spatial_shapes,
     return out
 
 
+def multi_scale_deformable_attn_sca(value, value_spatial_shapes, reference_points, sampling_offsets,
+                                    attention_weights, bev_mask, accum=None):
+    """Fused SpatialCrossAttention sampling: ``accum[q, :] += sum_b bev_mask[b, q] * MSDA(...)[b, q]``
+    — what ``(queries * bev_mask).sum(0)`` computes from the plugin output (spatial_cross_attention.py:264-270) —
+    without ever writing the per-camera output. ``bev_mask``: [bs, nq] or [bs, nq, 1]; ``accum``: float32
+    [nq, heads*channels] (allocated and zeroed when None; accumulated into when given). Returns ``accum``."""
+    assert value.is_cuda
+    dims = _check_inputs(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights)
+    bs, _, num_heads, channels, _, num_query, _, _ = dims
+    dt = value.dtype
+    if dt not in (torch.float32, torch.float16):
+        raise _lib.B200OpsError("multi_scale_deformable_attn_sca", 1)
+    lib = _lib.load()
+    value = value.contiguous()
+    shapes = _shapes_i32(value_spatial_shapes, value.device)
+    ref = reference_points.to(dt).contiguous()
+    off = sampling_offsets.to(dt).contiguous()
+    w = attention_weights.to(dt).contiguous()
+    mask = bev_mask.reshape(bs, num_query).to(torch.float32).contiguous()
+    if accum is None:
+        accum = torch.zeros(num_query, num_heads * channels, dtype=torch.float32, device=value.device)
+    else:
+        if accum.dtype != torch.float32 or not accum.is_contiguous() or accum.numel() != num_query * num_heads * channels:
+            raise ValueError("accum must be a contiguous float32 [num_query, heads*channels] tensor")
+    name = "b200_msda_sca_f32" if dt == torch.float32 else "b200_msda_sca_f16"
+    with torch.cuda.device(value.device):
+        st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
+                                mask.data_ptr(), *dims, accum.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
+    _lib.check(name, st)
+    return accum
+
+
 def msda_sampling_indices(value_spatial_shapes, reference_points, sampling_offsets, num_heads):
     """Diagnostic: int32 [bs, nq, heads, L*P, 4] records {in_range, h_low, w_low, tap_mask} from the device code."""
     assert reference_points.is_cuda and reference_points.dtype in (torch.float32, torch.float16)

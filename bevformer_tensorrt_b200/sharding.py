@@ -38,6 +38,27 @@ def plan_units(num_cams: int, num_query: int, world_size: int, align: int = 8) -
     return per_rank
 
 
+def plan_chunked(num_cams: int, num_query: int, world_size: int, chunks: int, align: int = 8) -> List[List[List[Unit]]]:
+    """Splits the query range into ``chunks`` pieces and plans each piece like ``plan_units``: result[chunk][rank] is
+    that rank's unit list for that query chunk. Every rank has the same amount of work in every chunk, so the
+    all-reduce of chunk k can overlap the kernels of chunk k+1 without stragglers."""
+    chunks = max(1, min(chunks, num_query // align if num_query >= align else 1))
+    edges = [min(num_query, ((num_query * c // chunks + align - 1) // align) * align) for c in range(chunks)] + [num_query]
+    out = []
+    for c in range(chunks):
+        q0, q1 = edges[c], edges[c + 1]
+        if q1 <= q0:
+            continue
+        per_rank = plan_units(num_cams, q1 - q0, world_size, align)
+        out.append([[Unit(u.cam, u.q0 + q0, u.q1 + q0) for u in units] for units in per_rank])
+    return out
+
+
+def plan_chunk_bounds(plan) -> List[tuple]:
+    """(q_lo, q_hi) of every chunk of a ``plan_chunked`` result, over all ranks."""
+    return [(min(u.q0 for units in chunk for u in units), max(u.q1 for units in chunk for u in units)) for chunk in plan]
+
+
 def merge_units(units: Sequence[Unit]) -> List[Unit]:
     """Coalesces adjacent query tiles of the same camera (fewer, larger kernel launches)."""
     out: List[Unit] = []
@@ -63,44 +84,75 @@ def group_cameras(units: Sequence[Unit]):
 class ShardedSCASampler:
     """Holds one rank's slice of the SCA sampling inputs and produces the all-reduced BEV accumulator.
 
-    ``msda`` is the operator to run per unit (the product passes ``multi_scale_deformable_attn``; the CPU tests pass a
-    checker so the host-side plumbing — planning, slicing, masking, the collective — is covered without a GPU).
+    ``units`` is either one unit list (single collective at the end) or a list of per-chunk unit lists from
+    ``plan_chunked`` (the all-reduce of query chunk k is issued asynchronously right after chunk k's kernels and runs
+    on the communication stream while chunk k+1 computes). ``msda`` is the operator to run per launch group (the
+    product passes ``multi_scale_deformable_attn``; the CPU tests pass a checker so the host-side plumbing — planning,
+    slicing, masking, the collective — is covered without a GPU). ``fused_sca`` (optional,
+    ``multi_scale_deformable_attn_sca``) folds MSDA + bev_mask camera-sum into one kernel writing the accumulator.
     """
 
-    def __init__(self, units: Sequence[Unit], num_query: int, msda: Callable, group=None,
-                 accum_dtype: torch.dtype = torch.float32):  # fmt: skip
-        self.units = merge_units(units)
+    def __init__(self, units, num_query: int, msda: Callable, group=None, accum_dtype: torch.dtype = torch.float32,
+                 fused_sca: Callable = None, chunk_bounds=None):  # fmt: skip
+        chunked = len(units) > 0 and isinstance(units[0], (list, tuple))
+        self.chunk_units = [merge_units(u) for u in units] if chunked else [merge_units(units)]
         self.num_query = num_query
         self.msda = msda
         self.group = group
         self.accum_dtype = accum_dtype
-        self.local = []  # per launch group: (value[c,S,M,C], ref[c,q,1,2G], off[c,q,M,*], logits[c,q,M,*], mask[c,q,1])
-        self.groups = []
+        self.fused_sca = fused_sca if accum_dtype == torch.float32 else None
+        # the accumulator slice every rank reduces for chunk k — must be identical on all ranks (plan_chunk_bounds)
+        self.chunk_bounds = list(chunk_bounds) if chunk_bounds is not None else None
+        if chunked and self.chunk_bounds is None:
+            raise ValueError("chunked unit lists need chunk_bounds (use plan_chunk_bounds on the full plan)")
+        self.chunks = []  # per chunk: (q_lo, q_hi, [(cam0, cam1, q0, q1)], [(value, ref, off, logits, mask)])
         self.shapes = None
         self.accum = None
 
     def load(self, value, shapes, ref, off, logits, bev_mask, device):
         """Copies this rank's units out of full-size host tensors (a real model produces them in place)."""
         self.shapes = shapes.to(device)
-        self.local = []
-        self.groups = group_cameras(self.units)  # (cam0, cam1, q0, q1): consecutive cameras sharing a query range
-        for c0, c1, q0, q1 in self.groups:
-            sl = slice(q0, q1)
-            self.local.append(tuple(t.to(device).contiguous() for t in (
-                value[c0:c1], ref[c0:c1, sl], off[c0:c1, sl], logits[c0:c1, sl], bev_mask[c0:c1, sl])))  # fmt: skip
+        self.chunks = []
+        cams = {}
+        for units in self.chunk_units:
+            groups = group_cameras(units)  # (cam0, cam1, q0, q1): consecutive cameras sharing a query range
+            local = []
+            for c0, c1, q0, q1 in groups:
+                sl = slice(q0, q1)
+                if (c0, c1) not in cams:  # one device copy of a camera's value stack, shared by its query tiles
+                    cams[(c0, c1)] = value[c0:c1].to(device).contiguous()
+                local.append((cams[(c0, c1)],) + tuple(
+                    t.to(device).contiguous() for t in (ref[c0:c1, sl], off[c0:c1, sl], logits[c0:c1, sl],
+                                                        bev_mask[c0:c1, sl])))  # fmt: skip
+            lo, hi = self.chunk_bounds[len(self.chunks)] if self.chunk_bounds is not None else (0, self.num_query)
+            self.chunks.append((lo, hi, groups, local))
         M, C = value.shape[2], value.shape[3]
         self.accum = torch.zeros(self.num_query, M * C, dtype=self.accum_dtype, device=device)
         return self
 
-    def step(self, reduce: bool = True):
-        """One SCA sampling step on this rank: kernels for the local units, masked camera-sum, one all-reduce."""
-        import torch.distributed as dist
-
-        self.accum.zero_()
-        for (c0, c1, q0, q1), (v, r, o, w, mask) in zip(self.groups, self.local):
+    def _compute(self, groups, local):
+        for (c0, c1, q0, q1), (v, r, o, w, mask) in zip(groups, local):
+            if self.fused_sca is not None:
+                self.fused_sca(v, self.shapes, r, o, w, mask, self.accum[q0:q1])
+                continue
             out = self.msda(v, self.shapes, r, o, w)  # [cams, q, M, C]
             weighted = out.reshape(c1 - c0, q1 - q0, -1).to(self.accum_dtype) * mask.to(self.accum_dtype)
             self.accum[q0:q1] += weighted.sum(0)
-        if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.accum, op=dist.ReduceOp.SUM, group=self.group)
+
+    def step(self, reduce: bool = True):
+        """One SCA sampling step on this rank: kernels for the local units, masked camera-sum, all-reduce (one
+        collective, or one per query chunk overlapped with the next chunk's kernels)."""
+        import torch.distributed as dist
+
+        do_reduce = reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        self.accum.zero_()
+        works = []
+        for lo, hi, groups, local in self.chunks:
+            self._compute(groups, local)
+            if do_reduce and hi > lo:
+                works.append(dist.all_reduce(self.accum[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                                             async_op=len(self.chunks) > 1))  # fmt: skip
+        for w in works:
+            if w is not None:
+                w.wait()
         return self.accum

@@ -83,6 +83,22 @@ int b200_msda_i8(const int8_t *value, float scale_value, const int32_t *spatial_
                  float scale_weight, int batch, int spatial_size, int num_heads, int channels, int num_levels,
                  int num_query, int num_point, int points_per_group, int8_t *out, float scale_out, void *stream);
 
+/* Fused spatial-cross-attention sampling (beyond the reference's plugin set): MSDA followed by the
+ * bev_mask-weighted sum over cameras that SpatialCrossAttention applies to the plugin output
+ * (det2trt/models/modules/spatial_cross_attention.py:270 — slots = (queries * bev_mask).sum(0)):
+ *     accum[q, m*channels + c] += bev_mask[b, q] * MSDA(value, …)[b, q, m, c]        (fp32 accumulator, += semantics)
+ * The per-camera output [batch, num_query, heads, channels] is never written; cameras that do not see a query add
+ * nothing. bev_mask: float [batch, num_query]; accum: float [num_query, num_heads*channels], zeroed by the caller.
+ * Needs channels == 32, num_point % 4 == 0, points_per_group in {1,2,4} (returns B200_ERR_UNSUPPORTED otherwise). */
+int b200_msda_sca_f32(const float *value, const int32_t *spatial_shapes, const float *reference_points,
+                      const float *sampling_offsets, const float *attn_weight, const float *bev_mask, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                      int points_per_group, float *accum, void *stream);
+int b200_msda_sca_f16(const void *value, const int32_t *spatial_shapes, const void *reference_points,
+                      const void *sampling_offsets, const void *attn_weight, const float *bev_mask, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                      int points_per_group, float *accum, void *stream);
+
 /* Test/diagnostic entry: writes, for every (batch, query, head, level*point), the sampling-index record
  * {in_range, h_low, w_low, tap_mask} (4 x int32) computed by the same device code as the kernels above.
  * dtype: 0 = float inputs, 1 = __half inputs. Used by the bit-exact index parity tests. */

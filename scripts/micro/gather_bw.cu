@@ -33,12 +33,13 @@ __global__ void __launch_bounds__(256) gather(const uint4* __restrict__ buf, uin
     uint4 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      seed = hash32(seed + u);
-      uint32_t tap;
-      if (MODE == 0) tap = seed % taps_in_buf;
-      else if (MODE == 1) tap = seed % s_taps;
-      else if (MODE == 2) tap = ((seed % (s_taps / 2)) * 2) | (grp & 1);  // even groups -> even taps, odd -> odd: no conflicts
-      else { uint32_t pair = __shfl_sync(0xffffffffu, seed, lane & ~7); tap = ((pair % (taps_in_buf / 2)) * 2) | (grp & 1); }
+      seed = seed * 1664525u + 1013904223u;  // LCG: 1 IMAD; use the high bits
+      const uint32_t rnd = seed >> 8;
+      uint32_t tap;  // all sizes are powers of two: masks, no modulo
+      if (MODE == 0) tap = rnd & (taps_in_buf - 1);
+      else if (MODE == 1) tap = rnd & (s_taps - 1);
+      else if (MODE == 2) tap = ((rnd & (s_taps / 2 - 1)) * 2) | (grp & 1);  // even groups -> even taps, odd -> odd: no conflicts
+      else { uint32_t pair = __shfl_sync(0xffffffffu, rnd, lane & ~7); tap = ((pair & (taps_in_buf / 2 - 1)) * 2) | (grp & 1); }
       if (MODE == 1 || MODE == 2) v[u] = smem[tap * 4 + sub];
       else v[u] = __ldg(buf + (size_t)tap * 4 + sub);
     }
@@ -70,19 +71,20 @@ void run(const char* name, const uint4* buf, size_t bytes, size_t smem_bytes, ui
 }
 
 int main() {
-  const size_t big = 96ull << 20;
-  uint4* buf; cudaMalloc(&buf, big); cudaMemset(buf, 1, big);
+  const size_t big = 64ull << 20;
+  uint4* buf; cudaMalloc(&buf, 128ull << 20); cudaMemset(buf, 1, big);
   uint4* out; cudaMalloc(&out, 148 * 8 * 256 * sizeof(uint4));
   for (int bps : {2, 4, 8}) {
     printf("-- %d blocks of 256 threads per SM\n", bps);
-    run<0>("LDG.128 random 64B taps, 96 MB (L2)", buf, big, 0, out, bps);
+    run<0>("LDG.128 random 64B taps, 64 MB (L2)", buf, big, 0, out, bps);
+    run<0>("LDG.128 random 64B taps, 128 MB (L2+HBM)", buf, 128ull << 20, 0, out, bps);
     run<0>("LDG.128 random 64B taps, 16 MB (L2)", buf, 16 << 20, 0, out, bps);
     run<0>("LDG.128 random 64B taps, 64 KB (L1)", buf, 64 << 10, 0, out, bps);
-    run<3>("LDG.128 tap pairs sharing a 128B line, 96 MB", buf, big, 0, out, bps);
+    run<3>("LDG.128 tap pairs sharing a 128B line, 64 MB", buf, big, 0, out, bps);
     run<3>("LDG.128 tap pairs sharing a 128B line, 64 KB", buf, 64 << 10, 0, out, bps);
-    if (bps * 48 * 1024 <= 220 * 1024) {
-      run<1>("LDS.128 random 64B taps (48 KB smem)", buf, big, 48 << 10, out, bps);
-      run<2>("LDS.128 conflict-free 64B taps (48 KB smem)", buf, big, 48 << 10, out, bps);
+    if (bps * 32 * 1024 <= 220 * 1024) {
+      run<1>("LDS.128 random 64B taps (32 KB smem)", buf, big, 32 << 10, out, bps);
+      run<2>("LDS.128 conflict-free 64B taps (32 KB smem)", buf, big, 32 << 10, out, bps);
     }
   }
   return 0;

@@ -315,3 +315,42 @@ def test_noncontiguous_and_int64_shapes():
     v_nc = value.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
     got = bt.multi_scale_deformable_attn(v_nc, shapes.long(), ref, off, logits)
     assert torch.equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused SCA sampling (MSDA + bev_mask camera-sum), SURVEY §8(f)-1
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 1e-3)])
+@pytest.mark.parametrize("name,dist", [("tiny_sca", "G"), ("small_sca", "edge")])
+def test_fused_sca_matches_masked_camera_sum_of_oracle(name, dist, dtype, tol):
+    from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img
+
+    cfg = _cfg(name)
+    inputs = make_msda_inputs(cfg, dist, 101, dtype)
+    if cfg.bev_hw[0] * cfg.bev_hw[1] == cfg.num_query:
+        _, mask = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(cfg.batch))
+    else:
+        mask = (torch.rand(cfg.batch, cfg.num_query, 1, generator=torch.Generator().manual_seed(3)) > 0.4).float()
+    per_cam = torch.from_numpy(_oracle_f32(inputs))  # [B,Q,M,C]
+    want = (per_cam.reshape(cfg.batch, cfg.num_query, -1) * mask).sum(0)  # spatial_cross_attention.py:270
+    got = bt.multi_scale_deformable_attn_sca(*_cuda(inputs), mask.cuda())
+    assert got.dtype == torch.float32 and got.shape == want.shape
+    assert (got.cpu() - want).abs().max().item() < tol
+    # += semantics on a caller-provided accumulator
+    acc = torch.ones_like(got)
+    bt.multi_scale_deformable_attn_sca(*_cuda(inputs), mask.cuda(), acc)
+    assert (acc - 1.0 - got).abs().max().item() < 1e-6
+
+
+def test_fused_sca_base_shapes_vs_plugin_op():
+    from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img
+
+    cfg = CONFIGS["base_sca"]
+    ins = _cuda(make_msda_inputs(cfg, "G", 7, torch.float16))
+    _, mask = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(6))
+    mask = mask.cuda()
+    fin = [t.float() if t.is_floating_point() else t for t in ins]
+    want = (bt.multi_scale_deformable_attn(*fin).reshape(6, cfg.num_query, -1) * mask).sum(0)
+    got = bt.multi_scale_deformable_attn_sca(*ins, mask)
+    assert (got - want).abs().max().item() < 1e-3
+    assert got.abs().max().item() > 0.1

@@ -10,7 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from bevformer_tensorrt_b200.sharding import ShardedSCASampler, group_cameras, plan_units
+from bevformer_tensorrt_b200.sharding import (ShardedSCASampler, group_cameras, plan_chunk_bounds, plan_chunked,
+                                              plan_units)
 from bevformer_tensorrt_b200.workloads import MSDAConfig, bev_reference_points_cam, camera_ring_lidar2img, make_msda_inputs
 
 CFG = MSDAConfig("shard_case", 6, 20 * 20, 8, 32, ((12, 20), (6, 10)), 8, 4, (20, 20))
@@ -27,6 +28,22 @@ def test_plan_covers_every_camera_query_pair_once_and_is_balanced(world):
     loads = [sum(u.q1 - u.q0 for u in units) for units in plan]
     assert max(loads) - min(loads) <= 8 * 6
     assert sum(len(group_cameras(u)) for u in plan) <= 2 * world + 6
+
+
+@pytest.mark.parametrize("world,chunks", [(2, 4), (4, 4), (8, 4), (8, 1)])
+def test_chunked_plan_is_balanced_per_chunk(world, chunks):
+    plan = plan_chunked(6, 40000, world, chunks)
+    cover = np.zeros((6, 40000), np.int32)
+    for chunk in plan:
+        loads = [sum(u.q1 - u.q0 for u in units) for units in chunk]
+        assert max(loads) - min(loads) <= 8 * 6
+        for units in chunk:
+            for u in units:
+                cover[u.cam, u.q0 : u.q1] += 1
+    assert (cover == 1).all()
+    bounds = plan_chunk_bounds(plan)
+    assert bounds[0][0] == 0 and bounds[-1][1] == 40000
+    assert all(bounds[i][1] == bounds[i + 1][0] for i in range(len(bounds) - 1))
 
 
 def test_plan_rejects_nonsense():
@@ -56,7 +73,13 @@ def _worker(rank, world, port, q):
     plan = plan_units(6, CFG.num_query, world)
     s = ShardedSCASampler(plan[rank], CFG.num_query, _oracle_op).load(value, shapes, ref, off, logits, mask, "cpu")
     got = s.step()
-    q.put((rank, float((got - want).abs().max()), float(want.abs().max())))
+    err = float((got - want).abs().max())
+    # chunked plan: one (async) all-reduce per query chunk, overlapped with the next chunk's work
+    cplan = plan_chunked(6, CFG.num_query, world, 3)
+    s2 = ShardedSCASampler([c[rank] for c in cplan], CFG.num_query, _oracle_op,
+                           chunk_bounds=plan_chunk_bounds(cplan)).load(value, shapes, ref, off, logits, mask, "cpu")
+    err = max(err, float((s2.step() - want).abs().max()))
+    q.put((rank, err, float(want.abs().max())))
     dist.destroy_process_group()
 
 
