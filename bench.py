@@ -47,11 +47,19 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample-cams", type=int, default=1)
     ap.add_argument("--cpu-repeats", type=int, default=2)
-    ap.add_argument("--chunks", type=int, default=4, help="N>1: query chunks whose all-reduce overlaps the next chunk")
+    ap.add_argument("--chunks", type=int, default=1, help="N>1: query chunks whose all-reduce overlaps the next chunk")
     ap.add_argument("--unfused", action="store_true", help="N>1: plugin op + torch camera-sum instead of the fused kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other distribution / INT8) legs")
     return ap.parse_args()
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch measured by ncu for this kernel/config (profiles/ncu_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key)
+    except Exception:
+        return None
 
 
 def hbm_peak():
@@ -260,7 +268,8 @@ def run_single(args, cfg, peak, peak_src):
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "msda_gather_kernel", "kernel_ms": k_ms, "kernel_ms_min": per[0],
+                     "traffic": ncu_traffic(f"{args.dtype}_{args.dist}"), "kernel": "msda_gather_kernel",
+                     "kernel_ms": k_ms, "kernel_ms_min": per[0],
                      "algorithmic_bytes": alg, "peak_source": peak_src},
         "wall_s": wall,
     }  # fmt: skip
@@ -432,6 +441,26 @@ def main():
                         "roofline_frac": alg / (k * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg}
             del f2, _d, h
             torch.cuda.empty_cache()
+        # fused SCA sampling (MSDA + bev_mask camera-sum into the fp32 BEV accumulator): what the
+        # sharded N>1 path runs per rank, timed here on one GPU for reference (includes zeroing the accumulator)
+        import bevformer_tensorrt_b200 as bt
+        from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img, make_msda_inputs
+
+        _, bm = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(cfg.batch))
+        bm = bm.cuda()
+        for dist_name in ("U", "G"):
+            h = [t.cuda() for t in make_msda_inputs(cfg, dist_name, 0, torch.float16)]
+            acc = torch.zeros(cfg.num_query, cfg.num_heads * cfg.channels, device="cuda")
+
+            def fused():
+                acc.zero_()
+                bt.multi_scale_deformable_attn_sca(*h, bm, acc)
+
+            _, per = time_kernel(fused, 30, 5)
+            k = sum(per) / len(per)
+            sec[f"f16_{dist_name}_fused_sca"] = {"kernel_ms": k, "bev_queries_per_s": cfg.num_query / (k * 1e-3),
+                                                 "note": "zero 41 MB accumulator + fused kernel; no per-camera output"}
+            del h
         out["secondary"] = sec
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(cfg, args.dist, args.cpu_sample_cams, args.cpu_repeats)
