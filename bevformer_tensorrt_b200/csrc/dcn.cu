@@ -16,11 +16,29 @@
 //  — v1 exists to have a correct, measured DCN behind the final ABI first.
 #include <cublas_v2.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
 
 namespace b200 {
+
+// dcn_fused.cu
+size_t dcn_fused_workspace_bytes(int batch, int channels, int height, int width, int channels_out, int kk);
+bool dcn_fused_supported(int channels, int channels_out, int kk, int group, int deformable_group);
+int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias, const __half *offset,
+                  const __half *mask, __half *output, void *workspace, int batch, int channels, int height, int width,
+                  int channels_out, int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h,
+                  int dilation_w, int dilation_h, int Ho, int Wo, cudaStream_t stream);
+
+static int g_dcn_fused = -1;  // -1: read B200_DCN_FUSED once (default on)
+static bool dcn_fused_enabled() {
+  if (g_dcn_fused < 0) {
+    const char *e = getenv("B200_DCN_FUSED");
+    g_dcn_fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_dcn_fused == 1;
+}
 
 struct DcnParams {
   const void *im, *offset, *mask;
@@ -147,6 +165,14 @@ static int dcn_forward(const T *input, const T *weight, const T *bias, const T *
   const int kk = kernel_h * kernel_w;
   if (static_cast<long long>(channels) * kk * HoWo >= (1ll << 31)) return B200_ERR_BAD_PARAM;
 
+  if (sizeof(T) == 2 && dcn_fused_enabled() && dcn_fused_supported(channels, channels_out, kk, group, deformable_group) &&
+      reinterpret_cast<uintptr_t>(workspace) % 256 == 0)
+    return dcn_fused_f16(reinterpret_cast<const __half *>(input), reinterpret_cast<const __half *>(weight),
+                         reinterpret_cast<const __half *>(bias), reinterpret_cast<const __half *>(offset),
+                         reinterpret_cast<const __half *>(mask), reinterpret_cast<__half *>(output), workspace, batch,
+                         channels, height, width, channels_out, kernel_w, kernel_h, stride_w, stride_h, pad_w, pad_h,
+                         dilation_w, dilation_h, Ho, Wo, stream);
+
   DcnParams p{};
   p.im = input, p.offset = offset, p.mask = mask, p.col = workspace;
   p.B = batch, p.C = channels, p.H = height, p.W = width, p.kh = kernel_h, p.kw = kernel_w;
@@ -208,7 +234,17 @@ size_t b200_dcn_workspace_size(int dtype, int batch, int channels, int height, i
   const int Ho = (height + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
   const int Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
   if (Ho <= 0 || Wo <= 0 || batch <= 0 || channels <= 0) return 0;
-  return col_bytes(batch, channels, kernel_h, kernel_w, Ho, Wo, dtype == 0 ? 4 : 2);
+  const size_t v1 = col_bytes(batch, channels, kernel_h, kernel_w, Ho, Wo, dtype == 0 ? 4 : 2);
+  // the fused FP16 path needs the NHWC copy of the input + the permuted weights instead (channels_out is not an
+  // argument here; 512 is the largest the fused path takes)
+  const size_t fused = dtype == 0 ? 0 : dcn_fused_workspace_bytes(batch, channels, height, width, 512, kernel_h * kernel_w);
+  return v1 > fused ? v1 : fused;
+}
+
+int b200_dcn_set_fused(int enabled) {
+  const int prev = dcn_fused_enabled() ? 1 : 0;
+  g_dcn_fused = enabled ? 1 : 0;
+  return prev;
 }
 
 int b200_dcn_f32(const float *input, const float *weight, const float *bias, const float *offset, const float *mask,

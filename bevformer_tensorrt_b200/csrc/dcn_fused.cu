@@ -1,0 +1,401 @@
+// dcn_fused.cu — DCNv2 as ONE fused implicit GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), FP16.
+//
+// out[b, co, p] = bias[co] + sum_{t, c} W[co, c, t] * mask[b,t,p] * bilinear(x[b, c], p, t)     (reference:
+// modulatedDeformableConv2dKernel.cu:259-318 im2col + :735-759 cuBLAS GEMM + bias kernel, with a 26.7 MB column buffer
+// per image in between). Here the column tile never exists in global memory:
+//
+//   GEMM view   D[M = Co, N = 128 output pixels of one image] += A[M, K] * B[N, K]^T,  K = kh*kw*C ordered (tap, channel)
+//   A (weights) : pre-permuted once per call to [Co][tap][C] (K-major rows); producers copy the k-block slice into
+//                 shared memory in the canonical K-major SWIZZLE_128B layout (128-byte rows, 16-byte chunks XOR row&7).
+//   B (columns) : GATHERED by the producer warps straight into the same canonical layout: the input is first brought to
+//                 NHWC so that the 64 channels of a k-block are 128 contiguous bytes per bilinear corner; a thread
+//                 does 4 x LDG.128, blends 8 channels in fp32 with the (mask-folded) corner weights, packs to fp16 and
+//                 issues one swizzled STS.128. Sampling positions / corner weights of the tile's 128 pixels x kh*kw taps
+//                 are computed once per tile into a shared-memory table (fp32, op-for-op the reference's index math).
+//   MMA         : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 x N128 x K16, fp32 accumulate in
+//                 TMEM), Co/128 accumulators of 128 TMEM columns each; smem stages are released with tcgen05.commit on
+//                 mbarriers; producers signal filled stages after fence.proxy.async.
+//   epilogue    : the producer warps read their TMEM lane quadrant with tcgen05.ld.32x32b.x32 (thread = output channel,
+//                 registers = 32 consecutive pixels), add the bias, convert to fp16 and store NCHW rows (64-byte runs).
+// Persistent CTAs (one per SM) loop over (image, 128-pixel tile) work items.
+//
+// Requirements of this path (otherwise dcn.cu's v1 path runs): FP16, groups == 1, deformable_groups == 1,
+// C % 64 == 0, Co in {128, 256, 512}, kh*kw <= 9.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kBN = 128;            // output pixels per tile (UMMA N)
+constexpr int kBK = 64;             // channels per k-block: 64 fp16 = one 128-byte swizzle row
+constexpr int kProducerWarps = 8;
+constexpr int kFusedThreads = (kProducerWarps + 1) * 32;  // + 1 MMA/TMEM warp
+constexpr int kMaxTaps = 9;
+
+struct DcnFusedParams {
+  const __half *x_nhwc, *w_r, *bias, *offset, *mask;
+  __half *out;
+  int B, C, H, W, Co, kh, kw, pad_h, pad_w, stride_h, stride_w, dil_h, dil_w, Ho, Wo;
+  int tiles_per_img, num_tiles, kb_per_tap, num_kb;
+};
+
+struct __align__(8) TapEntry {
+  int pix;   // (h0*W + w0) of the top-left corner, clamped into the image
+  int step;  // bit0: column neighbour usable, bit1: row neighbour usable
+  float w1, w2, w3, w4;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(=1) | SBO(1024 B) |
+// version 1 | layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N>>3, M>>4.
+constexpr uint32_t kIdesc = (1u << 4) | (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- pre-passes -----------------------------------------------------------------------------------------------------
+// NCHW -> NHWC (fp16), 32 pixels x 64 channels per block through shared memory.
+__global__ void __launch_bounds__(256) dcn_nchw_to_nhwc_kernel(const __half *__restrict__ in, __half *__restrict__ out,
+                                                               int C, int HW) {
+  __shared__ __half tile[64][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
+  for (int c = ty; c < 64; c += 8) {
+    const int p = p0 + tx;
+    tile[c][tx] = (p < HW && c0 + c < C) ? in[(static_cast<long long>(b) * C + c0 + c) * HW + p] : __float2half(0.f);
+  }
+  __syncthreads();
+  // write: 32 pixels x 64 channels; a thread writes one half2 (2 channels)
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+    const int p = i >> 5, c2 = (i & 31) * 2;
+    if (p0 + p < HW && c0 + c2 < C) {
+      __half2 v = __halves2half2(tile[c2][p], tile[c2 + 1][p]);
+      *reinterpret_cast<__half2 *>(out + (static_cast<long long>(b) * HW + p0 + p) * C + c0 + c2) = v;
+    }
+  }
+}
+
+// W[co][c][t] -> Wr[co][t*C + c]
+__global__ void dcn_weight_reorder_kernel(const __half *__restrict__ w, __half *__restrict__ wr, int Co, int C, int kk) {
+  const long long n = static_cast<long long>(Co) * C * kk;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int t = static_cast<int>((i / C) % kk);
+    const long long co = i / (static_cast<long long>(C) * kk);
+    wr[i] = w[(co * C + c) * kk + t];
+  }
+}
+
+// ---- the fused kernel -----------------------------------------------------------------------------------------------
+template <int MH>
+struct FusedCfg {
+  static constexpr int kStages = MH == 1 ? 4 : (MH == 2 ? 3 : 2);
+  static constexpr int kABytes = MH * 128 * 128;  // Co rows x 128 B
+  static constexpr int kBBytes = kBN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTableBytes = kMaxTaps * kBN * static_cast<int>(sizeof(TapEntry));
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kTableBytes + 256 /*barriers*/;
+  static constexpr int kTmemCols = MH * 128 <= 128 ? 128 : (MH * 128 <= 256 ? 256 : 512);
+};
+
+template <int MH>
+__global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFusedParams p) {
+  using Cfg = FusedCfg<MH>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *stage_base = smem;
+  TapEntry *table = reinterpret_cast<TapEntry *>(smem + S * Cfg::kStageBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S * Cfg::kStageBytes + Cfg::kTableBytes);
+  // bars[0..S) full, [S..2S) empty, [2S] tmem_full, [2S+1] tmem_empty, then the TMEM base pointer
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * S + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+  const uint32_t tmem_full = smem_u32(bars + 2 * S), tmem_empty = smem_u32(bars + 2 * S + 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, kProducerWarps);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kProducerWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarps) {  // the MMA warp owns TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int HoWo = p.Ho * p.Wo, HW = p.H * p.W, kk = p.kh * p.kw, K = kk * p.C;
+  const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / gridDim.x;
+
+  if (warp == kProducerWarps) {
+    // =================================== MMA issuer ===================================
+    uint32_t kbt = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      if (it > 0) mbar_wait(tmem_empty, (it - 1) & 1);  // epilogue of the previous tile has drained TMEM
+      tc_fence_after();
+      for (int kb = 0; kb < p.num_kb; ++kb, ++kbt) {
+        const int s = kbt % S;
+        mbar_wait(full0 + 8 * s, (kbt / S) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(stage_base + s * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int mh = 0; mh < MH; ++mh) {
+#pragma unroll
+            for (int k4 = 0; k4 < kBK / 16; ++k4) {
+              umma_f16(tmem_base + mh * 128, make_sw128_desc(a_addr + mh * 16384 + k4 * 32),
+                       make_sw128_desc(b_addr + k4 * 32), kIdesc, (kb | k4) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty0 + 8 * s);                          // frees the stage when these MMAs have read it
+          if (kb == p.num_kb - 1) umma_commit(tmem_full);       // accumulators complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =================================== producers + epilogue ===================================
+    const int pt = threadIdx.x;  // 0..255
+    uint32_t kbt = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / p.tiles_per_img;
+      const int p0 = (tile - b * p.tiles_per_img) * kBN;
+
+      // ---- sampling table of this tile: (tap, pixel) -> clamped corner + mask-folded bilinear weights
+      for (int e = pt; e < kk * kBN; e += kProducerWarps * 32) {
+        const int n = e % kBN, t = e / kBN;
+        const int pix = p0 + n;
+        TapEntry te{0, 0, 0.f, 0.f, 0.f, 0.f};
+        if (pix < HoWo) {
+          const int h_col = pix / p.Wo, w_col = pix - h_col * p.Wo;
+          const int i = t / p.kw, j = t - i * p.kw;
+          const float oh = __half2float(__ldg(p.offset + (static_cast<long long>(b) * 2 * kk + 2 * t) * HoWo + pix));
+          const float ow = __half2float(__ldg(p.offset + (static_cast<long long>(b) * 2 * kk + 2 * t + 1) * HoWo + pix));
+          const float m = __half2float(__ldg(p.mask + (static_cast<long long>(b) * kk + t) * HoWo + pix));
+          const float h_im = __fadd_rn(static_cast<float>(h_col * p.stride_h - p.pad_h + i * p.dil_h), oh);
+          const float w_im = __fadd_rn(static_cast<float>(w_col * p.stride_w - p.pad_w + j * p.dil_w), ow);
+          if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(p.H) && w_im < static_cast<float>(p.W)) {
+            const float hf = floorf(h_im), wf = floorf(w_im);
+            const int h_low = static_cast<int>(hf), w_low = static_cast<int>(wf);
+            const float lh = __fsub_rn(h_im, hf), lw = __fsub_rn(w_im, wf), hh = 1.f - lh, hw = 1.f - lw;
+            const bool tp = h_low >= 0, bt = h_low + 1 <= p.H - 1, lf = w_low >= 0, rt = w_low + 1 <= p.W - 1;
+            te.pix = max(h_low, 0) * p.W + max(w_low, 0);
+            te.step = ((lf && rt) ? 1 : 0) | ((tp && bt) ? 2 : 0);
+            te.w1 = (tp && lf) ? hh * hw * m : 0.f;
+            te.w2 = (tp && rt) ? hh * lw * m : 0.f;
+            te.w3 = (bt && lf) ? lh * hw * m : 0.f;
+            te.w4 = (bt && rt) ? lh * lw * m : 0.f;
+          }
+        }
+        table[e] = te;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
+
+      // ---- k-blocks: fill stage s with the weight slice (A) and the gathered column tile (B)
+      const int j8 = pt & 7, rowp = pt >> 3;  // 16-byte chunk within the 128-byte row; row within a pass of 32 rows
+      const __half *xb = p.x_nhwc + static_cast<long long>(b) * HW * p.C;
+      for (int kb = 0; kb < p.num_kb; ++kb, ++kbt) {
+        const int s = kbt % S;
+        mbar_wait(empty0 + 8 * s, ((kbt / S) & 1) ^ 1);
+        uint8_t *a_st = stage_base + s * Cfg::kStageBytes;
+        uint8_t *b_st = a_st + Cfg::kABytes;
+        const int t = kb / p.kb_per_tap, cc = kb - t * p.kb_per_tap;
+        // B: 128 pixels x 64 channels of tap t
+#pragma unroll
+        for (int pass = 0; pass < kBN / 32; ++pass) {
+          const int n = pass * 32 + rowp;
+          const TapEntry te = table[t * kBN + n];
+          const __half *c00 = xb + static_cast<long long>(te.pix) * p.C + cc * kBK + j8 * 8;
+          const int dx = (te.step & 1) ? p.C : 0, dy = (te.step & 2) ? p.W * p.C : 0;
+          const uint4 v00 = ldg128(c00), v01 = ldg128(c00 + dx), v10 = ldg128(c00 + dy), v11 = ldg128(c00 + dy + dx);
+          const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, bq[4] = {v01.x, v01.y, v01.z, v01.w};
+          const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 fa = h2_to_f2(a[q]), fb = h2_to_f2(bq[q]), fc = h2_to_f2(c[q]), fd = h2_to_f2(d[q]);
+            const float r0 = fmaf(te.w4, fd.x, fmaf(te.w3, fc.x, fmaf(te.w2, fb.x, te.w1 * fa.x)));
+            const float r1 = fmaf(te.w4, fd.y, fmaf(te.w3, fc.y, fmaf(te.w2, fb.y, te.w1 * fa.y)));
+            o[q] = f2_to_h2(r0, r1);
+          }
+          *reinterpret_cast<uint4 *>(b_st + n * 128 + ((j8 ^ (n & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        // A: Co rows x 64 k of the permuted weights
+        const __half *wsrc = p.w_r + static_cast<long long>(kb) * kBK + j8 * 8;
+#pragma unroll
+        for (int q = 0; q < MH * 128 / 32; ++q) {
+          const int r = q * 32 + rowp;
+          const uint4 v = ldg128(wsrc + static_cast<long long>(r) * K);
+          *reinterpret_cast<uint4 *>(a_st + r * 128 + ((j8 ^ (r & 7)) << 4)) = v;
+        }
+        fence_proxy_async();  // make the generic-proxy stores visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + 8 * s);
+      }
+
+      // ---- epilogue: TMEM -> registers -> +bias -> fp16 -> NCHW
+      mbar_wait(tmem_full, it & 1);
+      tc_fence_after();
+      const int quad = warp & 3;
+      for (int mh = warp >> 2; mh < MH; mh += 2) {
+        const int co = mh * 128 + quad * 32 + lane;
+        const float bias = p.bias ? __half2float(__ldg(p.bias + co)) : 0.f;
+        __half *orow = p.out + (static_cast<long long>(b) * p.Co + co) * HoWo + p0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kBN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mh * 128 + c0, r);
+          if (p0 + c0 + 32 <= HoWo && (reinterpret_cast<uintptr_t>(orow + c0) & 15) == 0) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 o;
+              o.x = f2_to_h2(__uint_as_float(r[8 * v + 0]) + bias, __uint_as_float(r[8 * v + 1]) + bias);
+              o.y = f2_to_h2(__uint_as_float(r[8 * v + 2]) + bias, __uint_as_float(r[8 * v + 3]) + bias);
+              o.z = f2_to_h2(__uint_as_float(r[8 * v + 4]) + bias, __uint_as_float(r[8 * v + 5]) + bias);
+              o.w = f2_to_h2(__uint_as_float(r[8 * v + 6]) + bias, __uint_as_float(r[8 * v + 7]) + bias);
+              *reinterpret_cast<uint4 *>(orow + c0 + 8 * v) = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (p0 + c0 + i < HoWo) orow[c0 + i] = __float2half_rn(__uint_as_float(r[i]) + bias);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---- host -----------------------------------------------------------------------------------------------------------
+size_t dcn_fused_workspace_bytes(int batch, int channels, int height, int width, int channels_out, int kk) {
+  const size_t x = (static_cast<size_t>(batch) * height * width * channels * 2 + 255) / 256 * 256;
+  const size_t w = (static_cast<size_t>(channels_out) * channels * kk * 2 + 255) / 256 * 256;
+  return x + w;
+}
+
+bool dcn_fused_supported(int channels, int channels_out, int kk, int group, int deformable_group) {
+  return group == 1 && deformable_group == 1 && channels % kBK == 0 &&
+         (channels_out == 128 || channels_out == 256 || channels_out == 512) && kk <= kMaxTaps;
+}
+
+template <int MH>
+static int launch_fused(const DcnFusedParams &p, cudaStream_t stream) {
+  using Cfg = FusedCfg<MH>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(dcn_fused_kernel<MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
+        cudaSuccess)
+      return B200_ERR_LAUNCH;
+    configured = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  dcn_fused_kernel<MH><<<grid, kFusedThreads, Cfg::kSmemBytes, stream>>>(p);
+  return check_launch();
+}
+
+int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias, const __half *offset,
+                  const __half *mask, __half *output, void *workspace, int batch, int channels, int height, int width,
+                  int channels_out, int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h,
+                  int dilation_w, int dilation_h, int Ho, int Wo, cudaStream_t stream) {
+  const int kk = kernel_h * kernel_w, HW = height * width;
+  __half *x_nhwc = static_cast<__half *>(workspace);
+  __half *w_r = reinterpret_cast<__half *>(static_cast<uint8_t *>(workspace) +
+                                           (static_cast<size_t>(batch) * HW * channels * 2 + 255) / 256 * 256);
+  dcn_nchw_to_nhwc_kernel<<<dim3((HW + 31) / 32, (channels + 63) / 64, batch), 256, 0, stream>>>(input, x_nhwc, channels,
+                                                                                                  HW);
+  int st = check_launch();
+  if (st != B200_OK) return st;
+  const long long wn = static_cast<long long>(channels_out) * channels * kk;
+  dcn_weight_reorder_kernel<<<static_cast<unsigned>((wn + 255) / 256), 256, 0, stream>>>(weight, w_r, channels_out,
+                                                                                         channels, kk);
+  st = check_launch();
+  if (st != B200_OK) return st;
+
+  DcnFusedParams p{};
+  p.x_nhwc = x_nhwc, p.w_r = w_r, p.bias = bias, p.offset = offset, p.mask = mask, p.out = output;
+  p.B = batch, p.C = channels, p.H = height, p.W = width, p.Co = channels_out, p.kh = kernel_h, p.kw = kernel_w;
+  p.pad_h = pad_h, p.pad_w = pad_w, p.stride_h = stride_h, p.stride_w = stride_w, p.dil_h = dilation_h,
+  p.dil_w = dilation_w, p.Ho = Ho, p.Wo = Wo;
+  p.tiles_per_img = (Ho * Wo + kBN - 1) / kBN;
+  p.num_tiles = p.tiles_per_img * batch;
+  p.kb_per_tap = channels / kBK;
+  p.num_kb = kk * p.kb_per_tap;
+  switch (channels_out / 128) {
+    case 1: return launch_fused<1>(p, stream);
+    case 2: return launch_fused<2>(p, stream);
+    case 4: return launch_fused<4>(p, stream);
+    default: return B200_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace b200

@@ -195,6 +195,11 @@ size_t b200_dcn_workspace_size(int dtype /* 0 f32, 1 f16 */, int batch, int chan
                                int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h,
                                int dilation_w, int dilation_h);
 
+/* FP16 runs as one fused implicit GEMM on tcgen05 tensor cores (csrc/dcn_fused.cu) when groups == deformable_groups == 1,
+ * channels % 64 == 0 and channels_out in {128, 256, 512}; otherwise (and for FP32) as gather + cuBLAS GEMM.
+ * b200_dcn_set_fused(0) forces the second path (A/B measurements); returns the previous setting. */
+int b200_dcn_set_fused(int enabled);
+
 /* replaces ModulatedDeformConvForwardCUDAKernel<float> — …Conv2dKernel.cu:695-760 */
 int b200_dcn_f32(const float *input, const float *weight, const float *bias, const float *offset, const float *mask,
                  float *output, void *workspace, int batch, int channels, int height, int width, int channels_out,

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Kernel-level timings of the other ops on the path at BEVFormer-base shapes (CUDA events, L2-warm, 50 launches):
+grid sampler prev-BEV warp [1,256,200,200] and DCNv2 R101 stage-3 layer [6,256,58,100] 3x3. Prints one JSON line."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bevformer_tensorrt_b200 as bt  # noqa: E402
+from bevformer_tensorrt_b200.functions.grid_sampler import pack_chw  # noqa: E402
+
+
+def timeit(fn, n=50, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n * 1e3  # us
+
+
+def main():
+    peak = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    out = {}
+    # grid sampler: rotation grid like onnx_ops.py:226-232 (prev-BEV warp)
+    H = W = 200
+    x = torch.randn(1, 256, H, W, device="cuda")
+    th = 0.05
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, H, device="cuda"), torch.linspace(-1, 1, W, device="cuda"), indexing="ij")
+    grid = torch.stack([xs * 0.9988 - ys * th, xs * th + ys * 0.9988], 0)[None].contiguous() * 10
+    for name, xx, gg in (("f32", x, grid), ("f16", x.half(), grid.half())):
+        us = timeit(lambda: bt.grid_sampler(xx, gg, "bilinear", "zeros", False))
+        nbytes = 2 * xx.numel() * xx.element_size() + gg.numel() * gg.element_size()
+        out[f"grid_sampler_{name}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+    x2, g2 = pack_chw(x.half(), 2), grid.half().permute(0, 2, 3, 1).unsqueeze(1).contiguous()
+    us = timeit(lambda: bt.grid_sampler_chw2(x2, g2, 256, "bilinear", "zeros", False))
+    out["grid_sampler_f16_chw2"] = {"us": us, "hbm_frac": 41120000 / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+    xi = torch.randint(-127, 127, (1, 64, H, W, 4), dtype=torch.int8, device="cuda")
+    gi = torch.zeros(1, 1, H, W, 4, dtype=torch.int8, device="cuda")
+    gi[..., 0] = (grid[0, 0] * 12.7).round().clamp(-127, 127).to(torch.int8)
+    gi[..., 1] = (grid[0, 1] * 12.7).round().clamp(-127, 127).to(torch.int8)
+    us = timeit(lambda: bt.grid_sampler_int8(xi, 0.03, gi, 10 / 127, 0.03, 256, "bilinear", "zeros", False))
+    out["grid_sampler_i8_chw4"] = {"us": us, "hbm_frac": 20640000 / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+
+    # DCNv2 base backbone layer
+    xd = torch.randn(6, 256, 58, 100, device="cuda")
+    off = torch.randn(6, 18, 58, 100, device="cuda") * 2
+    mask = torch.sigmoid(torch.randn(6, 9, 58, 100, device="cuda"))
+    w = torch.randn(256, 256, 3, 3, device="cuda") / 48
+    b = torch.randn(256, device="cuda")
+    flops = 2 * 256 * 2304 * 5800 * 6
+    for name, cast in (("f32", lambda t: t), ("f16", lambda t: t.half())):
+        args = [cast(t) for t in (xd, off, mask, w, b)]
+        us = timeit(lambda: bt.modulated_deformable_conv2d(*args, 1, 1, 1, 1, 1), n=20)
+        out[f"dcn_{name}"] = {"us": us, "tflops": flops / (us * 1e-6) / 1e12, "tensor_frac_of_bf16_peak": flops / (us * 1e-6) / 1e12 / peak["bf16_tflops"]}
+    try:
+        import torchvision
+
+        us = timeit(lambda: torchvision.ops.deform_conv2d(xd.half(), off.half(), w.half(), b.half(), padding=1, mask=mask.half()), n=10)
+        out["torchvision_deform_conv2d_f16"] = {"us": us}
+    except Exception as e:  # noqa: BLE001
+        out["torchvision_deform_conv2d_f16"] = {"error": str(e)[:100]}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

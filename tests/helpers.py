@@ -64,6 +64,11 @@ DCN_CASES = {
     "k1_s1_p0_g1_dg1": (2, 8, 9, 9, 8, 1, 1, 1, 0, 1, 1, 1),
     "k3x5_s1_p1_g1_dg1": (1, 4, 11, 13, 4, 3, 5, 1, 1, 1, 1, 1),
     "backbone_like": (2, 64, 29, 50, 64, 3, 3, 1, 1, 1, 1, 1),  # BEVFormer R101 stage shapes, channels reduced
+    # shapes the fused tcgen05 path takes in FP16 (groups = dg = 1, C % 64 == 0, Co in {128, 256, 512})
+    "fused_co128": (2, 64, 20, 24, 128, 3, 3, 1, 1, 1, 1, 1),
+    "fused_co256_ragged": (3, 128, 29, 50, 256, 3, 3, 1, 1, 1, 1, 1),  # 1450 pixels: partial last tile, unaligned rows
+    "fused_co512_s2": (1, 64, 31, 33, 512, 3, 3, 2, 1, 1, 1, 1),
+    "fused_k1": (2, 128, 16, 16, 128, 1, 1, 1, 0, 1, 1, 1),
 }
 
 

@@ -35,6 +35,30 @@ def test_fp32_matches_oracle(case):
     assert np.abs(nb - (want - b.numpy()[None, :, None, None])).max() < 2e-4 * max(1.0, np.abs(want).max())
 
 
+FUSED_CASES = ["fused_co128", "fused_co256_ragged", "fused_co512_s2", "fused_k1"]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_fp16_fused_tcgen05_path_matches_oracle_and_gather_gemm_path(case):
+    """The fused implicit-GEMM kernel (csrc/dcn_fused.cu) against the oracle and against the library's own
+    gather + cuBLAS path on the same inputs."""
+    x, off, mask, w, b, kw = make_dcn_inputs(case, dtype=torch.float16)
+    want = odcn.modulated_deformable_conv2d(*(t.float().numpy() for t in (x, off, mask, w, b)), **kw)
+    lib = _lib.load()
+    prev = lib.b200_dcn_set_fused(1)
+    try:
+        fused = _call(bt.modulated_deformable_conv2d, x, off, mask, w, b, kw)
+        lib.b200_dcn_set_fused(0)
+        plain = _call(bt.modulated_deformable_conv2d, x, off, mask, w, b, kw)
+    finally:
+        lib.b200_dcn_set_fused(prev)
+    tol = 5e-3 * max(1.0, np.abs(want).max())
+    assert np.abs(fused.float().cpu().numpy() - want).max() < tol, np.abs(fused.float().cpu().numpy() - want).max()
+    assert np.abs(plain.float().cpu().numpy() - want).max() < tol
+    nb = _call(bt.modulated_deformable_conv2d, x, off, mask, w, None, kw)  # no bias
+    assert np.abs(nb.float().cpu().numpy() - (want - b.float().numpy()[None, :, None, None])).max() < tol
+
+
 @pytest.mark.parametrize("case", ["k3_s1_p1_g2_dg2", "backbone_like", "k3_s2_p1_g1_dg1"])
 def test_fp16_matches_oracle(case):
     x, off, mask, w, b, kw = make_dcn_inputs(case, dtype=torch.float16)
