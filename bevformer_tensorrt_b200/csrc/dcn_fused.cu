@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
       const int quad = warp & 3;
       for (int mh = warp >> 2; mh < MH; mh += 2) {
         const int co = mh * 128 + quad * 32 + lane;
-        const float bias = p.bias ? __half2float(__ldg(p.bias + co)) : 0.f;
+        const float bias = __half2float(__ldg(p.bias + co));
         __half *orow = p.out + (static_cast<long long>(b) * p.Co + co) * HoWo + p0;
 #pragma unroll 1
         for (int c0 = 0; c0 < kBN; c0 += 32) {
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
 size_t dcn_fused_workspace_bytes(int batch, int channels, int height, int width, int channels_out, int kk) {
   const size_t x = (static_cast<size_t>(batch) * height * width * channels * 2 + 255) / 256 * 256;
   const size_t w = (static_cast<size_t>(channels_out) * channels * kk * 2 + 255) / 256 * 256;
-  return x + w;
+  return x + w + 1024;  // + a zero bias vector for the bias-less call (<= 512 channels x 2 B)
 }
 
 bool dcn_fused_supported(int channels, int channels_out, int kk, int group, int deformable_group) {
@@ -371,6 +371,12 @@ int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias,
   __half *x_nhwc = static_cast<__half *>(workspace);
   __half *w_r = reinterpret_cast<__half *>(static_cast<uint8_t *>(workspace) +
                                            (static_cast<size_t>(batch) * HW * channels * 2 + 255) / 256 * 256);
+  if (!bias) {  // the kernel always reads a bias vector (no per-thread null test in the epilogue): use zeros
+    __half *zb = reinterpret_cast<__half *>(reinterpret_cast<uint8_t *>(w_r) +
+                                            (static_cast<size_t>(channels_out) * channels * kk * 2 + 255) / 256 * 256);
+    if (cudaMemsetAsync(zb, 0, static_cast<size_t>(channels_out) * 2, stream) != cudaSuccess) return B200_ERR_LAUNCH;
+    bias = zb;
+  }
   dcn_nchw_to_nhwc_kernel<<<dim3((HW + 31) / 32, (channels + 63) / 64, batch), 256, 0, stream>>>(input, x_nhwc, channels,
                                                                                                   HW);
   int st = check_launch();
