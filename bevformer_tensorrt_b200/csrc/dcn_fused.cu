@@ -4,8 +4,9 @@
 // modulatedDeformableConv2dKernel.cu:259-318 im2col + :735-759 cuBLAS GEMM + bias kernel, with a 26.7 MB column buffer
 // per image in between). Here the column tile never exists in global memory:
 //
-//   GEMM view   D[M = Co, N = 128 output pixels of one image] += A[M, K] * B[N, K]^T,  K = kh*kw*C ordered (tap, channel)
-//   A (weights) : pre-permuted once per call to [Co][tap][C] (K-major rows); producers copy the k-block slice into
+//   GEMM view   D[M = Co, N = 128 output pixels of one image] += A[M, K] * B[N, K]^T,  K = kh*kw*C ordered
+//               (64-channel chunk, tap, channel)
+//   A (weights) : pre-permuted once per call to [Co][C/64][tap][64] (K-major rows); producers copy the k-block slice into
 //                 shared memory in the canonical K-major SWIZZLE_128B layout (128-byte rows, 16-byte chunks XOR row&7).
 //   B (columns) : GATHERED by the producer warps straight into the same canonical layout: the input is first brought to
 //                 NHWC so that the 64 channels of a k-block are 128 contiguous bytes per bilinear corner; a thread
@@ -27,7 +28,7 @@ namespace b200 {
 
 constexpr int kBN = 128;            // output pixels per tile (UMMA N)
 constexpr int kBK = 64;             // channels per k-block: 64 fp16 = one 128-byte swizzle row
-constexpr int kProducerWarps = 8;
+constexpr int kProducerWarps = 16;  // 512 gather threads: the kernel is latency-bound on the corner loads
 constexpr int kFusedThreads = (kProducerWarps + 1) * 32;  // + 1 MMA/TMEM warp
 constexpr int kMaxTaps = 9;
 
@@ -98,36 +99,54 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---- pre-passes -----------------------------------------------------------------------------------------------------
-// NCHW -> NHWC (fp16), 32 pixels x 64 channels per block through shared memory.
-__global__ void __launch_bounds__(256) dcn_nchw_to_nhwc_kernel(const __half *__restrict__ in, __half *__restrict__ out,
+// NCHW -> NHWC (fp16): 64 channels x 64 pixels per block through shared memory; 128-bit global accesses on both sides
+// when HW % 8 == 0 (rows of the NCHW planes are then 16-byte aligned), scalar loads otherwise.
+__global__ void __launch_bounds__(512) dcn_nchw_to_nhwc_kernel(const __half *__restrict__ in, __half *__restrict__ out,
                                                                int C, int HW) {
-  __shared__ __half tile[64][33];
-  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
-  for (int c = ty; c < 64; c += 8) {
-    const int p = p0 + tx;
-    tile[c][tx] = (p < HW && c0 + c < C) ? in[(static_cast<long long>(b) * C + c0 + c) * HW + p] : __float2half(0.f);
+  __shared__ __half tile[64][66];  // row stride 33 words: column reads are conflict-free
+  const int b = blockIdx.z, p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+  {
+    const int c = t >> 3, pj = (t & 7) * 8;  // 64 channel rows x 8 chunks of 8 pixels
+    const __half *src = in + (static_cast<long long>(b) * C + c0 + c) * HW + p0 + pj;
+    if ((HW & 7) == 0 && p0 + pj + 8 <= HW) {
+      const uint4 v = ldg128(src);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint32_t *>(&tile[c][pj + 2 * i]) = w[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tile[c][pj + i] = (p0 + pj + i < HW) ? src[i] : __float2half(0.f);
+    }
   }
   __syncthreads();
-  // write: 32 pixels x 64 channels; a thread writes one half2 (2 channels)
-  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-    const int p = i >> 5, c2 = (i & 31) * 2;
-    if (p0 + p < HW && c0 + c2 < C) {
-      __half2 v = __halves2half2(tile[c2][p], tile[c2 + 1][p]);
-      *reinterpret_cast<__half2 *>(out + (static_cast<long long>(b) * HW + p0 + p) * C + c0 + c2) = v;
+  {
+    const int pp = t >> 3, cj = (t & 7) * 8;  // 64 pixels x 8 chunks of 8 channels
+    if (p0 + pp < HW) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __half2 h = __halves2half2(tile[cj + 2 * i][pp], tile[cj + 2 * i + 1][pp]);
+        w[i] = *reinterpret_cast<const uint32_t *>(&h);
+      }
+      *reinterpret_cast<uint4 *>(out + (static_cast<long long>(b) * HW + p0 + pp) * C + c0 + cj) =
+          make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 }
 
-// W[co][c][t] -> Wr[co][t*C + c]
+// W[co][c][t] -> Wr[co][k],  k = (c / 64) * (kk * 64) + t * 64 + (c % 64): K is ordered (channel chunk, tap, channel).
+// Consecutive k-blocks are then the kh*kw taps of ONE 64-channel chunk, whose bilinear corners overlap spatially, so the
+// gather of tap t+1 mostly hits in L1 what tap t brought in.
 __global__ void dcn_weight_reorder_kernel(const __half *__restrict__ w, __half *__restrict__ wr, int Co, int C, int kk) {
   const long long n = static_cast<long long>(Co) * C * kk;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const int t = static_cast<int>((i / C) % kk);
+    const int ci = static_cast<int>(i % kBK);
+    const int t = static_cast<int>((i / kBK) % kk);
+    const int cc = static_cast<int>((i / (static_cast<long long>(kBK) * kk)) % (C / kBK));
     const long long co = i / (static_cast<long long>(C) * kk);
-    wr[i] = w[(co * C + c) * kk + t];
+    wr[i] = w[(co * C + cc * kBK + ci) * kk + t];
   }
 }
 
@@ -211,7 +230,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
     }
   } else {
     // =================================== producers + epilogue ===================================
-    const int pt = threadIdx.x;  // 0..255
+    const int pt = threadIdx.x;  // 0..kProducerWarps*32-1
     uint32_t kbt = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
@@ -249,41 +268,56 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
       asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
 
       // ---- k-blocks: fill stage s with the weight slice (A) and the gathered column tile (B)
-      const int j8 = pt & 7, rowp = pt >> 3;  // 16-byte chunk within the 128-byte row; row within a pass of 32 rows
+      constexpr int kRowsPerPass = kProducerWarps * 32 / 8;
+      const int j8 = pt & 7, rowp = pt >> 3;  // 16-byte chunk within the 128-byte row; row within a pass
       const __half *xb = p.x_nhwc + static_cast<long long>(b) * HW * p.C;
       for (int kb = 0; kb < p.num_kb; ++kb, ++kbt) {
         const int s = kbt % S;
-        mbar_wait(empty0 + 8 * s, ((kbt / S) & 1) ^ 1);
         uint8_t *a_st = stage_base + s * Cfg::kStageBytes;
         uint8_t *b_st = a_st + Cfg::kABytes;
-        const int t = kb / p.kb_per_tap, cc = kb - t * p.kb_per_tap;
-        // B: 128 pixels x 64 channels of tap t
+        const int cc = kb / kk, t = kb - cc * kk;  // K order: (channel chunk, tap, channel)
+        constexpr int kPasses = kBN / kRowsPerPass, kAQ = MH * 128 / kRowsPerPass;
+        // Issue every global load of this k-block first (corner vectors of B, weight slice of A) and only then wait for
+        // the stage to be free: the loads fly while the tensor core still reads the stage's previous contents.
+        TapEntry te[kPasses];
+        uint4 v[kPasses][4], wv[kAQ];
 #pragma unroll
-        for (int pass = 0; pass < kBN / 32; ++pass) {
-          const int n = pass * 32 + rowp;
-          const TapEntry te = table[t * kBN + n];
-          const __half *c00 = xb + static_cast<long long>(te.pix) * p.C + cc * kBK + j8 * 8;
-          const int dx = (te.step & 1) ? p.C : 0, dy = (te.step & 2) ? p.W * p.C : 0;
-          const uint4 v00 = ldg128(c00), v01 = ldg128(c00 + dx), v10 = ldg128(c00 + dy), v11 = ldg128(c00 + dy + dx);
-          const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, bq[4] = {v01.x, v01.y, v01.z, v01.w};
-          const uint32_t c[4] = {v10.x, v10.y, v10.z, v10.w}, d[4] = {v11.x, v11.y, v11.z, v11.w};
+        for (int pass = 0; pass < kPasses; ++pass) te[pass] = table[t * kBN + pass * kRowsPerPass + rowp];
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const __half *c00 = xb + static_cast<long long>(te[pass].pix) * p.C + cc * kBK + j8 * 8;
+          const int dx = (te[pass].step & 1) ? p.C : 0, dy = (te[pass].step & 2) ? p.W * p.C : 0;
+          v[pass][0] = ldg128(c00), v[pass][1] = ldg128(c00 + dx), v[pass][2] = ldg128(c00 + dy),
+          v[pass][3] = ldg128(c00 + dy + dx);
+        }
+        const __half *wsrc = p.w_r + static_cast<long long>(kb) * kBK + j8 * 8;
+#pragma unroll
+        for (int q = 0; q < kAQ; ++q) wv[q] = ldg128(wsrc + static_cast<long long>(q * kRowsPerPass + rowp) * K);
+
+        mbar_wait(empty0 + 8 * s, ((kbt / S) & 1) ^ 1);
+        // B: 128 pixels x 64 channels of tap t, blended in fp32, packed to fp16, swizzled 16-byte store
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const int n = pass * kRowsPerPass + rowp;
+          const uint32_t a[4] = {v[pass][0].x, v[pass][0].y, v[pass][0].z, v[pass][0].w};
+          const uint32_t bq[4] = {v[pass][1].x, v[pass][1].y, v[pass][1].z, v[pass][1].w};
+          const uint32_t c[4] = {v[pass][2].x, v[pass][2].y, v[pass][2].z, v[pass][2].w};
+          const uint32_t d[4] = {v[pass][3].x, v[pass][3].y, v[pass][3].z, v[pass][3].w};
           uint32_t o[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float2 fa = h2_to_f2(a[q]), fb = h2_to_f2(bq[q]), fc = h2_to_f2(c[q]), fd = h2_to_f2(d[q]);
-            const float r0 = fmaf(te.w4, fd.x, fmaf(te.w3, fc.x, fmaf(te.w2, fb.x, te.w1 * fa.x)));
-            const float r1 = fmaf(te.w4, fd.y, fmaf(te.w3, fc.y, fmaf(te.w2, fb.y, te.w1 * fa.y)));
+            const float r0 = fmaf(te[pass].w4, fd.x, fmaf(te[pass].w3, fc.x, fmaf(te[pass].w2, fb.x, te[pass].w1 * fa.x)));
+            const float r1 = fmaf(te[pass].w4, fd.y, fmaf(te[pass].w3, fc.y, fmaf(te[pass].w2, fb.y, te[pass].w1 * fa.y)));
             o[q] = f2_to_h2(r0, r1);
           }
           *reinterpret_cast<uint4 *>(b_st + n * 128 + ((j8 ^ (n & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
         // A: Co rows x 64 k of the permuted weights
-        const __half *wsrc = p.w_r + static_cast<long long>(kb) * kBK + j8 * 8;
 #pragma unroll
-        for (int q = 0; q < MH * 128 / 32; ++q) {
-          const int r = q * 32 + rowp;
-          const uint4 v = ldg128(wsrc + static_cast<long long>(r) * K);
-          *reinterpret_cast<uint4 *>(a_st + r * 128 + ((j8 ^ (r & 7)) << 4)) = v;
+        for (int q = 0; q < kAQ; ++q) {
+          const int r = q * kRowsPerPass + rowp;
+          *reinterpret_cast<uint4 *>(a_st + r * 128 + ((j8 ^ (r & 7)) << 4)) = wv[q];
         }
         fence_proxy_async();  // make the generic-proxy stores visible to the tensor-core (async) proxy
         __syncwarp();
@@ -293,13 +327,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
       // ---- epilogue: TMEM -> registers -> +bias -> fp16 -> NCHW
       mbar_wait(tmem_full, it & 1);
       tc_fence_after();
+      // a warp may only touch its own TMEM lane quadrant (warp % 4); the warps of a quadrant split the
+      // (accumulator, 32-column chunk) units between them
       const int quad = warp & 3;
-      for (int mh = warp >> 2; mh < MH; mh += 2) {
+      for (int u = warp >> 2; u < MH * (kBN / 32); u += kProducerWarps / 4) {
+        const int mh = u / (kBN / 32), c0 = (u % (kBN / 32)) * 32;
         const int co = mh * 128 + quad * 32 + lane;
         const float bias = __half2float(__ldg(p.bias + co));
         __half *orow = p.out + (static_cast<long long>(b) * p.Co + co) * HoWo + p0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kBN; c0 += 32) {
+        {
           uint32_t r[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mh * 128 + c0, r);
           if (p0 + c0 + 32 <= HoWo && (reinterpret_cast<uintptr_t>(orow + c0) & 15) == 0) {
@@ -377,7 +413,7 @@ int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias,
     if (cudaMemsetAsync(zb, 0, static_cast<size_t>(channels_out) * 2, stream) != cudaSuccess) return B200_ERR_LAUNCH;
     bias = zb;
   }
-  dcn_nchw_to_nhwc_kernel<<<dim3((HW + 31) / 32, (channels + 63) / 64, batch), 256, 0, stream>>>(input, x_nhwc, channels,
+  dcn_nchw_to_nhwc_kernel<<<dim3((HW + 63) / 64, channels / 64, batch), 512, 0, stream>>>(input, x_nhwc, channels,
                                                                                                   HW);
   int st = check_launch();
   if (st != B200_OK) return st;

@@ -13,13 +13,20 @@ from bevformer_tensorrt_b200.functions.grid_sampler import pack_chw  # noqa: E40
 
 
 def timeit(fn, n=50, warm=5):
+    """Device time per call: the calls are captured into one CUDA graph (the ops launch on torch's current stream through
+    the C ABI, so they are capturable) and the graph replay is timed with events — no Python/launch overhead inside."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(n):
-        fn()
+    g.replay()
     b.record()
     torch.cuda.synchronize()
     return a.elapsed_time(b) / n * 1e3  # us
