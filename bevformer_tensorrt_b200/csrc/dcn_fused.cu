@@ -18,18 +18,20 @@
 //                 mbarriers; producers signal filled stages after fence.proxy.async.
 //   epilogue    : the producer warps read their TMEM lane quadrant with tcgen05.ld.32x32b.x32 (thread = output channel,
 //                 registers = 32 consecutive pixels), add the bias, convert to fp16 and store NCHW rows (64-byte runs).
-// Persistent CTAs (one per SM) loop over (image, 128-pixel tile) work items.
+// Persistent CTAs (one per SM) loop over (image, 256- or 128-pixel tile) work items.
 //
 // Requirements of this path (otherwise dcn.cu's v1 path runs): FP16, groups == 1, deformable_groups == 1,
 // C % 64 == 0, Co in {128, 256, 512}, kh*kw <= 9.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace b200 {
 
-constexpr int kBN = 128;            // output pixels per tile (UMMA N)
+constexpr int kMaxBN = 256;         // output pixels per tile (UMMA N): 256 when the accumulators fit TMEM, else 128
 constexpr int kBK = 64;             // channels per k-block: 64 fp16 = one 128-byte swizzle row
 constexpr int kProducerWarps = 16;  // 512 gather threads: the kernel is latency-bound on the corner loads
-constexpr int kFusedThreads = (kProducerWarps + 1) * 32;  // + 1 MMA/TMEM warp
+constexpr int kFusedThreads = (kProducerWarps + 2) * 32;  // + 1 MMA/TMEM warp + 1 TMA warp (weights)
 constexpr int kMaxTaps = 9;
 
 struct DcnFusedParams {
@@ -39,10 +41,11 @@ struct DcnFusedParams {
   int tiles_per_img, num_tiles, kb_per_tap, num_kb;
 };
 
-struct __align__(8) TapEntry {
-  int pix;   // (h0*W + w0) of the top-left corner, clamped into the image
-  int step;  // bit0: column neighbour usable, bit1: row neighbour usable
-  float w1, w2, w3, w4;
+struct __align__(16) TapEntry {  // 16 bytes: one LDS.128 / STS.128
+  int pix;       // (h0*W + w0) of the top-left corner, clamped into the image
+  int step;      // bit0: column neighbour usable, bit1: row neighbour usable
+  uint32_t w12;  // fp16 pair: corner weights (top-left, top-right), mask folded in
+  uint32_t w34;  // fp16 pair: (bottom-left, bottom-right)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
@@ -83,7 +86,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
          (1ull << 46) | (2ull << 61);
 }
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N>>3, M>>4.
-constexpr uint32_t kIdesc = (1u << 4) | (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+template <int BN>
+constexpr uint32_t kIdesc = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -153,19 +157,26 @@ __global__ void dcn_weight_reorder_kernel(const __half *__restrict__ w, __half *
 // ---- the fused kernel -----------------------------------------------------------------------------------------------
 template <int MH>
 struct FusedCfg {
-  static constexpr int kStages = MH == 1 ? 4 : (MH == 2 ? 3 : 2);
+  // A 128x128x16 MMA reads 8 KB of operands per 64 tensor cycles — the whole shared-memory port — so the tile is made
+  // 256 pixels wide whenever MH x 256 fp32 accumulator columns fit the 512 TMEM columns (Co <= 256): half the A re-reads
+  // per MAC. Co = 512 keeps 128-pixel tiles.
+  static constexpr int kBN = MH <= 2 ? 256 : 128;
   static constexpr int kABytes = MH * 128 * 128;  // Co rows x 128 B
   static constexpr int kBBytes = kBN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTableBytes = kMaxTaps * kBN * static_cast<int>(sizeof(TapEntry));
+  static constexpr int kStages = (220 * 1024 - kTableBytes) / kStageBytes >= 4 ? 4 : (220 * 1024 - kTableBytes) / kStageBytes;
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kTableBytes + 256 /*barriers*/;
-  static constexpr int kTmemCols = MH * 128 <= 128 ? 128 : (MH * 128 <= 256 ? 256 : 512);
+  static constexpr int kTmemCols = MH * kBN <= 128 ? 128 : (MH * kBN <= 256 ? 256 : 512);
+  static_assert(kStages >= 2 && MH * kBN <= 512, "tile does not fit shared memory / TMEM");
 };
 
 template <int MH>
-__global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFusedParams p,
+                                                                     const __grid_constant__ CUtensorMap tmap_w) {
   using Cfg = FusedCfg<MH>;
   constexpr int S = Cfg::kStages;
+  constexpr int kBN = Cfg::kBN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *stage_base = smem;
@@ -180,7 +191,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full0 + 8 * s, kProducerWarps);
+      mbar_init(full0 + 8 * s, kProducerWarps + 1);  // 16 gather warps + the TMA warp's expect_tx arrive
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(tmem_full, 1);
@@ -201,7 +212,30 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
   const int HoWo = p.Ho * p.Wo, HW = p.H * p.W, kk = p.kh * p.kw, K = kk * p.C;
   const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / gridDim.x;
 
-  if (warp == kProducerWarps) {
+  if (warp == kProducerWarps + 1) {
+    // =================================== TMA: weight slices (A) ===================================
+    // cp.async.bulk.tensor writes the [128 rows x 64 k] box in the same 128-byte-swizzled layout the UMMA descriptor
+    // expects; completion is counted in bytes on the stage's full barrier.
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+      uint32_t kbt = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int kb = 0; kb < p.num_kb; ++kb, ++kbt) {
+          const int s = kbt % S;
+          mbar_wait(empty0 + 8 * s, ((kbt / S) & 1) ^ 1);
+          const uint32_t bar = full0 + 8 * s;
+          const uint32_t dst = smem_u32(stage_base + s * Cfg::kStageBytes);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(Cfg::kABytes) : "memory");
+#pragma unroll
+          for (int mh = 0; mh < MH; ++mh)
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"(dst + mh * 16384), "l"(&tmap_w), "r"(kb * kBK), "r"(mh * 128), "r"(bar)
+                : "memory");
+        }
+      }
+    }
+  } else if (warp == kProducerWarps) {
     // =================================== MMA issuer ===================================
     uint32_t kbt = 0;
     for (int it = 0; it < my_tiles; ++it) {
@@ -218,8 +252,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
           for (int mh = 0; mh < MH; ++mh) {
 #pragma unroll
             for (int k4 = 0; k4 < kBK / 16; ++k4) {
-              umma_f16(tmem_base + mh * 128, make_sw128_desc(a_addr + mh * 16384 + k4 * 32),
-                       make_sw128_desc(b_addr + k4 * 32), kIdesc, (kb | k4) != 0 ? 1u : 0u);
+              umma_f16(tmem_base + mh * kBN, make_sw128_desc(a_addr + mh * 16384 + k4 * 32),
+                       make_sw128_desc(b_addr + k4 * 32), kIdesc<kBN>, (kb | k4) != 0 ? 1u : 0u);
             }
           }
           umma_commit(empty0 + 8 * s);                          // frees the stage when these MMAs have read it
@@ -241,7 +275,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
       for (int e = pt; e < kk * kBN; e += kProducerWarps * 32) {
         const int n = e % kBN, t = e / kBN;
         const int pix = p0 + n;
-        TapEntry te{0, 0, 0.f, 0.f, 0.f, 0.f};
+        TapEntry te{0, 0, 0u, 0u};
         if (pix < HoWo) {
           const int h_col = pix / p.Wo, w_col = pix - h_col * p.Wo;
           const int i = t / p.kw, j = t - i * p.kw;
@@ -257,10 +291,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
             const bool tp = h_low >= 0, bt = h_low + 1 <= p.H - 1, lf = w_low >= 0, rt = w_low + 1 <= p.W - 1;
             te.pix = max(h_low, 0) * p.W + max(w_low, 0);
             te.step = ((lf && rt) ? 1 : 0) | ((tp && bt) ? 2 : 0);
-            te.w1 = (tp && lf) ? hh * hw * m : 0.f;
-            te.w2 = (tp && rt) ? hh * lw * m : 0.f;
-            te.w3 = (bt && lf) ? lh * hw * m : 0.f;
-            te.w4 = (bt && rt) ? lh * lw * m : 0.f;
+            te.w12 = f2_to_h2((tp && lf) ? hh * hw * m : 0.f, (tp && rt) ? hh * lw * m : 0.f);
+            te.w34 = f2_to_h2((bt && lf) ? lh * hw * m : 0.f, (bt && rt) ? lh * lw * m : 0.f);
           }
         }
         table[e] = te;
@@ -271,16 +303,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
       constexpr int kRowsPerPass = kProducerWarps * 32 / 8;
       const int j8 = pt & 7, rowp = pt >> 3;  // 16-byte chunk within the 128-byte row; row within a pass
       const __half *xb = p.x_nhwc + static_cast<long long>(b) * HW * p.C;
+      constexpr int kPasses = kBN / kRowsPerPass;
       for (int kb = 0; kb < p.num_kb; ++kb, ++kbt) {
         const int s = kbt % S;
-        uint8_t *a_st = stage_base + s * Cfg::kStageBytes;
-        uint8_t *b_st = a_st + Cfg::kABytes;
+        uint8_t *b_st = stage_base + s * Cfg::kStageBytes + Cfg::kABytes;
         const int cc = kb / kk, t = kb - cc * kk;  // K order: (channel chunk, tap, channel)
-        constexpr int kPasses = kBN / kRowsPerPass, kAQ = MH * 128 / kRowsPerPass;
-        // Issue every global load of this k-block first (corner vectors of B, weight slice of A) and only then wait for
-        // the stage to be free: the loads fly while the tensor core still reads the stage's previous contents.
+        // Issue every corner load of this k-block first and only then wait for the stage to be free: the loads fly
+        // while the tensor core still reads the stage's previous contents. (The weight slice A arrives by TMA.)
         TapEntry te[kPasses];
-        uint4 v[kPasses][4], wv[kAQ];
+        uint4 v[kPasses][4];
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) te[pass] = table[t * kBN + pass * kRowsPerPass + rowp];
 #pragma unroll
@@ -290,15 +321,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
           v[pass][0] = ldg128(c00), v[pass][1] = ldg128(c00 + dx), v[pass][2] = ldg128(c00 + dy),
           v[pass][3] = ldg128(c00 + dy + dx);
         }
-        const __half *wsrc = p.w_r + static_cast<long long>(kb) * kBK + j8 * 8;
-#pragma unroll
-        for (int q = 0; q < kAQ; ++q) wv[q] = ldg128(wsrc + static_cast<long long>(q * kRowsPerPass + rowp) * K);
-
         mbar_wait(empty0 + 8 * s, ((kbt / S) & 1) ^ 1);
-        // B: 128 pixels x 64 channels of tap t, blended in fp32, packed to fp16, swizzled 16-byte store
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) {
           const int n = pass * kRowsPerPass + rowp;
+          // The column operand is FP16 in any case (tensor-core input); blending the four corners with packed HFMA2
+          // (fp16 weights = mask x bilinear, <= 1) instead of fp32 costs two extra 2^-11 roundings on values that are
+          // then summed over K = kh*kw*C with fp32 accumulation — far below the FP16 output rounding — and removes all
+          // conversions from the producers' inner loop (the reference's FP16 im2col is fp16 arithmetic too, :321-388).
+          const __half2 w12 = *reinterpret_cast<const __half2 *>(&te[pass].w12);
+          const __half2 w34 = *reinterpret_cast<const __half2 *>(&te[pass].w34);
+          const __half2 w1 = __low2half2(w12), w2 = __high2half2(w12), w3 = __low2half2(w34), w4 = __high2half2(w34);
           const uint32_t a[4] = {v[pass][0].x, v[pass][0].y, v[pass][0].z, v[pass][0].w};
           const uint32_t bq[4] = {v[pass][1].x, v[pass][1].y, v[pass][1].z, v[pass][1].w};
           const uint32_t c[4] = {v[pass][2].x, v[pass][2].y, v[pass][2].z, v[pass][2].w};
@@ -306,18 +339,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
           uint32_t o[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 fa = h2_to_f2(a[q]), fb = h2_to_f2(bq[q]), fc = h2_to_f2(c[q]), fd = h2_to_f2(d[q]);
-            const float r0 = fmaf(te[pass].w4, fd.x, fmaf(te[pass].w3, fc.x, fmaf(te[pass].w2, fb.x, te[pass].w1 * fa.x)));
-            const float r1 = fmaf(te[pass].w4, fd.y, fmaf(te[pass].w3, fc.y, fmaf(te[pass].w2, fb.y, te[pass].w1 * fa.y)));
-            o[q] = f2_to_h2(r0, r1);
+            __half2 r = __hmul2(w1, *reinterpret_cast<const __half2 *>(&a[q]));
+            r = __hfma2(w2, *reinterpret_cast<const __half2 *>(&bq[q]), r);
+            r = __hfma2(w3, *reinterpret_cast<const __half2 *>(&c[q]), r);
+            r = __hfma2(w4, *reinterpret_cast<const __half2 *>(&d[q]), r);
+            o[q] = *reinterpret_cast<const uint32_t *>(&r);
           }
           *reinterpret_cast<uint4 *>(b_st + n * 128 + ((j8 ^ (n & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        // A: Co rows x 64 k of the permuted weights
-#pragma unroll
-        for (int q = 0; q < kAQ; ++q) {
-          const int r = q * kRowsPerPass + rowp;
-          *reinterpret_cast<uint4 *>(a_st + r * 128 + ((j8 ^ (r & 7)) << 4)) = wv[q];
         }
         fence_proxy_async();  // make the generic-proxy stores visible to the tensor-core (async) proxy
         __syncwarp();
@@ -337,7 +365,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
         __half *orow = p.out + (static_cast<long long>(b) * p.Co + co) * HoWo + p0;
         {
           uint32_t r[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mh * 128 + c0, r);
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mh * kBN + c0, r);
           if (p0 + c0 + 32 <= HoWo && (reinterpret_cast<uintptr_t>(orow + c0) & 15) == 0) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
@@ -381,6 +409,30 @@ bool dcn_fused_supported(int channels, int channels_out, int kk, int group, int 
          (channels_out == 128 || channels_out == 256 || channels_out == 512) && kk <= kMaxTaps;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D tensor map over the permuted weights Wr[Co][K] (fp16): box = 64 k x 128 rows, 128-byte swizzle.
+static int make_weight_tmap(CUtensorMap *tm, const __half *w_r, int Co, int K) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return B200_ERR_LAUNCH;
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(Co)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(K) * 2};
+  const cuuint32_t box[2] = {kBK, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(w_r), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? B200_OK : B200_ERR_LAUNCH;
+}
+
 template <int MH>
 static int launch_fused(const DcnFusedParams &p, cudaStream_t stream) {
   using Cfg = FusedCfg<MH>;
@@ -395,7 +447,10 @@ static int launch_fused(const DcnFusedParams &p, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  dcn_fused_kernel<MH><<<grid, kFusedThreads, Cfg::kSmemBytes, stream>>>(p);
+  CUtensorMap tmap;
+  const int ts = make_weight_tmap(&tmap, p.w_r, p.Co, p.kh * p.kw * p.C);
+  if (ts != B200_OK) return ts;
+  dcn_fused_kernel<MH><<<grid, kFusedThreads, Cfg::kSmemBytes, stream>>>(p, tmap);
   return check_launch();
 }
 
@@ -428,11 +483,13 @@ int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias,
   p.B = batch, p.C = channels, p.H = height, p.W = width, p.Co = channels_out, p.kh = kernel_h, p.kw = kernel_w;
   p.pad_h = pad_h, p.pad_w = pad_w, p.stride_h = stride_h, p.stride_w = stride_w, p.dil_h = dilation_h,
   p.dil_w = dilation_w, p.Ho = Ho, p.Wo = Wo;
-  p.tiles_per_img = (Ho * Wo + kBN - 1) / kBN;
-  p.num_tiles = p.tiles_per_img * batch;
   p.kb_per_tap = channels / kBK;
   p.num_kb = kk * p.kb_per_tap;
-  switch (channels_out / 128) {
+  const int mh = channels_out / 128;
+  const int bn = mh == 1 ? FusedCfg<1>::kBN : (mh == 2 ? FusedCfg<2>::kBN : FusedCfg<4>::kBN);
+  p.tiles_per_img = (Ho * Wo + bn - 1) / bn;
+  p.num_tiles = p.tiles_per_img * batch;
+  switch (mh) {
     case 1: return launch_fused<1>(p, stream);
     case 2: return launch_fused<2>(p, stream);
     case 4: return launch_fused<4>(p, stream);
