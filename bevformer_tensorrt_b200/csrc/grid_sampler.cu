@@ -146,8 +146,10 @@ struct Pk<kI8x4> {  // kCHW4: [N, ceil(C/4), H, W, 4]; grid = (x, y, pad, pad) i
 };
 
 // ---- 2-D kernel -----------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(256) grid_sample_2d_kernel(const GsParams p) {
+// INTERP is a template parameter so that the bilinear kernel (the one BEVFormer uses) does not carry the bicubic
+// path's registers: 64 registers -> 4 CTAs of 256 threads per SM.
+template <int K, int INTERP>
+__global__ void __launch_bounds__(256, INTERP == 2 ? 2 : 4) grid_sample_2d_kernel(const GsParams p) {
   using P = Pk<K>;
   using T = typename P::T;
   constexpr int W = P::W;
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(256) grid_sample_2d_kernel(const GsParams p) {
     const T *in_n = static_cast<const T *>(p.in) + (n * p.CP + cp0) * plane_i;
     T *out_p = static_cast<T *>(p.out) + (n * p.CP + cp0) * plane_o + pix;
 
-    if (p.interp == 0) {  // bilinear (:700-740)
+    if (INTERP == 0) {  // bilinear (:700-740)
       const float ix = gs_source_index(gx, p.Wi, p.padding, align);
       const float iy = gs_source_index(gy, p.Hi, p.padding, align);
       const int ix_nw = static_cast<int>(floorf(ix)), iy_nw = static_cast<int>(floorf(iy));
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(256) grid_sample_2d_kernel(const GsParams p) {
         for (int i = 0; i < W; ++i) o[i] = fmaf(d[i], w_se, fmaf(c[i], w_sw, fmaf(b[i], w_ne, a[i] * w_nw)));
         P::store(op, o, so);
       }
-    } else if (p.interp == 1) {  // nearest (:741-756): ::round, half away from zero
+    } else if (INTERP == 1) {  // nearest (:741-756): ::round, half away from zero
       const float ix = gs_source_index(gx, p.Wi, p.padding, align);
       const float iy = gs_source_index(gy, p.Hi, p.padding, align);
       const int ixn = static_cast<int>(roundf(ix)), iyn = static_cast<int>(roundf(iy));
@@ -351,9 +353,14 @@ static int launch_gs(void *out, const void *in, const void *grid, const int *od,
   p.slices = (p.CP + p.cps - 1) / p.cps;
   const long long total = pixels * p.slices;
   const unsigned blocks = static_cast<unsigned>(total / 256 + 1 < (1 << 22) ? total / 256 + 1 : (1 << 22));
-  if (nb == 4)
-    grid_sample_2d_kernel<K><<<blocks, 256, 0, s>>>(p);
-  else
+  if (nb == 4) {
+    if (interp == 0)
+      grid_sample_2d_kernel<K, 0><<<blocks, 256, 0, s>>>(p);
+    else if (interp == 1)
+      grid_sample_2d_kernel<K, 1><<<blocks, 256, 0, s>>>(p);
+    else
+      grid_sample_2d_kernel<K, 2><<<blocks, 256, 0, s>>>(p);
+  } else
     grid_sample_3d_kernel<(K == kF16 ? kF16 : kF32)><<<blocks, 256, 0, s>>>(p);
   return check_launch();
 }
