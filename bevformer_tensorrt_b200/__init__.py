@@ -26,6 +26,7 @@ from .functions import (  # noqa: E402
     grid_sampler_int8,
     modulated_deformable_conv2d,
     modulated_deformable_conv2d2,
+    modulated_deformable_conv2d_int8,
     multi_scale_deformable_attn,
     multi_scale_deformable_attn2,
     multi_scale_deformable_attn_int8,
@@ -40,6 +41,7 @@ __all__ = [
     "grid_sampler_int8",
     "modulated_deformable_conv2d",
     "modulated_deformable_conv2d2",
+    "modulated_deformable_conv2d_int8",
     "multi_scale_deformable_attn",
     "multi_scale_deformable_attn2",
     "multi_scale_deformable_attn_int8",

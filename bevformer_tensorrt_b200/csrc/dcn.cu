@@ -31,6 +31,12 @@ int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias,
                   int channels_out, int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h,
                   int dilation_w, int dilation_h, int Ho, int Wo, cudaStream_t stream);
 
+int dcn_fused_i8(const int8_t *input, float scale_i, const int8_t *weight, float scale_w, const void *bias, int bias_is_half,
+                 const int8_t *offset, float scale_off, const int8_t *mask, float scale_mask, int8_t *output, float scale_o,
+                 void *workspace, int batch, int channels, int height, int width, int channels_out, int kernel_w,
+                 int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w, int dilation_h, int Ho,
+                 int Wo, cudaStream_t stream);
+
 static int g_dcn_fused = -1;  // -1: read B200_DCN_FUSED once (default on)
 static bool dcn_fused_enabled() {
   if (g_dcn_fused < 0) {
@@ -245,6 +251,28 @@ int b200_dcn_set_fused(int enabled) {
   const int prev = dcn_fused_enabled() ? 1 : 0;
   g_dcn_fused = enabled ? 1 : 0;
   return prev;
+}
+
+int b200_dcn_i8(const int8_t *input, float scale_i, const int8_t *weight, float scale_w, const void *bias, int bias_is_half,
+                const int8_t *offset, float scale_off, const int8_t *mask, float scale_mask, int8_t *output, float scale_o,
+                void *workspace, int batch, int channels, int height, int width, int channels_out, int kernel_w,
+                int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w, int dilation_h, int group,
+                int deformable_group, int im2col_step, void *cublas_handle, void *stream) {
+  (void)im2col_step, (void)cublas_handle;
+  if (!input || !weight || !offset || !mask || !output || !workspace) return B200_ERR_BAD_PARAM;
+  if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || channels_out <= 0 || kernel_w <= 0 || kernel_h <= 0 ||
+      stride_w <= 0 || stride_h <= 0 || dilation_w <= 0 || dilation_h <= 0 || !(scale_o > 0.f))
+    return B200_ERR_BAD_PARAM;
+  const int Ho = (height + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
+  const int Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
+  if (Ho <= 0 || Wo <= 0) return B200_ERR_BAD_PARAM;
+  // INT8 runs on the fused tensor-core path only (every DCN of the BEVFormer backbones qualifies)
+  if (!dcn_fused_supported(channels, channels_out, kernel_h * kernel_w, group, deformable_group) ||
+      reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
+    return B200_ERR_UNSUPPORTED;
+  return dcn_fused_i8(input, scale_i, weight, scale_w, bias, bias_is_half, offset, scale_off, mask, scale_mask, output,
+                      scale_o, workspace, batch, channels, height, width, channels_out, kernel_w, kernel_h, stride_w,
+                      stride_h, pad_w, pad_h, dilation_w, dilation_h, Ho, Wo, static_cast<cudaStream_t>(stream));
 }
 
 int b200_dcn_f32(const float *input, const float *weight, const float *bias, const float *offset, const float *mask,

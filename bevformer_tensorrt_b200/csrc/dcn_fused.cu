@@ -35,8 +35,10 @@ constexpr int kFusedThreads = (kProducerWarps + 2) * 32;  // + 1 MMA/TMEM warp +
 constexpr int kMaxTaps = 9;
 
 struct DcnFusedParams {
-  const __half *x_nhwc, *w_r, *bias, *offset, *mask;
-  __half *out;
+  const __half *x_nhwc, *w_r;
+  const void *bias, *offset, *mask;  // FP16 path: __half; INT8 path: offset/mask int8, bias float (converted by the host)
+  void *out;                         // FP16 path: __half; INT8 path: int8
+  float scale_off, scale_mask, out_mul, out_div;  // INT8 path: dequant scales; out = T2int8((acc*out_mul + bias)/out_div)
   int B, C, H, W, Co, kh, kw, pad_h, pad_w, stride_h, stride_w, dil_h, dil_w, Ho, Wo;
   int tiles_per_img, num_tiles, kb_per_tap, num_kb;
 };
@@ -171,7 +173,10 @@ struct FusedCfg {
   static_assert(kStages >= 2 && MH * kBN <= 512, "tile does not fit shared memory / TMEM");
 };
 
-template <int MH>
+// I8 = true: the INT8 plugin flavour computed by in-register dequantisation — the pre-passes hand this kernel the int8
+// activations / weights as (exact) fp16 integers, offsets and masks are dequantised while the sampling table is built,
+// the fp32 accumulators are rescaled by scale_in*scale_w, biased and requantised once (T2int8) in the epilogue.
+template <int MH, bool I8>
 __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFusedParams p,
                                                                      const __grid_constant__ CUtensorMap tmap_w) {
   using Cfg = FusedCfg<MH>;
@@ -279,9 +284,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
         if (pix < HoWo) {
           const int h_col = pix / p.Wo, w_col = pix - h_col * p.Wo;
           const int i = t / p.kw, j = t - i * p.kw;
-          const float oh = __half2float(__ldg(p.offset + (static_cast<long long>(b) * 2 * kk + 2 * t) * HoWo + pix));
-          const float ow = __half2float(__ldg(p.offset + (static_cast<long long>(b) * 2 * kk + 2 * t + 1) * HoWo + pix));
-          const float m = __half2float(__ldg(p.mask + (static_cast<long long>(b) * kk + t) * HoWo + pix));
+          const long long oi = (static_cast<long long>(b) * 2 * kk + 2 * t) * HoWo + pix;
+          const long long mi = (static_cast<long long>(b) * kk + t) * HoWo + pix;
+          float oh, ow, m;
+          if (I8) {  // off*scale rounded to fp32 first, like the reference INT8 im2col (…Conv2dKernel.cu:509-514)
+            oh = static_cast<float>(__ldg(static_cast<const int8_t *>(p.offset) + oi)) * p.scale_off;
+            ow = static_cast<float>(__ldg(static_cast<const int8_t *>(p.offset) + oi + HoWo)) * p.scale_off;
+            m = static_cast<float>(__ldg(static_cast<const int8_t *>(p.mask) + mi)) * p.scale_mask;
+          } else {
+            oh = __half2float(__ldg(static_cast<const __half *>(p.offset) + oi));
+            ow = __half2float(__ldg(static_cast<const __half *>(p.offset) + oi + HoWo));
+            m = __half2float(__ldg(static_cast<const __half *>(p.mask) + mi));
+          }
           const float h_im = __fadd_rn(static_cast<float>(h_col * p.stride_h - p.pad_h + i * p.dil_h), oh);
           const float w_im = __fadd_rn(static_cast<float>(w_col * p.stride_w - p.pad_w + j * p.dil_w), ow);
           if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(p.H) && w_im < static_cast<float>(p.W)) {
@@ -361,8 +375,37 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
       for (int u = warp >> 2; u < MH * (kBN / 32); u += kProducerWarps / 4) {
         const int mh = u / (kBN / 32), c0 = (u % (kBN / 32)) * 32;
         const int co = mh * 128 + quad * 32 + lane;
-        const float bias = __half2float(__ldg(p.bias + co));
-        __half *orow = p.out + (static_cast<long long>(b) * p.Co + co) * HoWo + p0;
+        if (I8) {
+          const float bias = __ldg(static_cast<const float *>(p.bias) + co);
+          int8_t *orow = static_cast<int8_t *>(p.out) + (static_cast<long long>(b) * p.Co + co) * HoWo + p0;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mh * kBN + c0, r);
+          // out = T2int8((acc * scale_i*scale_w + bias) / scale_o)   (…Conv2dKernel.cu:578-579)
+          if (p0 + c0 + 32 <= HoWo && (reinterpret_cast<uintptr_t>(orow + c0) & 15) == 0) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float real = fmaf(__uint_as_float(r[16 * v + 4 * q + i]), p.out_mul, bias);
+                  word |= (static_cast<uint32_t>(to_int8_sat(real / p.out_div)) & 0xffu) << (8 * i);
+                }
+                w4[q] = word;
+              }
+              *reinterpret_cast<uint4 *>(orow + c0 + 16 * v) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (p0 + c0 + i < HoWo)
+                orow[c0 + i] = static_cast<int8_t>(to_int8_sat(fmaf(__uint_as_float(r[i]), p.out_mul, bias) / p.out_div));
+          }
+        } else {
+        const float bias = __half2float(__ldg(static_cast<const __half *>(p.bias) + co));
+        __half *orow = static_cast<__half *>(p.out) + (static_cast<long long>(b) * p.Co + co) * HoWo + p0;
         {
           uint32_t r[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mh * kBN + c0, r);
@@ -381,6 +424,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
             for (int i = 0; i < 32; ++i)
               if (p0 + c0 + i < HoWo) orow[c0 + i] = __float2half_rn(__uint_as_float(r[i]) + bias);
           }
+        }
         }
       }
       tc_fence_before();
@@ -401,7 +445,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
 size_t dcn_fused_workspace_bytes(int batch, int channels, int height, int width, int channels_out, int kk) {
   const size_t x = (static_cast<size_t>(batch) * height * width * channels * 2 + 255) / 256 * 256;
   const size_t w = (static_cast<size_t>(channels_out) * channels * kk * 2 + 255) / 256 * 256;
-  return x + w + 1024;  // + a zero bias vector for the bias-less call (<= 512 channels x 2 B)
+  return x + w + 2048;  // + a zero / fp32 bias vector (<= 512 channels x 4 B)
 }
 
 bool dcn_fused_supported(int channels, int channels_out, int kk, int group, int deformable_group) {
@@ -433,12 +477,12 @@ static int make_weight_tmap(CUtensorMap *tm, const __half *w_r, int Co, int K) {
   return r == CUDA_SUCCESS ? B200_OK : B200_ERR_LAUNCH;
 }
 
-template <int MH>
+template <int MH, bool I8>
 static int launch_fused(const DcnFusedParams &p, cudaStream_t stream) {
   using Cfg = FusedCfg<MH>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(dcn_fused_kernel<MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
+    if (cudaFuncSetAttribute(dcn_fused_kernel<MH, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
         cudaSuccess)
       return B200_ERR_LAUNCH;
     configured = true;
@@ -450,7 +494,7 @@ static int launch_fused(const DcnFusedParams &p, cudaStream_t stream) {
   CUtensorMap tmap;
   const int ts = make_weight_tmap(&tmap, p.w_r, p.Co, p.kh * p.kw * p.C);
   if (ts != B200_OK) return ts;
-  dcn_fused_kernel<MH><<<grid, kFusedThreads, Cfg::kSmemBytes, stream>>>(p, tmap);
+  dcn_fused_kernel<MH, I8><<<grid, kFusedThreads, Cfg::kSmemBytes, stream>>>(p, tmap);
   return check_launch();
 }
 
@@ -490,9 +534,98 @@ int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias,
   p.tiles_per_img = (Ho * Wo + bn - 1) / bn;
   p.num_tiles = p.tiles_per_img * batch;
   switch (mh) {
-    case 1: return launch_fused<1>(p, stream);
-    case 2: return launch_fused<2>(p, stream);
-    case 4: return launch_fused<4>(p, stream);
+    case 1: return launch_fused<1, false>(p, stream);
+    case 2: return launch_fused<2, false>(p, stream);
+    case 4: return launch_fused<4, false>(p, stream);
+    default: return B200_ERR_UNSUPPORTED;
+  }
+}
+
+// ---- INT8 flavour: pre-passes + launch ---------------------------------------------------------------------------------
+// input kCHW4 int8 [B, C/4, H, W, 4] -> NHWC fp16 (the int8 values as exact fp16 integers)
+__global__ void __launch_bounds__(256) dcn_chw4_to_nhwc_f16_kernel(const int8_t *__restrict__ in, __half *__restrict__ out,
+                                                                   int C, int HW) {
+  // thread = (pixel, group of 8 channels = two CHW4 packs): two 4-byte loads, one 16-byte store
+  const long long total = static_cast<long long>(gridDim.z) * HW * (C / 8);
+  (void)total;
+  const int b = blockIdx.z;
+  const int c8 = blockIdx.y;  // group of 8 channels
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(in) + (static_cast<long long>(b) * (C / 4) + 2 * c8) * HW + p;
+  const uint32_t u0 = __ldg(src), u1 = __ldg(src + HW);
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    o[i] = f2_to_h2(static_cast<float>(static_cast<int8_t>(u0 >> (16 * i))),
+                    static_cast<float>(static_cast<int8_t>(u0 >> (16 * i + 8))));
+    o[2 + i] = f2_to_h2(static_cast<float>(static_cast<int8_t>(u1 >> (16 * i))),
+                        static_cast<float>(static_cast<int8_t>(u1 >> (16 * i + 8))));
+  }
+  *reinterpret_cast<uint4 *>(out + (static_cast<long long>(b) * HW + p) * C + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// weight kCHW4 int8 [Co, C/4, kh, kw, 4] -> Wr fp16 [Co][C/64][t][64]
+__global__ void dcn_weight_reorder_i8_kernel(const int8_t *__restrict__ w, __half *__restrict__ wr, int Co, int C, int kk) {
+  const long long n = static_cast<long long>(Co) * C * kk;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % kBK);
+    const int t = static_cast<int>((i / kBK) % kk);
+    const int cc = static_cast<int>((i / (static_cast<long long>(kBK) * kk)) % (C / kBK));
+    const long long co = i / (static_cast<long long>(C) * kk);
+    const int c = cc * kBK + ci;
+    wr[i] = __float2half_rn(static_cast<float>(w[((co * (C / 4) + c / 4) * kk + t) * 4 + (c & 3)]));
+  }
+}
+
+// bias (float or half, may be null) -> float vector
+__global__ void dcn_bias_to_f32_kernel(const void *bias, int is_half, float *out, int Co) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Co) out[i] = !bias ? 0.f : (is_half ? __half2float(static_cast<const __half *>(bias)[i]) : static_cast<const float *>(bias)[i]);
+}
+
+int dcn_fused_i8(const int8_t *input, float scale_i, const int8_t *weight, float scale_w, const void *bias, int bias_is_half,
+                 const int8_t *offset, float scale_off, const int8_t *mask, float scale_mask, int8_t *output, float scale_o,
+                 void *workspace, int batch, int channels, int height, int width, int channels_out, int kernel_w,
+                 int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w, int dilation_h, int Ho,
+                 int Wo, cudaStream_t stream) {
+  const int kk = kernel_h * kernel_w, HW = height * width;
+  uint8_t *ws = static_cast<uint8_t *>(workspace);
+  __half *x_nhwc = reinterpret_cast<__half *>(ws);
+  ws += (static_cast<size_t>(batch) * HW * channels * 2 + 255) / 256 * 256;
+  __half *w_r = reinterpret_cast<__half *>(ws);
+  ws += (static_cast<size_t>(channels_out) * channels * kk * 2 + 255) / 256 * 256;
+  float *bias_f = reinterpret_cast<float *>(ws);  // 512 floats fit the 2 KB tail reserved by dcn_fused_workspace_bytes
+
+  dcn_chw4_to_nhwc_f16_kernel<<<dim3((HW + 255) / 256, channels / 8, batch), 256, 0, stream>>>(input, x_nhwc, channels, HW);
+  int st = check_launch();
+  if (st != B200_OK) return st;
+  const long long wn = static_cast<long long>(channels_out) * channels * kk;
+  dcn_weight_reorder_i8_kernel<<<static_cast<unsigned>((wn + 255) / 256), 256, 0, stream>>>(weight, w_r, channels_out,
+                                                                                            channels, kk);
+  st = check_launch();
+  if (st != B200_OK) return st;
+  dcn_bias_to_f32_kernel<<<(channels_out + 255) / 256, 256, 0, stream>>>(bias, bias_is_half, bias_f, channels_out);
+  st = check_launch();
+  if (st != B200_OK) return st;
+
+  DcnFusedParams p{};
+  p.x_nhwc = x_nhwc, p.w_r = w_r, p.bias = bias_f, p.offset = offset, p.mask = mask, p.out = output;
+  p.scale_off = scale_off, p.scale_mask = scale_mask, p.out_mul = scale_i * scale_w, p.out_div = scale_o;
+  p.B = batch, p.C = channels, p.H = height, p.W = width, p.Co = channels_out, p.kh = kernel_h, p.kw = kernel_w;
+  p.pad_h = pad_h, p.pad_w = pad_w, p.stride_h = stride_h, p.stride_w = stride_w, p.dil_h = dilation_h,
+  p.dil_w = dilation_w, p.Ho = Ho, p.Wo = Wo;
+  p.kb_per_tap = channels / kBK;
+  p.num_kb = kk * p.kb_per_tap;
+  const int mh = channels_out / 128;
+  const int bn = mh == 1 ? FusedCfg<1>::kBN : (mh == 2 ? FusedCfg<2>::kBN : FusedCfg<4>::kBN);
+  p.tiles_per_img = (Ho * Wo + bn - 1) / bn;
+  p.num_tiles = p.tiles_per_img * batch;
+  switch (mh) {
+    case 1: return launch_fused<1, true>(p, stream);
+    case 2: return launch_fused<2, true>(p, stream);
+    case 4: return launch_fused<4, true>(p, stream);
     default: return B200_ERR_UNSUPPORTED;
   }
 }

@@ -2,7 +2,11 @@
 registry (det2trt/models/utils/register.py:9-69,86): ``TRT_FUNCTIONS.get("multi_scale_deformable_attn")`` etc."""
 from ..registry import TRT_FUNCTIONS
 from .grid_sampler import grid_sampler, grid_sampler2, grid_sampler_chw2, grid_sampler_int8
-from .modulated_deformable_conv2d import modulated_deformable_conv2d, modulated_deformable_conv2d2
+from .modulated_deformable_conv2d import (
+    modulated_deformable_conv2d,
+    modulated_deformable_conv2d2,
+    modulated_deformable_conv2d_int8,
+)
 from .multi_scale_deformable_attn import (
     multi_scale_deformable_attn,
     multi_scale_deformable_attn2,
@@ -17,6 +21,7 @@ TRT_FUNCTIONS.register_module(module=grid_sampler_int8)
 
 TRT_FUNCTIONS.register_module(module=modulated_deformable_conv2d)
 TRT_FUNCTIONS.register_module(module=modulated_deformable_conv2d2)
+TRT_FUNCTIONS.register_module(module=modulated_deformable_conv2d_int8)
 
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn2)

@@ -80,3 +80,36 @@ def modulated_deformable_conv2d2(input, offset, mask, weight, bias=None, stride=
     """Plugin ModulatedDeformableConv2dTRT2 (FP16 as half2). Same contract as the reference wrapper (:251-291)."""
     return _ModulatedDeformableConv2dFunction2.apply(input, offset, mask, weight, bias, stride, padding, dilation,
                                                      groups, deform_groups)  # fmt: skip
+
+
+def modulated_deformable_conv2d_int8(input_chw4, scale_i, offset_q, scale_off, mask_q, scale_mask, weight_chw4, scale_w,
+                                     bias, scale_o, channels, stride=1, padding=0, dilation=1, groups=1, deform_groups=1):
+    """INT8 flavour of the plugin (…Conv2dPlugin.cpp:117-199 / launcher …Conv2dKernel.h:21-29): ``input_chw4`` int8
+    [N, C/4, H, W, 4] and ``weight_chw4`` int8 [Co, C/4, kh, kw, 4] in TensorRT's kCHW4 layout
+    (``functions.grid_sampler.pack_chw(x, 4)``), ``offset_q`` / ``mask_q`` int8 NCHW, per-tensor scales
+    (real = q*scale), ``bias`` float32/float16 or None. Returns int8 [N, Co, Ho, Wo] at ``scale_o``."""
+    assert input_chw4.is_cuda and input_chw4.dtype == torch.int8 and input_chw4.shape[-1] == 4
+    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
+    n, c4, h, w, _ = input_chw4.shape
+    co, _, kh, kw, _ = weight_chw4.shape
+    if c4 * 4 != channels or weight_chw4.shape[1] * 4 * groups != channels:
+        raise ValueError("channels must be a multiple of 4 and match the packed tensors")
+    ho = (h + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    wo = (w + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    lib = _lib.load()
+    ws_bytes = lib.b200_dcn_workspace_size(1, n, channels, h, w, kw, kh, sw, sh, pw, ph, dw, dh)
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=input_chw4.device)
+    out = torch.empty(n, co, ho, wo, dtype=torch.int8, device=input_chw4.device)
+    x, wt, off, msk = (t.contiguous() for t in (input_chw4, weight_chw4, offset_q, mask_q))
+    bias_t = bias.contiguous() if bias is not None else None
+    if bias_t is not None and bias_t.dtype not in (torch.float32, torch.float16):
+        raise _lib.B200OpsError("modulated_deformable_conv2d_int8", 1)
+    with torch.cuda.device(x.device):
+        st = lib.b200_dcn_i8(x.data_ptr(), float(scale_i), wt.data_ptr(), float(scale_w),
+                             bias_t.data_ptr() if bias_t is not None else None,
+                             int(bias_t is not None and bias_t.dtype == torch.float16), off.data_ptr(), float(scale_off),
+                             msk.data_ptr(), float(scale_mask), out.data_ptr(), float(scale_o), workspace.data_ptr(), n,
+                             channels, h, w, co, kw, kh, sw, sh, pw, ph, dw, dh, groups, deform_groups, min(n, 32), None,
+                             _lib.current_stream_ptr())  # fmt: skip
+    _lib.check("b200_dcn_i8", st)
+    return out

@@ -206,6 +206,20 @@ int b200_dcn_f32(const float *input, const float *weight, const float *bias, con
                  int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
                  int dilation_h, int group, int deformable_group, int im2col_step, void *cublas_handle, void *stream);
 
+/* replaces ModulatedDeformConvForwardCUDAKernel_int8<float> / <__half> — …Conv2dKernel.h:21-29, .cu:897-978.
+ * input int8 kCHW4 [batch, channels/4, H, W, 4], weight int8 kCHW4 [channels_out, channels/4, kh, kw, 4], offset / mask
+ * int8 kLINEAR, output int8 kLINEAR, per-tensor scales (real = q*scale); bias float (bias_is_half == 0), __half, or NULL.
+ * Arithmetic: in-register dequantisation (int8 values are exact in FP16), FP16 tensor-core products with FP32
+ * accumulation, one requantisation T2int8((acc*scale_i*scale_w + bias)/scale_o) — the reference requantises the
+ * sampled columns to int8 first (:536-545). Runs on the fused path only: groups == deformable_groups == 1,
+ * channels % 64 == 0, channels_out in {128, 256, 512}; B200_ERR_UNSUPPORTED otherwise. workspace: b200_dcn_workspace_size
+ * with dtype 1. */
+int b200_dcn_i8(const int8_t *input, float scale_i, const int8_t *weight, float scale_w, const void *bias, int bias_is_half,
+                const int8_t *offset, float scale_off, const int8_t *mask, float scale_mask, int8_t *output, float scale_o,
+                void *workspace, int batch, int channels, int height, int width, int channels_out, int kernel_w,
+                int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w, int dilation_h, int group,
+                int deformable_group, int im2col_step, void *cublas_handle, void *stream);
+
 /* replaces ModulatedDeformConvForwardCUDAKernel<__half> / <__half2> — …Conv2dKernel.cu:762-895 (kLINEAR tensors) */
 int b200_dcn_f16(const void *input, const void *weight, const void *bias, const void *offset, const void *mask,
                  void *output, void *workspace, int batch, int channels, int height, int width, int channels_out,

@@ -73,6 +73,17 @@ def main():
         out["torchvision_deform_conv2d_f16"] = {"us": us}
     except Exception as e:  # noqa: BLE001
         out["torchvision_deform_conv2d_f16"] = {"error": str(e)[:100]}
+    # the other MSDA call sites of BEVFormer-base: TSA (2 x 40000 queries, 1 level 200x200, 4 points)
+    # and the decoder (900 queries)
+    from bevformer_tensorrt_b200.workloads import CONFIGS, make_msda_inputs
+
+    for name in ("base_tsa", "base_decoder", "tiny_sca"):
+        cfg = CONFIGS[name]
+        for dt, tag in ((torch.float16, "f16"), (torch.float32, "f32")):
+            ins = [t.cuda() for t in make_msda_inputs(cfg, "U", 0, dt)]
+            us = timeit(lambda: bt.multi_scale_deformable_attn(*ins), n=20)
+            nbytes = cfg.algorithmic_bytes(2 if dt == torch.float16 else 4)
+            out[f"msda_{name}_{tag}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
     print(json.dumps(out))
 
 

@@ -129,3 +129,34 @@ def test_error_behaviour():
     assert lib.b200_dcn_f32(1, 1, None, 1, 1, 1, 1, 1, 6, 4, 4, 4, 3, 3, 1, 1, 1, 1, 1, 1, 4, 1, 1, None, None) == 1
     assert lib.b200_dcn_f32(None, None, None, None, None, None, None, 1, 4, 4, 4, 4, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1,
                             None, None) == 2
+
+
+@pytest.mark.parametrize("bias_dtype", [torch.float32, torch.float16, None])
+@pytest.mark.parametrize("case", ["fused_co128", "fused_co256_ragged", "fused_co512_s2"])
+def test_int8_matches_dequant_oracle(case, bias_dtype):
+    """INT8 DCN: int8 kCHW4 input / weight, int8 offset / mask, per-tensor MinMax scales; checked against the FP32
+    formulas on the dequantised tensors, requantised with T2int8. Tolerance: the FP16 rounding of the sampled columns
+    (2^-11 relative on values <= 127 in input-scale units) summed over K, expressed in output steps."""
+    from bevformer_tensorrt_b200.functions.grid_sampler import pack_chw
+    from bevformer_tensorrt_b200.workloads import quantize_per_tensor
+
+    x, off, mask, w, b, kw = make_dcn_inputs(case)
+    xq, si = quantize_per_tensor(x)
+    oq, so_ = quantize_per_tensor(off)
+    mq, sm = quantize_per_tensor(mask)
+    wq, sw = quantize_per_tensor(w)
+    bias = None if bias_dtype is None else b.to(bias_dtype)
+    real = odcn.modulated_deformable_conv2d(xq.float().numpy() * si, oq.float().numpy() * so_, mq.float().numpy() * sm,
+                                            wq.float().numpy() * sw, None if bias is None else bias.float().numpy(), **kw)
+    sout = float(np.abs(real).max()) / 127.0
+    got = bt.modulated_deformable_conv2d_int8(
+        pack_chw(xq, 4).cuda(), si, oq.cuda(), so_, mq.cuda(), sm, pack_chw(wq, 4).cuda(), sw,
+        None if bias is None else bias.cuda(), sout, x.shape[1], kw["stride"], kw["padding"], kw["dilation"], 1, 1)
+    assert got.dtype == torch.int8 and tuple(got.shape) == real.shape
+    err = np.abs(got.cpu().numpy().astype(np.float32) * sout - real).max()
+    assert err <= 0.75 * sout, (err, sout)  # half a step from the requantisation + fp16 column rounding
+    # unsupported shapes are a status, not a crash
+    with pytest.raises(_lib.B200OpsError):
+        bt.modulated_deformable_conv2d_int8(pack_chw(xq, 4).cuda(), si, oq.cuda(), so_, mq.cuda(), sm,
+                                            pack_chw(wq, 4).cuda(), sw, None, sout, x.shape[1], kw["stride"],
+                                            kw["padding"], kw["dilation"], 2, 1)
