@@ -159,4 +159,4 @@ def test_int8_matches_dequant_oracle(case, bias_dtype):
     with pytest.raises(_lib.B200OpsError):
         bt.modulated_deformable_conv2d_int8(pack_chw(xq, 4).cuda(), si, oq.cuda(), so_, mq.cuda(), sm,
                                             pack_chw(wq, 4).cuda(), sw, None, sout, x.shape[1], kw["stride"],
-                                            kw["padding"], kw["dilation"], 2, 1)
+                                            kw["padding"], kw["dilation"], 1, 2)  # deform_groups = 2: not on the fused path
