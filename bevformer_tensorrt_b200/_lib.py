@@ -53,6 +53,8 @@ SIGNATURES = {
     "b200_msda_supports_format": (_i, [_i, ctypes.POINTER(TensorDesc), _i, _i]),
     "b200_dcn_workspace_size": (ctypes.c_size_t, [_i] * 13),
     "b200_dcn_set_fused": (_i, [_i]),
+    "b200_dcn_pack_weights_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200_dcn_f16_ex": (_i, [_vp] * 7 + [_i] * 16 + [_vp]),
     "b200_dcn_i8": (_i, [_vp, _f, _vp, _f, _vp, _i, _vp, _f, _vp, _f, _vp, _f, _vp] + [_i] * 16 + [_vp, _vp]),
     "b200_dcn_f32": (_i, [_vp] * 7 + [_i] * 16 + [_vp, _vp]),
     "b200_dcn_f16": (_i, [_vp] * 7 + [_i] * 16 + [_vp, _vp]),

@@ -29,7 +29,8 @@ bool dcn_fused_supported(int channels, int channels_out, int kk, int group, int 
 int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias, const __half *offset,
                   const __half *mask, __half *output, void *workspace, int batch, int channels, int height, int width,
                   int channels_out, int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h,
-                  int dilation_w, int dilation_h, int Ho, int Wo, cudaStream_t stream);
+                  int dilation_w, int dilation_h, int Ho, int Wo, int flags, cudaStream_t stream);
+int dcn_pack_weights_f16(const __half *weight, __half *packed, int channels_out, int channels, int kk, cudaStream_t stream);
 
 int dcn_fused_i8(const int8_t *input, float scale_i, const int8_t *weight, float scale_w, const void *bias, int bias_is_half,
                  const int8_t *offset, float scale_off, const int8_t *mask, float scale_mask, int8_t *output, float scale_o,
@@ -177,7 +178,7 @@ static int dcn_forward(const T *input, const T *weight, const T *bias, const T *
                          reinterpret_cast<const __half *>(bias), reinterpret_cast<const __half *>(offset),
                          reinterpret_cast<const __half *>(mask), reinterpret_cast<__half *>(output), workspace, batch,
                          channels, height, width, channels_out, kernel_w, kernel_h, stride_w, stride_h, pad_w, pad_h,
-                         dilation_w, dilation_h, Ho, Wo, stream);
+                         dilation_w, dilation_h, Ho, Wo, 0, stream);
 
   DcnParams p{};
   p.im = input, p.offset = offset, p.mask = mask, p.col = workspace;
@@ -247,10 +248,40 @@ size_t b200_dcn_workspace_size(int dtype, int batch, int channels, int height, i
   return v1 > fused ? v1 : fused;
 }
 
-int b200_dcn_set_fused(int enabled) {
+int b200_dcn_set_fused(int enabled) {  // enabled < 0: query only
   const int prev = dcn_fused_enabled() ? 1 : 0;
-  g_dcn_fused = enabled ? 1 : 0;
+  if (enabled >= 0) g_dcn_fused = enabled ? 1 : 0;
   return prev;
+}
+
+int b200_dcn_pack_weights_f16(const void *weight, void *packed, int channels_out, int channels, int kernel_h, int kernel_w,
+                              void *stream) {
+  if (!weight || !packed || channels_out <= 0 || channels <= 0 || kernel_h <= 0 || kernel_w <= 0) return B200_ERR_BAD_PARAM;
+  if (!dcn_fused_supported(channels, channels_out, kernel_h * kernel_w, 1, 1)) return B200_ERR_UNSUPPORTED;
+  return dcn_pack_weights_f16(static_cast<const __half *>(weight), static_cast<__half *>(packed), channels_out, channels,
+                              kernel_h * kernel_w, static_cast<cudaStream_t>(stream));
+}
+
+int b200_dcn_f16_ex(const void *input, const void *weight, const void *bias, const void *offset, const void *mask,
+                    void *output, void *workspace, int batch, int channels, int height, int width, int channels_out,
+                    int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                    int dilation_h, int group, int deformable_group, int flags, void *stream) {
+  if (!input || !weight || !offset || !mask || !output || !workspace) return B200_ERR_BAD_PARAM;
+  if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || channels_out <= 0 || kernel_w <= 0 || kernel_h <= 0 ||
+      stride_w <= 0 || stride_h <= 0 || dilation_w <= 0 || dilation_h <= 0)
+    return B200_ERR_BAD_PARAM;
+  const int Ho = (height + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
+  const int Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
+  if (Ho <= 0 || Wo <= 0) return B200_ERR_BAD_PARAM;
+  if (!dcn_fused_supported(channels, channels_out, kernel_h * kernel_w, group, deformable_group) ||
+      reinterpret_cast<uintptr_t>(workspace) % 256 != 0 || reinterpret_cast<uintptr_t>(input) % 16 != 0 ||
+      reinterpret_cast<uintptr_t>(weight) % 16 != 0)
+    return B200_ERR_UNSUPPORTED;
+  return dcn_fused_f16(static_cast<const __half *>(input), static_cast<const __half *>(weight),
+                       static_cast<const __half *>(bias), static_cast<const __half *>(offset),
+                       static_cast<const __half *>(mask), static_cast<__half *>(output), workspace, batch, channels,
+                       height, width, channels_out, kernel_w, kernel_h, stride_w, stride_h, pad_w, pad_h, dilation_w,
+                       dilation_h, Ho, Wo, flags, static_cast<cudaStream_t>(stream));
 }
 
 int b200_dcn_i8(const int8_t *input, float scale_i, const int8_t *weight, float scale_w, const void *bias, int bias_is_half,

@@ -501,7 +501,8 @@ static int launch_fused(const DcnFusedParams &p, cudaStream_t stream) {
 int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias, const __half *offset,
                   const __half *mask, __half *output, void *workspace, int batch, int channels, int height, int width,
                   int channels_out, int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h,
-                  int dilation_w, int dilation_h, int Ho, int Wo, cudaStream_t stream) {
+                  int dilation_w, int dilation_h, int Ho, int Wo, int flags, cudaStream_t stream) {
+  // flags: bit 0 = `input` is already NHWC (channels-last), bit 1 = `weight` is already permuted (b200_dcn_pack_weights_f16)
   const int kk = kernel_h * kernel_w, HW = height * width;
   __half *x_nhwc = static_cast<__half *>(workspace);
   __half *w_r = reinterpret_cast<__half *>(static_cast<uint8_t *>(workspace) +
@@ -512,15 +513,23 @@ int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias,
     if (cudaMemsetAsync(zb, 0, static_cast<size_t>(channels_out) * 2, stream) != cudaSuccess) return B200_ERR_LAUNCH;
     bias = zb;
   }
-  dcn_nchw_to_nhwc_kernel<<<dim3((HW + 63) / 64, channels / 64, batch), 512, 0, stream>>>(input, x_nhwc, channels,
-                                                                                                  HW);
-  int st = check_launch();
-  if (st != B200_OK) return st;
-  const long long wn = static_cast<long long>(channels_out) * channels * kk;
-  dcn_weight_reorder_kernel<<<static_cast<unsigned>((wn + 255) / 256), 256, 0, stream>>>(weight, w_r, channels_out,
-                                                                                         channels, kk);
-  st = check_launch();
-  if (st != B200_OK) return st;
+  int st = B200_OK;
+  if (flags & 1) {
+    x_nhwc = const_cast<__half *>(input);
+  } else {
+    dcn_nchw_to_nhwc_kernel<<<dim3((HW + 63) / 64, channels / 64, batch), 512, 0, stream>>>(input, x_nhwc, channels, HW);
+    st = check_launch();
+    if (st != B200_OK) return st;
+  }
+  if (flags & 2) {
+    w_r = const_cast<__half *>(weight);
+  } else {
+    const long long wn = static_cast<long long>(channels_out) * channels * kk;
+    dcn_weight_reorder_kernel<<<static_cast<unsigned>((wn + 255) / 256), 256, 0, stream>>>(weight, w_r, channels_out,
+                                                                                           channels, kk);
+    st = check_launch();
+    if (st != B200_OK) return st;
+  }
 
   DcnFusedParams p{};
   p.x_nhwc = x_nhwc, p.w_r = w_r, p.bias = bias, p.offset = offset, p.mask = mask, p.out = output;
@@ -539,6 +548,13 @@ int dcn_fused_f16(const __half *input, const __half *weight, const __half *bias,
     case 4: return launch_fused<4, false>(p, stream);
     default: return B200_ERR_UNSUPPORTED;
   }
+}
+
+int dcn_pack_weights_f16(const __half *weight, __half *packed, int channels_out, int channels, int kk, cudaStream_t stream) {
+  const long long wn = static_cast<long long>(channels_out) * channels * kk;
+  dcn_weight_reorder_kernel<<<static_cast<unsigned>((wn + 255) / 256), 256, 0, stream>>>(weight, packed, channels_out,
+                                                                                         channels, kk);
+  return check_launch();
 }
 
 // ---- INT8 flavour: pre-passes + launch ---------------------------------------------------------------------------------

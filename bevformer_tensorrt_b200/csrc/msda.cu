@@ -338,6 +338,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
   const T *lg_item = static_cast<const T *>(prm.logits) + it * NP;
   T *out_item = static_cast<T *>(prm.out) + it * C + sub * VEC;
 
+  if (EPI == 1) {
+    // Fused SCA epilogue: a (camera, query) pair with bev_mask == 0 contributes exactly nothing, whatever it samples.
+    // When that holds for every item of the warp (one query x 8 heads share the mask value) nothing is read at all —
+    // for a camera ring about 4 of 5 warps leave here.
+    const float mk0 = __ldg(prm.mask + bq);
+    if (__ballot_sync(kFullMask, active && mk0 != 0.f) == 0u) return;
+  }
+
   // Level table, per warp and without any block barrier: lane l < L holds (H_l, W_l) and the exclusive prefix sum of
   // H*W (the level's first pixel); consumers fetch their level's entry with shuffles. All global loads of the prologue
   // (shapes, reference points, offsets) are independent, so a warp pays one memory latency before it can decide whether

@@ -33,6 +33,10 @@ def _forward(input, offset, mask, weight, bias, stride, padding, dilation, group
     if tuple(mask.shape) != (n, deform_groups * kh * kw, ho, wo):
         raise ValueError(f"mask must be {(n, deform_groups * kh * kw, ho, wo)}, got {tuple(mask.shape)}")
     lib = _lib.load()
+    fused = (dt == torch.float16 and groups == 1 and deform_groups == 1 and c % 64 == 0 and co in (128, 256, 512)
+             and kh * kw <= 9 and lib.b200_dcn_set_fused(-1) == 1)
+    if fused:
+        return _forward_fused_f16(lib, input, offset, mask, weight, bias, (sh, sw), (ph, pw), (dh, dw), (ho, wo))
     input, offset, mask, weight = (t.to(dt).contiguous() for t in (input, offset, mask, weight))
     bias_t = bias.to(dt).contiguous() if bias is not None else None
     ws_bytes = lib.b200_dcn_workspace_size(int(dt == torch.float16), n, c, h, w, kw, kh, sw, sh, pw, ph, dw, dh)
@@ -45,6 +49,53 @@ def _forward(input, offset, mask, weight, bias, stride, padding, dilation, group
                                 co, kw, kh, sw, sh, pw, ph, dw, dh, groups, deform_groups, min(n, 32), None,
                                 _lib.current_stream_ptr())  # fmt: skip
     _lib.check(name, st)
+    return out
+
+
+_PACKED = {}  # (weight storage ptr, version, shape) -> weights permuted for the fused kernel (constant at inference)
+
+
+def _packed_weight(lib, weight):
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
+    hit = _PACKED.get(key)
+    if hit is None:
+        if len(_PACKED) > 256:
+            _PACKED.clear()
+        co, c, kh, kw = weight.shape
+        hit = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        with torch.cuda.device(weight.device):
+            _lib.check("b200_dcn_pack_weights_f16",
+                       lib.b200_dcn_pack_weights_f16(weight.data_ptr(), hit.data_ptr(), co, c, kh, kw,
+                                                     _lib.current_stream_ptr()))  # fmt: skip
+        _PACKED[key] = hit
+    return hit
+
+
+def _forward_fused_f16(lib, input, offset, mask, weight, bias, stride, padding, dilation, out_hw):
+    """FP16 fused tensor-core path: the weight permutation is cached per weight tensor, and a channels-last input is
+    consumed in place (no NCHW->NHWC pre-pass)."""
+    n, c, h, w = input.shape
+    co, _, kh, kw = weight.shape
+    dt = torch.float16
+    flags = 2
+    if input.is_contiguous(memory_format=torch.channels_last) and not input.is_contiguous():
+        flags |= 1  # NHWC bytes already
+        x = input
+    else:
+        x = input.contiguous()
+    wp = _packed_weight(lib, weight.contiguous())
+    offset, mask = offset.to(dt).contiguous(), mask.to(dt).contiguous()
+    bias_t = bias.to(dt).contiguous() if bias is not None else None
+    ws_bytes = lib.b200_dcn_workspace_size(1, n, c, h, w, kw, kh, stride[1], stride[0], padding[1], padding[0],
+                                           dilation[1], dilation[0])  # fmt: skip
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=input.device)
+    out = torch.empty(n, co, out_hw[0], out_hw[1], dtype=dt, device=input.device)
+    with torch.cuda.device(input.device):
+        st = lib.b200_dcn_f16_ex(x.data_ptr(), wp.data_ptr(), bias_t.data_ptr() if bias_t is not None else None,
+                                 offset.data_ptr(), mask.data_ptr(), out.data_ptr(), workspace.data_ptr(), n, c, h, w, co,
+                                 kw, kh, stride[1], stride[0], padding[1], padding[0], dilation[1], dilation[0], 1, 1,
+                                 flags, _lib.current_stream_ptr())  # fmt: skip
+    _lib.check("b200_dcn_f16_ex", st)
     return out
 
 

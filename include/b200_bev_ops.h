@@ -197,7 +197,8 @@ size_t b200_dcn_workspace_size(int dtype /* 0 f32, 1 f16 */, int batch, int chan
 
 /* FP16 runs as one fused implicit GEMM on tcgen05 tensor cores (csrc/dcn_fused.cu) when groups == deformable_groups == 1,
  * channels % 64 == 0 and channels_out in {128, 256, 512}; otherwise (and for FP32) as gather + cuBLAS GEMM.
- * b200_dcn_set_fused(0) forces the second path (A/B measurements); returns the previous setting. */
+ * b200_dcn_set_fused(0) forces the second path (A/B measurements), a negative argument only queries; returns the
+ * previous setting. */
 int b200_dcn_set_fused(int enabled);
 
 /* replaces ModulatedDeformConvForwardCUDAKernel<float> — …Conv2dKernel.cu:695-760 */
@@ -205,6 +206,18 @@ int b200_dcn_f32(const float *input, const float *weight, const float *bias, con
                  float *output, void *workspace, int batch, int channels, int height, int width, int channels_out,
                  int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
                  int dilation_h, int group, int deformable_group, int im2col_step, void *cublas_handle, void *stream);
+
+/* Deployment helpers for the fused FP16 path (beyond the reference's launcher set): weights are constants at inference
+ * time and feature maps may already be channels-last, so both pre-passes of b200_dcn_f16 can be hoisted out of the call.
+ *   b200_dcn_pack_weights_f16: weight [Co, C, kh, kw] -> packed [Co][C/64][kh*kw][64] (same byte size), once per layer.
+ *   b200_dcn_f16_ex: flags bit 0 = `input` is NHWC [batch, H, W, channels]; bit 1 = `weight` is already packed.
+ *   Fused path only (see b200_dcn_set_fused): returns B200_ERR_UNSUPPORTED for other shapes. */
+int b200_dcn_pack_weights_f16(const void *weight, void *packed, int channels_out, int channels, int kernel_h, int kernel_w,
+                              void *stream);
+int b200_dcn_f16_ex(const void *input, const void *weight, const void *bias, const void *offset, const void *mask,
+                    void *output, void *workspace, int batch, int channels, int height, int width, int channels_out,
+                    int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                    int dilation_h, int group, int deformable_group, int flags, void *stream);
 
 /* replaces ModulatedDeformConvForwardCUDAKernel_int8<float> / <__half> — …Conv2dKernel.h:21-29, .cu:897-978.
  * input int8 kCHW4 [batch, channels/4, H, W, 4], weight int8 kCHW4 [channels_out, channels/4, kh, kw, 4], offset / mask

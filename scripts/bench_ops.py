@@ -66,6 +66,11 @@ def main():
         args = [cast(t) for t in (xd, off, mask, w, b)]
         us = timeit(lambda: bt.modulated_deformable_conv2d(*args, 1, 1, 1, 1, 1), n=20)
         out[f"dcn_{name}"] = {"us": us, "tflops": flops / (us * 1e-6) / 1e12, "tensor_frac_of_bf16_peak": flops / (us * 1e-6) / 1e12 / peak["bf16_tflops"]}
+    xcl = xd.half().contiguous(memory_format=torch.channels_last)
+    a16 = [t.half() for t in (off, mask, w, b)]
+    us = timeit(lambda: bt.modulated_deformable_conv2d(xcl, *a16, 1, 1, 1, 1, 1), n=20)
+    out["dcn_f16_channels_last_input"] = {"us": us, "tflops": flops / (us * 1e-6) / 1e12,
+                                          "tensor_frac_of_bf16_peak": flops / (us * 1e-6) / 1e12 / peak["bf16_tflops"]}
     try:
         import torchvision
 

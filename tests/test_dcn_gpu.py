@@ -59,6 +59,20 @@ def test_fp16_fused_tcgen05_path_matches_oracle_and_gather_gemm_path(case):
     assert np.abs(nb.float().cpu().numpy() - (want - b.float().numpy()[None, :, None, None])).max() < tol
 
 
+def test_fp16_fused_channels_last_input_and_packed_weight_cache():
+    x, off, mask, w, b, kw = make_dcn_inputs("fused_co256_ragged", dtype=torch.float16)
+    args = [t.cuda() for t in (x, off, mask, w, b)]
+    want = bt.modulated_deformable_conv2d(*args, kw["stride"], kw["padding"], kw["dilation"], 1, 1)
+    x_cl = args[0].contiguous(memory_format=torch.channels_last)  # NHWC bytes: consumed without the transpose pre-pass
+    got = bt.modulated_deformable_conv2d(x_cl, *args[1:], kw["stride"], kw["padding"], kw["dilation"], 1, 1)
+    assert torch.equal(got, want)
+    again = bt.modulated_deformable_conv2d(*args, kw["stride"], kw["padding"], kw["dilation"], 1, 1)  # cached weights
+    assert torch.equal(again, want)
+    args[3].mul_(2.0)  # in-place weight update bumps the version: the cache must not serve stale weights
+    upd = bt.modulated_deformable_conv2d(*args, kw["stride"], kw["padding"], kw["dilation"], 1, 1)
+    assert not torch.equal(upd, want)
+
+
 @pytest.mark.parametrize("case", ["k3_s1_p1_g2_dg2", "backbone_like", "k3_s2_p1_g1_dg1"])
 def test_fp16_matches_oracle(case):
     x, off, mask, w, b, kw = make_dcn_inputs(case, dtype=torch.float16)
