@@ -93,7 +93,7 @@ class ShardedSCASampler:
     """
 
     def __init__(self, units, num_query: int, msda: Callable, group=None, accum_dtype: torch.dtype = torch.float32,
-                 fused_sca: Callable = None, chunk_bounds=None):  # fmt: skip
+                 fused_sca: Callable = None, chunk_bounds=None, wire_dtype: torch.dtype = None):  # fmt: skip
         chunked = len(units) > 0 and isinstance(units[0], (list, tuple))
         self.chunk_units = [merge_units(u) for u in units] if chunked else [merge_units(units)]
         self.num_query = num_query
@@ -101,6 +101,10 @@ class ShardedSCASampler:
         self.group = group
         self.accum_dtype = accum_dtype
         self.fused_sca = fused_sca if accum_dtype == torch.float32 else None
+        # dtype on the wire: every rank accumulates in accum_dtype (fp32); with wire_dtype=float16 the partial sums are
+        # rounded once to fp16 for the collective (half the NVLink bytes) and the reduced result is widened back
+        self.wire_dtype = wire_dtype if wire_dtype not in (None, accum_dtype) else None
+        self._wire = None
         # the accumulator slice every rank reduces for chunk k — must be identical on all ranks (plan_chunk_bounds)
         self.chunk_bounds = list(chunk_bounds) if chunk_bounds is not None else None
         if chunked and self.chunk_bounds is None:
@@ -128,6 +132,8 @@ class ShardedSCASampler:
             self.chunks.append((lo, hi, groups, local))
         M, C = value.shape[2], value.shape[3]
         self.accum = torch.zeros(self.num_query, M * C, dtype=self.accum_dtype, device=device)
+        if self.wire_dtype is not None:
+            self._wire = torch.empty(self.num_query, M * C, dtype=self.wire_dtype, device=device)
         return self
 
     def _compute(self, groups, local):
@@ -150,9 +156,15 @@ class ShardedSCASampler:
         for lo, hi, groups, local in self.chunks:
             self._compute(groups, local)
             if do_reduce and hi > lo:
-                works.append(dist.all_reduce(self.accum[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                buf = self.accum[lo:hi]
+                if self._wire is not None:
+                    buf = self._wire[lo:hi]
+                    buf.copy_(self.accum[lo:hi])
+                works.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group,
                                              async_op=len(self.chunks) > 1))  # fmt: skip
         for w in works:
             if w is not None:
                 w.wait()
+        if do_reduce and self._wire is not None:
+            self.accum.copy_(self._wire)
         return self.accum

@@ -79,6 +79,10 @@ def _worker(rank, world, port, q):
     s2 = ShardedSCASampler([c[rank] for c in cplan], CFG.num_query, _oracle_op,
                            chunk_bounds=plan_chunk_bounds(cplan)).load(value, shapes, ref, off, logits, mask, "cpu")
     err = max(err, float((s2.step() - want).abs().max()))
+    # fp16 on the wire: partial sums rounded once to fp16 for the collective
+    s3 = ShardedSCASampler(plan[rank], CFG.num_query, _oracle_op, wire_dtype=torch.float16).load(
+        value, shapes, ref, off, logits, mask, "cpu")
+    assert float((s3.step() - want).abs().max()) < 2e-3
     q.put((rank, err, float(want.abs().max())))
     dist.destroy_process_group()
 
