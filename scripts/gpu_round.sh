@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU visit: parity tests, bench line, ncu launch list + one full capture of the top kernel.
+# One GPU visit: parity tests, smoke, bench lines, op timings, ncu launch list + full captures of the top kernels.
 # Usage (from the build box): gpurun --timeout 1500 -- 'bash scripts/gpu_round.sh [tag]'
 TAG=${1:-r01}
 OUT=gpurun_out
@@ -7,14 +7,18 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/${TAG}_smi.csv 2>&1
 python -c "import os; print('cpus', os.cpu_count())" >> $OUT/${TAG}_smi.csv
 lscpu | grep -E "Model name|^CPU\(s\)" >> $OUT/${TAG}_smi.csv
-( time python -m pytest tests -m gpu -q -s 2>&1 | tail -80 ) > $OUT/${TAG}_pytest.log 2>&1
+( time python -m pytest tests -m gpu -q -s 2>&1 | tail -40 ) > $OUT/${TAG}_pytest.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1
 python bench.py --steps 100 --warmup 10 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 python bench.py --steps 100 --warmup 10 --dist G --no-secondary --no-cpu-baseline > $OUT/${TAG}_bench_G.json 2>> $OUT/${TAG}_bench.err
+python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference.json 2>> $OUT/${TAG}_bench.err
+python scripts/bench_ops.py > $OUT/${TAG}_ops.json 2>> $OUT/${TAG}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -s 5 -c 40 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 10 --warmup 3 --no-secondary --no-cpu-baseline --e2e-steps 1 > $OUT/${TAG}_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:msda_gather -s 4 -c 1 -o $OUT/${TAG}_prof_U -f \
     python bench.py --steps 3 --warmup 3 --no-secondary --no-cpu-baseline --e2e-steps 1 > $OUT/${TAG}_ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:msda_gather -s 4 -c 1 -o $OUT/${TAG}_prof_G -f \
     python bench.py --steps 3 --warmup 3 --dist G --no-secondary --no-cpu-baseline --e2e-steps 1 >> $OUT/${TAG}_ncu_full.log 2>&1
-ls -la $OUT
+ncu --set full --clock-control none --import-source on -k regex:dcn_fused_kernel -s 2 -c 1 -o $OUT/${TAG}_prof_dcn -f \
+    python scripts/dcn_prof.py 4 >> $OUT/${TAG}_ncu_full.log 2>&1
+ls -la $OUT | tail -20
