@@ -375,9 +375,43 @@ def run_multi(args, cfg, peak, peak_src):
     b3.record()
     torch.cuda.synchronize()
     ms_reduce = a3.elapsed_time(b3) / 20
-    t = torch.tensor([ms, ms_compute, ms_reduce], device="cuda", dtype=torch.float64)
+    # end to end: every step copies this rank's shard of the inputs from pinned host memory, runs the sharded step and
+    # (rank 0) reads the reduced BEV accumulator back to pinned host memory
+    pinned = [[t.cpu().pin_memory() for t in grp[1:]] for _, _, _, loc in sampler.chunks for grp in loc]
+    pinned_value = {id(grp[0]): grp[0].cpu().pin_memory() for _, _, _, loc in sampler.chunks for grp in loc}
+    dev = [grp for _, _, _, loc in sampler.chunks for grp in loc]
+    out_host = torch.empty_like(sampler.accum, device="cpu").pin_memory()
+    h2d = sum(t.numel() * t.element_size() for p_ in pinned for t in p_) + sum(
+        t.numel() * t.element_size() for t in pinned_value.values())
+
+    def e2e_step():
+        for vid, hv in pinned_value.items():
+            next(g[0] for g in dev if id(g[0]) == vid).copy_(hv, non_blocking=True)
+        for g, hp in zip(dev, pinned):
+            for d_t, h_t in zip(g[1:], hp):
+                d_t.copy_(h_t, non_blocking=True)
+        sampler.step()
+        if rank == 0:
+            out_host.copy_(sampler.accum, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a4.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    b4.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_e2e = a4.elapsed_time(b4) / args.e2e_steps
+    t = torch.tensor([ms, ms_compute, ms_reduce, ms_e2e], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_compute, ms_reduce = t.tolist()
+    ms, ms_compute, ms_reduce, ms_e2e = t.tolist()
+    hb = torch.tensor([float(h2d)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+    h2d_total = int(hb.item())
     eb = 2 if td == torch.float16 else 4
     alg = cfg.algorithmic_bytes(eb)
     out = None
@@ -399,7 +433,11 @@ def run_multi(args, cfg, peak, peak_src):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "msda_gather_kernel (per-GPU share, local compute only)",
                          "algorithmic_bytes": alg, "peak_source": peak_src},
-            "e2e": None,
+            "e2e": {"value": cfg.num_query / (ms_e2e * 1e-3), "unit": "BEV queries/s", "h2d_bytes_per_step": h2d_total,
+                    "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e,
+                    "steps": args.e2e_steps,
+                    "note": "per rank: pinned host -> device copy of its shard (value, ref, offsets, logits, bev_mask) + "
+                            "sharded step; rank 0 copies the reduced accumulator to pinned host memory"},
         }  # fmt: skip
     dist.destroy_process_group()
     return out

@@ -20,13 +20,19 @@ class MSDeformableAttention3DTRTP(nn.Module):
         self.value_proj = nn.Linear(embed_dims, embed_dims)
         self.multi_scale_deformable_attn = TRT_FUNCTIONS.get(op) if isinstance(op, str) else op  # bound once (:692)
 
-    def forward_trt(self, query, value, reference_points, spatial_shapes):
+    def forward_trt(self, query, value, reference_points, spatial_shapes, bev_mask=None):
+        """With ``bev_mask`` (and the fused op registered) returns the camera-summed slots [1, nq, embed_dims] directly:
+        MSDA + ``(queries * bev_mask).sum(0)`` in one kernel, the per-camera output is never materialised."""
         value = self.value_proj(value).view(self.num_cams, -1, self.num_heads, self.embed_dims // self.num_heads)
         sampling_offsets = self.sampling_offsets(query)
         attention_weights = self.attention_weights(query)
         reference_points = reference_points.reshape(self.num_cams, -1, 1, reference_points.shape[-2] * 2)
         sampling_offsets = sampling_offsets.view(*sampling_offsets.shape[:2], self.num_heads, -1)
         attention_weights = attention_weights.view(*attention_weights.shape[:2], self.num_heads, -1)
+        if bev_mask is not None:
+            fused = TRT_FUNCTIONS.get("multi_scale_deformable_attn_sca")
+            slots = fused(value, spatial_shapes, reference_points, sampling_offsets, attention_weights, bev_mask)
+            return slots.to(query.dtype).unsqueeze(0)
         return self.multi_scale_deformable_attn(value, spatial_shapes, reference_points, sampling_offsets,
                                                 attention_weights).flatten(2)  # fmt: skip
 
@@ -35,9 +41,9 @@ class SpatialCrossAttentionTRTP(nn.Module):
     """query repeated per camera, per-camera MSDA, bev_mask-weighted camera sum, output projection, residual
     (spatial_cross_attention.py:248-273)."""
 
-    def __init__(self, embed_dims=256, num_cams=6, **attn):
+    def __init__(self, embed_dims=256, num_cams=6, fused=False, **attn):
         super().__init__()
-        self.embed_dims, self.num_cams = embed_dims, num_cams
+        self.embed_dims, self.num_cams, self.fused = embed_dims, num_cams, fused
         self.deformable_attention = MSDeformableAttention3DTRTP(embed_dims=embed_dims, num_cams=num_cams, **attn)
         self.output_proj = nn.Linear(embed_dims, embed_dims)
 
@@ -48,6 +54,9 @@ class SpatialCrossAttentionTRTP(nn.Module):
         query = query.repeat(self.num_cams, 1, 1)
         reference_points_cam = reference_points_cam.view(self.num_cams, -1, int(reference_points_cam.size(3)), 2)
         value = value.view(self.num_cams, -1, self.embed_dims)
+        if self.fused:  # MSDA + bev_mask camera-sum in one kernel (multi_scale_deformable_attn_sca)
+            slots = self.deformable_attention.forward_trt(query, value, reference_points_cam, spatial_shapes, bev_mask)
+            return self.output_proj(slots) + inp_residual
         queries = self.deformable_attention.forward_trt(query, value, reference_points_cam, spatial_shapes)
         slots = (queries * bev_mask).sum(0, keepdims=True)
         return self.output_proj(slots) + inp_residual

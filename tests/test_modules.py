@@ -70,6 +70,19 @@ def test_tiny_sca_module_on_gpu_matches_oracle_op(dtype, tol):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 4e-3)])
+def test_tiny_sca_module_fused_equals_unfused(dtype, tol):
+    torch.manual_seed(0)
+    sca = SpatialCrossAttentionTRTP(num_levels=1, num_points=8).cuda().to(dtype)
+    ins = _tiny_sca_inputs(dtype, "cuda")
+    with torch.no_grad():
+        want = sca.forward_trt(*ins)
+        sca.fused = True
+        got = sca.forward_trt(*ins)
+    assert got.shape == want.shape and (got.float() - want.float()).abs().max().item() < tol
+
+
+@pytest.mark.gpu
 def test_base_tsa_module_on_gpu_matches_oracle_op():
     torch.manual_seed(1)
     tsa = TemporalSelfAttentionTRTP().cuda()
