@@ -31,6 +31,11 @@ from .functions import (  # noqa: E402
     multi_scale_deformable_attn2,
     multi_scale_deformable_attn_int8,
     multi_scale_deformable_attn_sca,
+    rotate,
+    rotate2,
+    rotate_chw2,
+    rotate_hwc,
+    rotate_int8,
 )
 
 __all__ = [
@@ -46,5 +51,10 @@ __all__ = [
     "multi_scale_deformable_attn2",
     "multi_scale_deformable_attn_int8",
     "multi_scale_deformable_attn_sca",
+    "rotate",
+    "rotate2",
+    "rotate_chw2",
+    "rotate_hwc",
+    "rotate_int8",
 ]
 __version__ = "0.1.0"

@@ -62,6 +62,12 @@ SIGNATURES = {
     "b200_grid_sample_f16": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
     "b200_grid_sample_f16_chw2": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
     "b200_grid_sample_i8_chw4": (_i, [_vp, _f, _vp, _f, _vp, _f, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
+    "b200_rotate_f32": (_i, [_vp, _vp, _vp, _vp, _ip, _i, _vp]),
+    "b200_rotate_f16": (_i, [_vp, _vp, _vp, _vp, _ip, _i, _vp]),
+    "b200_rotate_f16_h2": (_i, [_vp, _vp, _vp, _vp, _ip, _i, _vp]),
+    "b200_rotate_i8": (_i, [_vp, _f, _vp, _f, _vp, _vp, _i, _ip, _i, _vp]),
+    "b200_rotate_hwc": (_i, [_vp, _vp, _vp, _vp, _i, _ip, _i, _vp]),
+    "b200_rotate_debug_indices": (_i, [_vp, _vp, _ip, _vp, _vp]),
 }  # fmt: skip
 
 _lib = None

@@ -7,6 +7,7 @@
 //   MultiScaleDeformableAttnTRT, MultiScaleDeformableAttnTRT2   (multiScaleDeformableAttnPlugin.cpp:19-23, :345-346)
 //   GridSampler2DTRT, GridSampler2DTRT2                           (gridSamplerPlugin.cpp:20-26, :558-561)
 //   ModulatedDeformableConv2dTRT, ModulatedDeformableConv2dTRT2   (modulatedDeformableConv2dPlugin.cpp:19-23, :515-516)
+//   RotateTRT, RotateTRT2                                         (rotatePlugin.cpp:19-21, :216-330)
 // enqueue() forwards to the C ABI (include/b200_bev_ops.h); nothing is computed here.
 #if __has_include(<NvInfer.h>)
 #include <NvInfer.h>
@@ -22,11 +23,11 @@ using namespace nvinfer1;
 
 static_assert(sizeof(b200_tensor_desc) == sizeof(PluginTensorDesc), "b200_tensor_desc must mirror PluginTensorDesc");
 
-enum class Op { kMSDA, kGridSampler2D, kDCN };
+enum class Op { kMSDA, kGridSampler2D, kDCN, kRotate };
 
 struct Attrs {  // serialised verbatim (the reference serialises the same fields: gridSamplerPlugin.cpp:157-166,
                 // modulatedDeformableConv2dPlugin.cpp:200-211; MSDA serialises nothing, …Plugin.cpp:142-146)
-  int32_t interp = 0, padding = 0, align = 0;                           // grid sampler
+  int32_t interp = 0, padding = 0, align = 0;                           // grid sampler; rotate uses interp only
   int32_t stride[2] = {1, 1}, pad[2] = {0, 0}, dil[2] = {1, 1}, groups = 1, deform_groups = 1;  // DCN
 };
 
@@ -43,7 +44,10 @@ class Plugin final : public IPluginV2DynamicExt {
   DimsExprs getOutputDimensions(int32_t, const DimsExprs *in, int32_t nb, IExprBuilder &) noexcept override {
     DimsExprs o{};
     o.nbDims = 4;
-    if (op_ == Op::kMSDA) {  // [value.d0, offsets.d1, value.d2, value.d3] (…Plugin.cpp:48-58)
+    if (op_ == Op::kRotate) {  // output = img dims [C, H, W] (rotatePlugin.cpp:52-62)
+      o.nbDims = 3;
+      o.d[0] = in[0].d[0], o.d[1] = in[0].d[1], o.d[2] = in[0].d[2];
+    } else if (op_ == Op::kMSDA) {  // [value.d0, offsets.d1, value.d2, value.d3] (…Plugin.cpp:48-58)
       o.d[0] = in[0].d[0], o.d[1] = in[3].d[1], o.d[2] = in[0].d[2], o.d[3] = in[0].d[3];
     } else if (op_ == Op::kGridSampler2D) {  // [in.d0, in.d1, grid.d2, grid.d3] (gridSamplerPlugin.cpp:85-96)
       o.d[0] = in[0].d[0], o.d[1] = in[0].d[1], o.d[2] = in[1].d[2], o.d[3] = in[1].d[3];
@@ -56,6 +60,19 @@ class Plugin final : public IPluginV2DynamicExt {
   bool supportsFormatCombination(int32_t pos, const PluginTensorDesc *io, int32_t nbIn, int32_t nbOut) noexcept override {
     if (op_ == Op::kMSDA)
       return b200_msda_supports_format(pos, reinterpret_cast<const b200_tensor_desc *>(io), nbIn, nbOut) != 0;
+    if (op_ == Op::kRotate) {  // rotatePlugin.cpp:122-153: img fp32/fp16 linear (kCHW2 for …TRT2) or int8 kCHW4
+      const PluginTensorDesc &d = io[pos], &img = io[0];
+      if (pos == 0) {
+        if (d.type == DataType::kINT8) return d.format == TensorFormat::kCHW4;
+        if (d.type == DataType::kHALF) return d.format == (v2_ ? TensorFormat::kCHW2 : TensorFormat::kLINEAR);
+        return d.type == DataType::kFLOAT && d.format == TensorFormat::kLINEAR;
+      }
+      if (pos == nbIn) return d.type == img.type && d.format == img.format;
+      if (d.format != TensorFormat::kLINEAR) return false;  // angle, center
+      if (img.type == DataType::kINT8)
+        return (d.type == DataType::kFLOAT || d.type == DataType::kHALF) && d.type == io[1].type;
+      return d.type == img.type;
+    }
     // grid sampler / DCN: fp32 or fp16, linear, every tensor the same type (the packed kCHW2 / kCHW4 variants of the
     // reference map to b200_grid_sample_f16_chw2 / _i8_chw4 and are negotiated the same way when enabled)
     const bool ok_type = io[pos].type == DataType::kFLOAT || io[pos].type == DataType::kHALF;
@@ -63,7 +80,7 @@ class Plugin final : public IPluginV2DynamicExt {
   }
   void configurePlugin(const DynamicPluginTensorDesc *, int32_t, const DynamicPluginTensorDesc *, int32_t) noexcept override {}
   size_t getWorkspaceSize(const PluginTensorDesc *in, int32_t, const PluginTensorDesc *, int32_t) const noexcept override {
-    if (op_ != Op::kDCN) return 0;  // MSDA / grid sampler need none (…Plugin.cpp:64-69)
+    if (op_ != Op::kDCN) return 0;  // MSDA / grid sampler / rotate need none (…Plugin.cpp:64-69)
     const Dims &x = in[0].dims, &w = in[3].dims;
     return b200_dcn_workspace_size(in[0].type == DataType::kHALF, x.d[0], x.d[1], x.d[2], x.d[3], w.d[3], w.d[2],
                                    a_.stride[1], a_.stride[0], a_.pad[1], a_.pad[0], a_.dil[1], a_.dil[0]);
@@ -73,6 +90,20 @@ class Plugin final : public IPluginV2DynamicExt {
     if (op_ == Op::kMSDA)
       return b200_msda_enqueue(reinterpret_cast<const b200_tensor_desc *>(in),
                                reinterpret_cast<const b200_tensor_desc *>(out), inputs, outputs, workspace, stream, v2_);
+    if (op_ == Op::kRotate) {  // inputs: img, angle, center (rotatePlugin.cpp:75-113)
+      const int *dims = in[0].dims.d;
+      if (in[0].type == DataType::kFLOAT)
+        return b200_rotate_f32(static_cast<float *>(outputs[0]), static_cast<const float *>(inputs[0]),
+                               static_cast<const float *>(inputs[1]), static_cast<const float *>(inputs[2]), dims,
+                               a_.interp, stream);
+      if (in[0].type == DataType::kHALF)
+        return (v2_ ? b200_rotate_f16_h2 : b200_rotate_f16)(outputs[0], inputs[0], inputs[1], inputs[2], dims, a_.interp,
+                                                            stream);
+      if (in[0].type == DataType::kINT8)
+        return b200_rotate_i8(static_cast<int8_t *>(outputs[0]), out[0].scale, static_cast<const int8_t *>(inputs[0]),
+                              in[0].scale, inputs[1], inputs[2], in[1].type == DataType::kHALF, dims, a_.interp, stream);
+      return 1;
+    }
     if (op_ == Op::kGridSampler2D) {
       int id[4], gd[4], od[4];
       for (int i = 0; i < 4; ++i) id[i] = in[0].dims.d[i], gd[i] = in[1].dims.d[i], od[i] = out[0].dims.d[i];
@@ -100,6 +131,7 @@ class Plugin final : public IPluginV2DynamicExt {
     switch (op_) {
       case Op::kMSDA: return v2_ ? "MultiScaleDeformableAttnTRT2" : "MultiScaleDeformableAttnTRT";
       case Op::kGridSampler2D: return v2_ ? "GridSampler2DTRT2" : "GridSampler2DTRT";
+      case Op::kRotate: return v2_ ? "RotateTRT2" : "RotateTRT";
       default: return v2_ ? "ModulatedDeformableConv2dTRT2" : "ModulatedDeformableConv2dTRT";
     }
   }
@@ -133,6 +165,8 @@ class Creator final : public IPluginCreator {
       fields_ = {{"interpolation_mode", nullptr, PluginFieldType::kINT32, 1},
                  {"padding_mode", nullptr, PluginFieldType::kINT32, 1},
                  {"align_corners", nullptr, PluginFieldType::kINT32, 1}};
+    } else if (op == Op::kRotate) {
+      fields_ = {{"interpolation", nullptr, PluginFieldType::kINT32, 1}};
     } else if (op == Op::kDCN) {
       fields_ = {{"stride", nullptr, PluginFieldType::kINT32, 2},   {"padding", nullptr, PluginFieldType::kINT32, 2},
                  {"dilation", nullptr, PluginFieldType::kINT32, 2}, {"groups", nullptr, PluginFieldType::kINT32, 1},
@@ -151,7 +185,7 @@ class Creator final : public IPluginCreator {
       const auto *v = static_cast<const int32_t *>(f.data);
       if (!v || !f.name) continue;
       const std::string n = f.name;
-      if (n == "interpolation_mode") a.interp = v[0];
+      if (n == "interpolation_mode" || n == "interpolation") a.interp = v[0];
       else if (n == "padding_mode") a.padding = v[0];
       else if (n == "align_corners") a.align = v[0];
       else if (n == "stride") a.stride[0] = v[0], a.stride[1] = f.length > 1 ? v[1] : v[0];
@@ -206,6 +240,8 @@ B200_REGISTER(GridSampler2DCreator, Op::kGridSampler2D, false);
 B200_REGISTER(GridSampler2DCreator2, Op::kGridSampler2D, true);
 B200_REGISTER(DcnCreator, Op::kDCN, false);
 B200_REGISTER(DcnCreator2, Op::kDCN, true);
+B200_REGISTER(RotateCreator, Op::kRotate, false);
+B200_REGISTER(RotateCreator2, Op::kRotate, true);
 
 }  // namespace b200_trt
 #endif  // __has_include(<NvInfer.h>)

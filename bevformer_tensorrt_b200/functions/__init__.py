@@ -13,6 +13,7 @@ from .multi_scale_deformable_attn import (
     multi_scale_deformable_attn_int8,
     multi_scale_deformable_attn_sca,
 )
+from .rotate import rotate, rotate2, rotate_chw2, rotate_hwc, rotate_int8
 
 TRT_FUNCTIONS.register_module(module=grid_sampler)
 TRT_FUNCTIONS.register_module(module=grid_sampler2)
@@ -27,3 +28,9 @@ TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn2)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_int8)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_sca)
+
+TRT_FUNCTIONS.register_module(module=rotate)
+TRT_FUNCTIONS.register_module(module=rotate2)
+TRT_FUNCTIONS.register_module(module=rotate_chw2)
+TRT_FUNCTIONS.register_module(module=rotate_hwc)
+TRT_FUNCTIONS.register_module(module=rotate_int8)

@@ -174,6 +174,46 @@ int b200_grid_sample_i8_chw4(int8_t *output, float scale_o, const int8_t *input,
                              float scale_g, const int *output_dims, const int *input_dims, const int *grid_dims,
                              int nb_dims, int interp, int padding, int align_corners, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Rotate (plugins RotateTRT / RotateTRT2; det2trt/models/functions/rotate.py:7-124)
+ *
+ *   input / output [C, H, W]   (input_dims = HOST int[3] {C, H, W}, as the plugin passes inputDesc[0].dims.d)
+ *   angle  [1] degrees, counter-clockwise; center [2] = (x, y) in pixels: DEVICE pointers (plugin inputs 1, 2)
+ *   interp: 0 bilinear, 1 nearest (RotateInterpolation, TensorRT/plugin/rotate/rotateKernel.h:12); zero padding.
+ *
+ * Semantics = the reference FP32 kernel (rotateKernel.cu:128-210) — its index arithmetic is reproduced operation for
+ * operation (b200_rotate_debug_indices exposes it to the tests). FP16 / INT8 images are converted in registers;
+ * matrix, coordinates and blending stay FP32 (the reference computes them in half precision, :213-260, :416-456).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* replaces rotate<float>        — rotateKernel.h:14-16, .cu:708-719 */
+int b200_rotate_f32(float *output, const float *input, const float *angle, const float *center,
+                    const int *input_dims, int interp, void *stream);
+
+/* replaces rotate<__half>       — same launcher, T=__half: image, angle and center are __half, kLINEAR */
+int b200_rotate_f16(void *output, const void *input, const void *angle, const void *center, const int *input_dims,
+                    int interp, void *stream);
+
+/* replaces rotate_h2            — rotateKernel.h:18-20, .cu:721-732: image in kCHW2 ([ceil(C/2), H, W, 2] __half) */
+int b200_rotate_f16_h2(void *output, const void *input, const void *angle, const void *center, const int *input_dims,
+                       int interp, void *stream);
+
+/* replaces rotate_int8<float|__half> — rotateKernel.h:22-26, .cu:734-748: image in kCHW4 ([ceil(C/4), H, W, 4] int8),
+ * per-tensor scales (real = q * scale); angle / center are float (angle_is_half = 0) or __half (1), as
+ * rotatePlugin.cpp:101-111 dispatches on inputDesc[1].type. */
+int b200_rotate_i8(int8_t *output, float scale_o, const int8_t *input, float scale_i, const void *angle,
+                   const void *center, int angle_is_half, const int *input_dims, int interp, void *stream);
+
+/* B200 extension: channels-last image [H, W, C] (input_dims still {C, H, W}). prev_bev is stored [H*W, C] at the call
+ * site (det2trt/models/modules/transformer.py:296-304); this entry rotates it in place of permute -> RotateTRT ->
+ * permute. dtype 0: float image/angle/center, 1: __half. Needs C % 4 == 0 (fp32) / C % 8 == 0 (fp16) and 16-byte
+ * aligned buffers, else B200_ERR_UNSUPPORTED. */
+int b200_rotate_hwc(void *output, const void *input, const void *angle, const void *center, int dtype,
+                    const int *input_dims, int interp, void *stream);
+
+/* Test hook: source_xy[H*W*2] = (ix, iy), the fractional source pixel of every output pixel, from FP32 angle/center. */
+int b200_rotate_debug_indices(const float *angle, const float *center, const int *input_dims, float *source_xy,
+                              void *stream);
+
 
 /* ------------------------------------------------------------------------------------------------------------
  * Modulated deformable convolution, DCNv2 (plugins ModulatedDeformableConv2dTRT / …TRT2)

@@ -6,6 +6,7 @@
 //   TensorRT/plugin/multi_scale_deformable_attn/multiScaleDeformableAttnKernel.h:12-38
 //   TensorRT/plugin/grid_sampler/gridSamplerKernel.h:14-26
 //   TensorRT/plugin/modulated_deformable_conv2d/modulatedDeformableConv2dKernel.h:11-29
+//   TensorRT/plugin/rotate/rotateKernel.h:14-26
 // This file contains no arithmetic. It is linked only into oracle/_ref/libref_kernels.so.
 #include <cublas_v2.h>
 #include <cuda_fp16.h>
@@ -14,6 +15,7 @@
 #include "gridSamplerKernel.h"
 #include "modulatedDeformableConv2dKernel.h"
 #include "multiScaleDeformableAttnKernel.h"
+#include "rotateKernel.h"
 
 extern "C" {
 
@@ -99,6 +101,31 @@ void ref_dcn(int dtype, const void *input, const void *weight, const void *bias,
         (const __half *)mask, (__half *)output, workspace, batch, channels, height, width, channels_out, kernel_w,
         kernel_h, stride_w, stride_h, pad_w, pad_h, dilation_w, dilation_h, group, deformable_group, im2col_step,
         handle_for(s), s);
+}
+
+// dtype: 0 f32, 1 f16 (kLINEAR), 2 f16 as half2 (kCHW2). dims = HOST int[3] {C, H, W}; angle/center device, img dtype.
+void ref_rotate(int dtype, void *out, void *in, void *angle, void *center, int *dims, int interp, void *stream) {
+  auto im = (RotateInterpolation)interp;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == 0)
+    rotate<float>((float *)out, (float *)in, (float *)angle, (float *)center, dims, im, s);
+  else if (dtype == 1)
+    rotate<__half>((__half *)out, (__half *)in, (__half *)angle, (__half *)center, dims, im, s);
+  else
+    rotate_h2((__half2 *)out, (__half2 *)in, (__half *)angle, (__half *)center, dims, im, s);
+}
+
+// kCHW4 image; angle/center fp32 (angle_is_half = 0) or fp16 (1).
+void ref_rotate_int8(void *out, float scale_o, const void *in, float scale_i, const void *angle, const void *center,
+                     int angle_is_half, int *dims, int interp, void *stream) {
+  auto im = (RotateInterpolation)interp;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (angle_is_half)
+    rotate_int8<__half>((int8_4 *)out, scale_o, (const int8_4 *)in, scale_i, (const __half *)angle,
+                        (const __half *)center, dims, im, s);
+  else
+    rotate_int8<float>((int8_4 *)out, scale_o, (const int8_4 *)in, scale_i, (const float *)angle,
+                       (const float *)center, dims, im, s);
 }
 
 } // extern "C"

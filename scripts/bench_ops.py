@@ -89,6 +89,19 @@ def main():
             us = timeit(lambda: bt.multi_scale_deformable_attn(*ins), n=20)
             nbytes = cfg.algorithmic_bytes(2 if dt == torch.float16 else 4)
             out[f"msda_{name}_{tag}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+    # RotateTRT: prev_bev [256, 200, 200] by a few degrees about the BEV centre (transformer.py:296-304)
+    ang, ctr = torch.tensor([2.3], device="cuda"), torch.tensor([100.0, 100.0], device="cuda")
+    for tag, xx, aa, cc in (("f32", x[0], ang, ctr), ("f16", x[0].half(), ang.half(), ctr.half())):
+        nbytes = 2 * xx.numel() * xx.element_size()
+        for interp in ("bilinear", "nearest"):
+            us = timeit(lambda: bt.rotate(xx, aa, cc, interp))
+            out[f"rotate_{tag}_{interp}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+        hwc = xx.permute(1, 2, 0).contiguous()
+        us = timeit(lambda: bt.rotate_hwc(hwc, aa, cc, "bilinear"))
+        out[f"rotate_hwc_{tag}_bilinear"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+        # what the reference call site does around the plugin: permute -> rotate -> permute back (two extra copies)
+        us = timeit(lambda: bt.rotate(hwc.permute(2, 0, 1).contiguous(), aa, cc, "bilinear").permute(1, 2, 0).contiguous())
+        out[f"rotate_{tag}_bilinear_with_permutes"] = {"us": us}
     print(json.dumps(out))
 
 

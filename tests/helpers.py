@@ -56,6 +56,25 @@ def make_grid_sampler_inputs(N, C, Hi, Wi, Ho, Wo, seed=0, depth=None, span=15.0
     return inp, grid.contiguous()
 
 
+ROTATE_CASES = {
+    # name: (C, H, W, angle_deg, (center_x, center_y))
+    "bev_small": (8, 50, 50, 1.7, (25.0, 25.0)),        # prev_bev alignment: a few degrees about the BEV centre
+    "bev_neg": (6, 40, 48, -4.25, (24.0, 20.0)),
+    "big_angle": (5, 33, 47, 127.3, (20.5, 13.25)),     # reference test: angle ~ N(0,1)*360 (test_rotate.py:21-25)
+    "off_center": (4, 31, 29, -61.0, (40.0, 38.0)),     # centre outside the image (test_rotate.py: center = 500, 500)
+    "zero": (3, 17, 19, 0.0, (9.5, 8.5)),
+    "right_angle": (3, 16, 16, 90.0, (8.0, 8.0)),       # lands on x.5 / integer source indices
+    "odd_c": (7, 21, 23, 33.3, (11.0, 10.0)),           # C not a multiple of the kCHW2 / kCHW4 packet
+}
+
+
+def make_rotate_inputs(case, seed=0):
+    """img ~ N(0,1) [C,H,W], angle [1] (degrees), center [2] as float32 tensors (test_rotate.py:19-26)."""
+    C, H, W, ang, ctr = ROTATE_CASES[case]
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(C, H, W, generator=g), torch.tensor([ang]), torch.tensor(list(ctr))
+
+
 DCN_CASES = {
     # name: (N, Ci, H, W, Co, kh, kw, stride, padding, dilation, groups, deform_groups)
     "k3_s1_p1_g2_dg2": (2, 16, 13, 17, 12, 3, 3, 1, 1, 1, 2, 2),  # the reference op test's structure, reduced

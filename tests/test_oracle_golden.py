@@ -73,6 +73,60 @@ def test_grid_sampler_torch_port_matches_reference_python():
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# RotateTRT: golden vectors = the reference's own Python binding (tests/golden/make_golden_rotate.py)
+# ---------------------------------------------------------------------------------------------------------------
+from oracle import rotate as orot  # noqa: E402
+from tests.helpers import ROTATE_CASES, make_rotate_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("case", list(ROTATE_CASES))
+@pytest.mark.parametrize("interp", ["bilinear", "nearest"])
+def test_rotate_c_oracle_matches_reference_python(case, interp):
+    z = np.load(os.path.join(GOLDEN, "rotate_ref.npz"))
+    img, angle, center = make_rotate_inputs(case)
+    want = z[f"{case}_{interp}"]
+    got = orot.rotate(img.numpy(), float(angle[0]), center.numpy(), 0 if interp == "bilinear" else 1)
+    d = np.abs(got - want)
+    if interp == "nearest":
+        # kernel: ::round (half away from zero); binding: aten nearbyint (half to even) on a grid built through bmm.
+        # They pick different pixels only where the source index is within rounding of x.5 (right_angle / zero cases
+        # sit exactly there). The reference's own test absorbs this in a mean-abs delta (test_rotate.py:98-105).
+        frac = (d > 1e-6).mean()
+        assert frac < (0.08 if case in ("right_angle", "zero") else 0.005), frac
+    else:
+        assert d.max() < 5e-5, d.max()
+
+
+def test_rotate_torch_port_matches_reference_python():
+    z = np.load(os.path.join(GOLDEN, "rotate_ref.npz"))
+    for case in ROTATE_CASES:
+        img, angle, center = make_rotate_inputs(case)
+        for interp, name in ((0, "bilinear"), (1, "nearest")):
+            got = orot.rotate_torch_port(img, angle[0], center, interp).numpy()
+            assert np.array_equal(got, z[f"{case}_{name}"]), (case, name)
+
+
+def test_rotate_oracle_properties():
+    """Size-independent properties: zero angle about the image centre is the identity; a 90-degree turn of a square
+    image about its centre is an exact transpose-flip (both modes); rotation is linear in the image."""
+    rng = np.random.default_rng(5)
+    img = rng.standard_normal((3, 24, 24)).astype(np.float32)
+    assert np.array_equal(orot.rotate(img, 0.0, (12.0, 12.0), 1), img)
+    assert np.abs(orot.rotate(img, 0.0, (12.0, 12.0), 0) - img).max() < 1e-5  # (gx + 1) * W / 2 rounds in fp32
+    a, b = img, rng.standard_normal(img.shape).astype(np.float32)
+    lin = orot.rotate(a + 2 * b, 17.0, (11.0, 13.0), 0)
+    assert np.abs(lin - (orot.rotate(a, 17.0, (11.0, 13.0), 0) + 2 * orot.rotate(b, 17.0, (11.0, 13.0), 0))).max() < 1e-5
+    r90 = orot.rotate(img, 90.0, (12.0, 12.0), 0)
+    want = np.rot90(img, k=1, axes=(1, 2))  # counter-clockwise: out[h, w] = img[w, W-1-h]
+    assert np.abs(r90 - want).max() < 1e-4
+
+
+def test_rotate_t2int8_rounds_half_away_from_zero():
+    got = orot.t2int8(np.array([0.5, -0.5, 1.5, -1.5, 126.5, 127.4, 300.0, -128.6, -300.0, 0.49], np.float32))
+    assert got.tolist() == [1, -1, 2, -2, 127, 127, 127, -128, -128, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # DCNv2: mmcv (the reference binding's forward) is absent, so the oracle is pinned to torchvision's independent
 # implementation of the same definition (same offset channel order: 2*(i*kw+j) = dh, +1 = dw).
 # ---------------------------------------------------------------------------------------------------------------
