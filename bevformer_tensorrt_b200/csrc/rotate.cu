@@ -190,8 +190,10 @@ struct Vec16<kF16> {
   }
 };
 
+// LP lanes share one pixel: lane j blends the 16-byte vectors j, j + LP, ... of its four taps, so the index arithmetic
+// (two IEEE divisions) is paid once per LP-th of a pixel and each group of 8 lanes reads whole 128-byte lines.
 template <int K, int INTERP>
-__global__ void __launch_bounds__(256, 4) rotate_hwc_kernel(const RotParams p) {
+__global__ void __launch_bounds__(256, 3) rotate_hwc_kernel(const RotParams p) {
   using V = Vec16<K>;
   constexpr int N = V::N;
   __shared__ float sm[4];
@@ -202,32 +204,36 @@ __global__ void __launch_bounds__(256, 4) rotate_hwc_kernel(const RotParams p) {
   }
   __syncthreads();
   const float m[4] = {sm[0], sm[1], sm[2], sm[3]};
-  const int nvec = p.C / N;
-  const long long total = static_cast<long long>(p.H) * p.W * nvec;
-  const size_t esz = K == kF32 ? 4 : 2;
+  const int nvec = p.C / N, lp = p.slices;  // lanes per pixel (power of two <= 8)
+  const long long total = static_cast<long long>(p.H) * p.W * lp;
+  constexpr size_t esz = K == kF32 ? 4 : 2;
+  const size_t row = static_cast<size_t>(p.C) * esz;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(idx % nvec), pix = static_cast<int>(idx / nvec);
+    const int j = static_cast<int>(idx % lp), pix = static_cast<int>(idx / lp);
     const int w = pix % p.W, h = pix / p.W;
     float ix, iy;
     rot_source_index(m, w, h, p.W, p.H, ix, iy);
     const RotTaps t = rot_taps<INTERP>(ix, iy, p.W, p.H);
-    const char *ip = static_cast<const char *>(p.in) + static_cast<size_t>(v) * N * esz;
-    char *op = static_cast<char *>(p.out) + (static_cast<size_t>(pix) * p.C + static_cast<size_t>(v) * N) * esz;
-    const size_t row = static_cast<size_t>(p.C) * esz;
-    float o[N];
-    if (INTERP == 0) {
-      float a[N], b[N], c[N], d[N];
-      V::load(ip + t.o[0] * row, a), V::load(ip + t.o[1] * row, b);
-      V::load(ip + t.o[2] * row, c), V::load(ip + t.o[3] * row, d);
+    const char *i0 = static_cast<const char *>(p.in) + t.o[0] * row, *i1 = static_cast<const char *>(p.in) + t.o[1] * row;
+    const char *i2 = static_cast<const char *>(p.in) + t.o[2] * row, *i3 = static_cast<const char *>(p.in) + t.o[3] * row;
+    char *op = static_cast<char *>(p.out) + static_cast<size_t>(pix) * row;
+#pragma unroll 2
+    for (int v = j; v < nvec; v += lp) {
+      const size_t off = static_cast<size_t>(v) * N * esz;
+      float o[N];
+      if (INTERP == 0) {
+        float a[N], b[N], c[N], d[N];
+        V::load(i0 + off, a), V::load(i1 + off, b), V::load(i2 + off, c), V::load(i3 + off, d);
 #pragma unroll
-      for (int i = 0; i < N; ++i) o[i] = fmaf(d[i], t.w[3], fmaf(c[i], t.w[2], fmaf(b[i], t.w[1], a[i] * t.w[0])));
-    } else {
-      V::load(ip + t.o[0] * row, o);
+        for (int i = 0; i < N; ++i) o[i] = fmaf(d[i], t.w[3], fmaf(c[i], t.w[2], fmaf(b[i], t.w[1], a[i] * t.w[0])));
+      } else {
+        V::load(i0 + off, o);
 #pragma unroll
-      for (int i = 0; i < N; ++i) o[i] = t.w[0] != 0.f ? o[i] : 0.f;
+        for (int i = 0; i < N; ++i) o[i] = t.w[0] != 0.f ? o[i] : 0.f;
+      }
+      V::store(op + off, o);
     }
-    V::store(op, o);
   }
 }
 
@@ -288,7 +294,9 @@ static int launch_rotate_hwc(void *out, const void *in, const void *angle, const
   p.in = in, p.out = out, p.angle = angle, p.center = center, p.debug = debug;
   p.C = dims[0], p.H = dims[1], p.W = dims[2], p.CP = p.C;
   p.interp = interp, p.ac_half = K == kF16;
-  const long long total = static_cast<long long>(p.H) * p.W * (p.C / Vec16<K>::N);
+  const int nvec = p.C / Vec16<K>::N;
+  p.slices = nvec >= 8 ? 8 : nvec >= 4 ? 4 : nvec >= 2 ? 2 : 1;
+  const long long total = static_cast<long long>(p.H) * p.W * p.slices;
   const unsigned blocks = static_cast<unsigned>(total / 256 + 1 < (1 << 22) ? total / 256 + 1 : (1 << 22));
   if (interp == 0)
     rotate_hwc_kernel<K, 0><<<blocks, 256, 0, s>>>(p);

@@ -33,7 +33,8 @@ def device_trig(angle_deg):
 
 def debug_indices(angle, center, H, W):
     out = torch.empty(H, W, 2, dtype=torch.float32, device="cuda")
-    st = _lib.load().b200_rotate_debug_indices(angle.cuda().data_ptr(), center.cuda().data_ptr(),
+    angle, center = angle.cuda(), center.cuda()  # keep both alive across the launch
+    st = _lib.load().b200_rotate_debug_indices(angle.data_ptr(), center.data_ptr(),
                                                (ctypes.c_int * 3)(1, H, W), out.data_ptr(),
                                                _lib.current_stream_ptr())  # fmt: skip
     _lib.check("b200_rotate_debug_indices", st)
@@ -159,6 +160,11 @@ def test_int8_chw4_matches_dequant_oracle(interp, half_angle):
 def test_channels_last_entry_equals_planar(dtype, interp):
     g = torch.Generator().manual_seed(8)
     H, W, C = 50, 46, 64
+    for c_odd in (8, 24, 40, 88):  # vector counts that are not a multiple of the lanes sharing a pixel
+        x = torch.randn(9, 7, c_odd, generator=g).to(dtype).cuda()
+        a, c = torch.tensor([-33.0]).to(dtype).cuda(), torch.tensor([3.0, 4.0]).to(dtype).cuda()
+        assert torch.equal(bt.rotate_hwc(x, a, c, interp).permute(2, 0, 1),
+                           bt.rotate(x.permute(2, 0, 1).contiguous(), a, c, interp))
     bev = torch.randn(H * W, 1, C, generator=g).to(dtype).cuda()  # prev_bev as BEVFormer stores it
     angle, center = torch.tensor([2.9]).to(dtype).cuda(), torch.tensor([23.0, 25.0]).to(dtype).cuda()
     planar = bt.rotate(bev.view(H, W, C).permute(2, 0, 1).contiguous(), angle, center, interp)
@@ -181,7 +187,7 @@ def test_full_size_properties():
     ctr = torch.tensor([100.0, 100.0]).cuda()
     zero, ninety = torch.tensor([0.0]).cuda(), torch.tensor([90.0]).cuda()
     assert torch.equal(bt.rotate(img, zero, ctr, "nearest"), img)
-    assert (bt.rotate(img, zero, ctr, "bilinear") - img).abs().max().item() < 1e-4
+    assert (bt.rotate(img, zero, ctr, "bilinear") - img).abs().max().item() < 1e-3  # index rounding x gradient
     assert torch.equal(bt.rotate(img, ninety, ctr, "nearest"), torch.rot90(img, 1, (1, 2)))
     a = torch.tensor([7.3]).cuda()
     other = torch.randn(256, 200, 200, generator=g).cuda()
