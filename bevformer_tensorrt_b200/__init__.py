@@ -20,6 +20,8 @@ if not _building:
 
 from .functions import (  # noqa: E402
     TRT_FUNCTIONS,
+    bev_point_sampling,
+    get_reference_points_3d,
     grid_sampler,
     grid_sampler2,
     grid_sampler_chw2,
@@ -31,6 +33,7 @@ from .functions import (  # noqa: E402
     multi_scale_deformable_attn2,
     multi_scale_deformable_attn_int8,
     multi_scale_deformable_attn_sca,
+    point_sampling_trt,
     rotate,
     rotate2,
     rotate_chw2,
@@ -40,6 +43,8 @@ from .functions import (  # noqa: E402
 
 __all__ = [
     "TRT_FUNCTIONS",
+    "bev_point_sampling",
+    "get_reference_points_3d",
     "grid_sampler",
     "grid_sampler2",
     "grid_sampler_chw2",
@@ -51,6 +56,7 @@ __all__ = [
     "multi_scale_deformable_attn2",
     "multi_scale_deformable_attn_int8",
     "multi_scale_deformable_attn_sca",
+    "point_sampling_trt",
     "rotate",
     "rotate2",
     "rotate_chw2",

@@ -68,6 +68,7 @@ SIGNATURES = {
     "b200_rotate_i8": (_i, [_vp, _f, _vp, _f, _vp, _vp, _i, _ip, _i, _vp]),
     "b200_rotate_hwc": (_i, [_vp, _vp, _vp, _vp, _i, _ip, _i, _vp]),
     "b200_rotate_debug_indices": (_i, [_vp, _vp, _ip, _vp, _vp]),
+    "b200_bev_point_sampling": (_i, [_vp, ctypes.POINTER(ctypes.c_double), _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }  # fmt: skip
 
 _lib = None

@@ -1,0 +1,163 @@
+// point_sampling.cu — BEV pillar points -> per-camera reference points + visibility weights, on the device (sm_100a).
+//
+// Replaces the eager-PyTorch prologue of the BEVFormer encoder that feeds spatial cross-attention:
+//   BEVFormerEncoderTRTP.get_reference_points_3d  (det2trt/models/modules/encoder.py:168-194)
+//   BEVFormerEncoderTRTP.point_sampling_trt        (det2trt/models/modules/encoder.py:196-259)
+// ~30 small elementwise / matmul launches there; one kernel here, so reference_points_cam and bev_mask are produced
+// where the MSDA kernels (b200_msda_*, b200_msda_sca_*) consume them and never leave the GPU.
+//
+// Per BEV query q = (h, w) and pillar point d (encoder.py:172-193, :198-209):
+//   ref3d = ((w + 0.5) / W, (h + 0.5) / H, linspace(0.5, Z - 0.5, D)[d] / Z)          [or read from reference_points]
+//   p     = ref3d * (pc_range[3:6] - pc_range[0:3]) + pc_range[0:3]                    separately rounded mul, add
+//   cam   = lidar2img[c] @ (p, 1)                                                      (:211-217)
+//   vis   = cam.z > 1e-5;  uv = cam.xy / max(cam.z, 1e-5);  u /= image_w;  v /= image_h (:219-236)
+//   vis  &= 0 < v < 1  and  0 < u < 1                                                  (:238-249)
+//   reference_points_cam[c, 0, q, d, :] = uv                                           (:251 permute(2, 1, 3, 0, 4))
+//   seen[c, q] = any_d vis;  bev_mask[c, q, 0] = seen / max(sum_c seen, 1e-4)          (:252-254)
+//
+// One thread owns one query: the camera matrices sit in shared memory, the D pillar points and the per-camera `seen`
+// bits in registers, and each camera's D x 2 coordinates leave as 128-bit stores (consecutive threads = consecutive
+// queries = contiguous output). The 4x4 product is a left-to-right fma chain; the reference's comes from a batched
+// matmul whose summation order is the BLAS backend's, so parity here is a tolerance (1e-5 relative on cam.xyz), not
+// bit-exactness, and `vis` may differ for points within that rounding of an image border.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kMaxCams = 16, kMaxPillars = 8;
+
+struct PsParams {
+  const float *lidar2img;  // [cams, 4, 4]
+  const void *ref3d;       // optional [1, D, Q, 3] (fp32 or fp16 per out_half); NULL -> analytic pillar grid
+  void *ref_cam;           // [cams, 1, Q, D, 2]
+  void *bev_mask;          // [cams, Q, 1]
+  int cams, H, W, D, out_half;
+  float lo[3], ext[3];     // pc_range[0:3], pc_range[3:6] - pc_range[0:3]
+  float z_span;            // Z of get_reference_points_3d (pc_range[5] - pc_range[2] at the call site, encoder.py:284)
+  float img_w, img_h;      // image_shape[1], image_shape[0] (true divisions, as the exported ONNX Div nodes)
+};
+
+// torch.linspace(start, end, steps)[i] for float (ATen RangeFactories: step in float, symmetric evaluation)
+__device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
+  if (steps == 1) return start;
+  const float step = __fdiv_rn(__fsub_rn(end, start), static_cast<float>(steps - 1));
+  return i < steps / 2 ? __fadd_rn(start, __fmul_rn(step, static_cast<float>(i)))
+                       : __fsub_rn(end, __fmul_rn(step, static_cast<float>(steps - i - 1)));
+}
+
+__device__ __forceinline__ unsigned short f2h_sat(float x) {  // finite-saturating fp32 -> fp16
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) point_sampling_kernel(const PsParams p) {
+  __shared__ float sm[kMaxCams * 16];
+  for (int i = threadIdx.x; i < p.cams * 16; i += blockDim.x) sm[i] = __ldg(p.lidar2img + i);
+  __syncthreads();
+  const int Q = p.H * p.W;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int w = q % p.W, h = q / p.W;
+
+  float px[D], py[D], pz[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    float rx, ry, rz;
+    if (p.ref3d) {
+      const size_t o = (static_cast<size_t>(d) * Q + q) * 3;
+      if (p.out_half) {
+        const __half *r = static_cast<const __half *>(p.ref3d) + o;
+        rx = __half2float(r[0]), ry = __half2float(r[1]), rz = __half2float(r[2]);
+      } else {
+        const float *r = static_cast<const float *>(p.ref3d) + o;
+        rx = __ldg(r), ry = __ldg(r + 1), rz = __ldg(r + 2);
+      }
+    } else {
+      rx = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.W), 0.5f), p.W, w), static_cast<float>(p.W));
+      ry = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.H), 0.5f), p.H, h), static_cast<float>(p.H));
+      rz = __fdiv_rn(linspace_at(0.5f, __fsub_rn(p.z_span, 0.5f), D, d), p.z_span);
+    }
+    px[d] = __fadd_rn(__fmul_rn(rx, p.ext[0]), p.lo[0]);
+    py[d] = __fadd_rn(__fmul_rn(ry, p.ext[1]), p.lo[1]);
+    pz[d] = __fadd_rn(__fmul_rn(rz, p.ext[2]), p.lo[2]);
+  }
+
+  unsigned seen = 0;  // bit c: camera c sees at least one pillar point of this query
+  for (int c = 0; c < p.cams; ++c) {
+    const float *m = sm + c * 16;
+    float uv[2 * D];
+    bool any = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float cx = __fadd_rn(fmaf(m[2], pz[d], fmaf(m[1], py[d], __fmul_rn(m[0], px[d]))), m[3]);
+      const float cy = __fadd_rn(fmaf(m[6], pz[d], fmaf(m[5], py[d], __fmul_rn(m[4], px[d]))), m[7]);
+      const float cz = __fadd_rn(fmaf(m[10], pz[d], fmaf(m[9], py[d], __fmul_rn(m[8], px[d]))), m[11]);
+      const float eps = 1e-5f;
+      const float den = fmaxf(cz, eps);
+      const float u = __fdiv_rn(__fdiv_rn(cx, den), p.img_w), v = __fdiv_rn(__fdiv_rn(cy, den), p.img_h);
+      any |= cz > eps && v > 0.f && v < 1.f && u < 1.f && u > 0.f;
+      uv[2 * d] = u, uv[2 * d + 1] = v;
+    }
+    seen |= any ? (1u << c) : 0u;
+    const size_t o = (static_cast<size_t>(c) * Q + q) * (2 * D);
+    if (p.out_half) {
+      unsigned short *op = static_cast<unsigned short *>(p.ref_cam) + o;
+#pragma unroll
+      for (int i = 0; i < 2 * D; ++i) op[i] = f2h_sat(uv[i]);  // behind-camera points are ~1e8: saturate, not inf
+    } else {
+      float *op = static_cast<float *>(p.ref_cam) + o;
+#pragma unroll
+      for (int i = 0; i < 2 * D; ++i) op[i] = uv[i];
+    }
+  }
+  const float total = fmaxf(static_cast<float>(__popc(seen)), 1e-4f);
+  for (int c = 0; c < p.cams; ++c) {
+    const float wgt = __fdiv_rn((seen >> c) & 1u ? 1.f : 0.f, total);
+    if (p.out_half)
+      static_cast<__half *>(p.bev_mask)[static_cast<size_t>(c) * Q + q] = __float2half_rn(wgt);
+    else
+      static_cast<float *>(p.bev_mask)[static_cast<size_t>(c) * Q + q] = wgt;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_bev_point_sampling(const void *reference_points, const double *pc_range, const float *lidar2img,
+                                       int num_cams, int image_h, int image_w, int bev_h, int bev_w,
+                                       int num_points_in_pillar, int dtype, void *reference_points_cam,
+                                       void *bev_mask, void *stream) {
+  if (!pc_range || !lidar2img || !reference_points_cam || !bev_mask) return B200_ERR_BAD_PARAM;
+  if (num_cams <= 0 || image_h <= 0 || image_w <= 0 || bev_h <= 0 || bev_w <= 0 || num_points_in_pillar <= 0)
+    return B200_ERR_BAD_PARAM;
+  if (dtype != 0 && dtype != 1) return B200_ERR_BAD_PARAM;
+  if (num_cams > kMaxCams || num_points_in_pillar > kMaxPillars) return B200_ERR_UNSUPPORTED;
+  if (static_cast<long long>(bev_h) * bev_w >= (1ll << 28)) return B200_ERR_BAD_PARAM;
+  PsParams p{};
+  p.lidar2img = lidar2img, p.ref3d = reference_points, p.ref_cam = reference_points_cam, p.bev_mask = bev_mask;
+  p.cams = num_cams, p.H = bev_h, p.W = bev_w, p.D = num_points_in_pillar, p.out_half = dtype;
+  for (int i = 0; i < 3; ++i) {
+    // Python evaluates pc_range[3+i] - pc_range[i] in double and torch.tensor(..., dtype=float32) rounds it once
+    p.lo[i] = static_cast<float>(pc_range[i]);
+    p.ext[i] = static_cast<float>(pc_range[3 + i] - pc_range[i]);
+  }
+  p.z_span = static_cast<float>(pc_range[5] - pc_range[2]);
+  p.img_w = static_cast<float>(image_w), p.img_h = static_cast<float>(image_h);
+  const int Q = bev_h * bev_w;
+  const unsigned blocks = (Q + 127) / 128;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (num_points_in_pillar) {
+    case 1: point_sampling_kernel<1><<<blocks, 128, 0, s>>>(p); break;
+    case 2: point_sampling_kernel<2><<<blocks, 128, 0, s>>>(p); break;
+    case 3: point_sampling_kernel<3><<<blocks, 128, 0, s>>>(p); break;
+    case 4: point_sampling_kernel<4><<<blocks, 128, 0, s>>>(p); break;
+    case 5: point_sampling_kernel<5><<<blocks, 128, 0, s>>>(p); break;
+    case 6: point_sampling_kernel<6><<<blocks, 128, 0, s>>>(p); break;
+    case 7: point_sampling_kernel<7><<<blocks, 128, 0, s>>>(p); break;
+    default: point_sampling_kernel<8><<<blocks, 128, 0, s>>>(p); break;
+  }
+  return check_launch();
+}

@@ -13,6 +13,7 @@ from .multi_scale_deformable_attn import (
     multi_scale_deformable_attn_int8,
     multi_scale_deformable_attn_sca,
 )
+from .point_sampling import bev_point_sampling, get_reference_points_3d, point_sampling_trt
 from .rotate import rotate, rotate2, rotate_chw2, rotate_hwc, rotate_int8
 
 TRT_FUNCTIONS.register_module(module=grid_sampler)
@@ -34,3 +35,7 @@ TRT_FUNCTIONS.register_module(module=rotate2)
 TRT_FUNCTIONS.register_module(module=rotate_chw2)
 TRT_FUNCTIONS.register_module(module=rotate_hwc)
 TRT_FUNCTIONS.register_module(module=rotate_int8)
+
+TRT_FUNCTIONS.register_module(module=get_reference_points_3d)
+TRT_FUNCTIONS.register_module(module=point_sampling_trt)
+TRT_FUNCTIONS.register_module(module=bev_point_sampling)

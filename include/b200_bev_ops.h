@@ -216,6 +216,26 @@ int b200_rotate_debug_indices(const float *angle, const float *center, const int
 
 
 /* ------------------------------------------------------------------------------------------------------------
+ * BEV pillar points -> per-camera reference points and visibility weights (the encoder prologue that feeds spatial
+ * cross-attention; eager PyTorch in the reference, ONNX elementwise nodes in its engines — no plugin):
+ *   BEVFormerEncoderTRTP.get_reference_points_3d  det2trt/models/modules/encoder.py:168-194
+ *   BEVFormerEncoderTRTP.point_sampling_trt        det2trt/models/modules/encoder.py:196-259
+ *
+ *   reference_points      [1, D, bev_h*bev_w, 3] in [0,1] (what get_reference_points_3d returns), or NULL to generate
+ *                         that pillar grid analytically (Z = pc_range[5] - pc_range[2], encoder.py:281-289)
+ *   pc_range              HOST double[6] = (x0, y0, z0, x1, y1, z1)
+ *   lidar2img             DEVICE float [num_cams, 4, 4]
+ *   reference_points_cam  [num_cams, 1, Q, D, 2]  (u, v) normalised by (image_w, image_h) — the MSDA reference_points
+ *   bev_mask              [num_cams, Q, 1]        seen / max(sum over cameras of seen, 1e-4)
+ *   dtype                 0: float tensors, 1: __half tensors (reference_points in, both outputs; math stays FP32 and
+ *                         coordinates of points behind a camera saturate to +-65504 instead of overflowing to inf)
+ * num_cams <= 16, num_points_in_pillar <= 8, else B200_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200_bev_point_sampling(const void *reference_points, const double *pc_range, const float *lidar2img,
+                            int num_cams, int image_h, int image_w, int bev_h, int bev_w, int num_points_in_pillar,
+                            int dtype, void *reference_points_cam, void *bev_mask, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Modulated deformable convolution, DCNv2 (plugins ModulatedDeformableConv2dTRT / …TRT2)
  *
  *   input  [batch, channels, height, width]

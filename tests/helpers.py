@@ -75,6 +75,23 @@ def make_rotate_inputs(case, seed=0):
     return torch.randn(C, H, W, generator=g), torch.tensor([ang]), torch.tensor(list(ctr))
 
 
+_PC_RANGE = (-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)  # BEVFormer nuScenes configs (point_cloud_range)
+POINT_SAMPLING_CASES = {
+    # name: (bev_h, bev_w, num_points_in_pillar, image (h, w), pc_range)
+    "ring_small": (50, 50, 4, (928, 1600), _PC_RANGE),     # BEVFormer-tiny BEV size
+    "ring_rect": (30, 44, 4, (480, 800), _PC_RANGE),       # non-square BEV, small images (BEVFormer-small-like)
+    "ring_d8": (20, 20, 8, (928, 1600), (-40.0, -40.0, -1.0, 40.0, 40.0, 5.4)),
+    "ring_d1": (16, 24, 1, (928, 1600), _PC_RANGE),
+}
+
+
+def make_point_sampling_inputs(case):
+    """lidar2img [6, 4, 4] float32 of the synthetic camera ring (bevformer_tensorrt_b200.workloads)."""
+    from bevformer_tensorrt_b200.workloads import camera_ring_lidar2img
+
+    return camera_ring_lidar2img(6, img_hw=POINT_SAMPLING_CASES[case][3])
+
+
 DCN_CASES = {
     # name: (N, Ci, H, W, Co, kh, kw, stride, padding, dilation, groups, deform_groups)
     "k3_s1_p1_g2_dg2": (2, 16, 13, 17, 12, 3, 3, 1, 1, 1, 2, 2),  # the reference op test's structure, reduced

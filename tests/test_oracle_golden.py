@@ -127,6 +127,52 @@ def test_rotate_t2int8_rounds_half_away_from_zero():
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# BEV point sampling (encoder prologue): golden = the reference's own two methods (make_golden_point_sampling.py)
+# ---------------------------------------------------------------------------------------------------------------
+from oracle import point_sampling as ops  # noqa: E402
+from tests.helpers import POINT_SAMPLING_CASES, make_point_sampling_inputs  # noqa: E402
+
+
+def assert_point_sampling_close(cam, mask, want_cam, want_mask, rtol=2e-5):
+    """reference_points_cam: 2e-5 relative (coordinates of points behind a camera are ~1e8); bev_mask: identical except
+    for queries with a pillar point within rounding of an image border or of depth eps."""
+    assert cam.shape == want_cam.shape and mask.shape == want_mask.shape
+    rel = np.abs(cam - want_cam) / np.maximum(1.0, np.abs(want_cam))
+    assert rel.max() < rtol, rel.max()
+    assert (mask != want_mask).any(0).mean() < 2e-3
+
+
+@pytest.mark.parametrize("case", list(POINT_SAMPLING_CASES))
+def test_point_sampling_oracle_matches_reference_python(case):
+    z = np.load(os.path.join(GOLDEN, "point_sampling_ref.npz"))
+    H, W, D, img_hw, pc_range = POINT_SAMPLING_CASES[case]
+    ref3d = ops.get_reference_points_3d(H, W, pc_range[5] - pc_range[2], D)
+    # linspace / divide restated bit for bit. The reference hard-codes `.view(1, 4, -1, 3)` (encoder.py:193), so for
+    # D != 4 its tensor has the same memory under a different shape; point_sampling_trt re-views it by D (:208-210).
+    assert np.array_equal(ref3d.reshape(-1), z[f"{case}_ref3d"].reshape(-1))
+    cam, mask = ops.point_sampling(ref3d, pc_range, make_point_sampling_inputs(case).numpy(), img_hw)
+    assert_point_sampling_close(cam, mask, z[f"{case}_cam"], z[f"{case}_mask"])
+    # the fixture is not degenerate: every camera sees some queries, none sees all, weights sum to 1 where seen
+    m = z[f"{case}_mask"][..., 0]
+    assert ((m > 0).mean(1) > 0.02).all() and ((m > 0).mean(1) < 0.6).all()
+    s = m.sum(0)
+    assert np.all((np.abs(s - 1) < 1e-6) | (s == 0))
+
+
+def test_point_sampling_workload_generator_matches_reference_python():
+    """bevformer_tensorrt_b200.workloads.bev_reference_points_cam (the bench's distribution-G input generator) is the
+    same computation."""
+    from bevformer_tensorrt_b200.workloads import bev_reference_points_cam
+
+    z = np.load(os.path.join(GOLDEN, "point_sampling_ref.npz"))
+    H, W, D, img_hw, pc_range = POINT_SAMPLING_CASES["ring_small"]
+    uv, mask = bev_reference_points_cam((H, W), make_point_sampling_inputs("ring_small"), img_hw=img_hw,
+                                        Z=pc_range[5] - pc_range[2], pillars=D, pc_range=pc_range)  # fmt: skip
+    # einsum sums the 4x4 product in another order: where the depth nearly cancels the quotient moves by ~1e-4 relative
+    assert_point_sampling_close(uv.numpy()[:, None], mask.numpy(), z["ring_small_cam"], z["ring_small_mask"], rtol=3e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # DCNv2: mmcv (the reference binding's forward) is absent, so the oracle is pinned to torchvision's independent
 # implementation of the same definition (same offset channel order: 2*(i*kw+j) = dh, +1 = dw).
 # ---------------------------------------------------------------------------------------------------------------
