@@ -3,5 +3,7 @@
 operator is called *unchanged* — bound once at construction, invoked positionally — and to measure the op in situ
 (BASELINE configs[1]: tiny SpatialCrossAttention). They are not a port of the model graph."""
 from .attention import MSDeformableAttention3DTRTP, SpatialCrossAttentionTRTP, TemporalSelfAttentionTRTP
+from .encoder import BEVFormerEncoderPrologueTRTP
 
-__all__ = ["MSDeformableAttention3DTRTP", "SpatialCrossAttentionTRTP", "TemporalSelfAttentionTRTP"]
+__all__ = ["BEVFormerEncoderPrologueTRTP", "MSDeformableAttention3DTRTP", "SpatialCrossAttentionTRTP",
+           "TemporalSelfAttentionTRTP"]

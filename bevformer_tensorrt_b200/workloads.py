@@ -95,19 +95,20 @@ def bev_reference_points_cam(bev_hw, lidar2img, img_hw=(928, 1600), Z=8.0, pilla
     """encoder.py:170-259 restated: pillar grid -> per-camera normalised image coordinates + visibility weights.
     Returns (reference_points_cam [cams, nq, pillars, 2], bev_mask [cams, nq, 1])."""
     H, W = bev_hw
-    zs = (torch.linspace(0.5, Z - 0.5, pillars) / Z).view(pillars, 1, 1).expand(pillars, H, W)
-    xs = (torch.linspace(0.5, W - 0.5, W) / W).view(1, 1, W).expand(pillars, H, W)
-    ys = (torch.linspace(0.5, H - 0.5, H) / H).view(1, H, 1).expand(pillars, H, W)
+    dev = lidar2img.device
+    zs = (torch.linspace(0.5, Z - 0.5, pillars, device=dev) / Z).view(pillars, 1, 1).expand(pillars, H, W)
+    xs = (torch.linspace(0.5, W - 0.5, W, device=dev) / W).view(1, 1, W).expand(pillars, H, W)
+    ys = (torch.linspace(0.5, H - 0.5, H, device=dev) / H).view(1, H, 1).expand(pillars, H, W)
     ref3d = torch.stack((xs, ys, zs), -1).reshape(pillars, H * W, 3)
-    lo = torch.tensor(pc_range[:3])
-    ext = torch.tensor(pc_range[3:]) - lo
-    pts = torch.cat((ref3d * ext + lo, torch.ones(pillars, H * W, 1)), -1)  # [pillars, nq, 4]
+    lo = torch.tensor(pc_range[:3], device=dev)
+    ext = torch.tensor(pc_range[3:], device=dev) - lo
+    pts = torch.cat((ref3d * ext + lo, torch.ones(pillars, H * W, 1, device=dev)), -1)  # [pillars, nq, 4]
     cam = torch.einsum("cij,pqj->cqpi", lidar2img, pts)  # [cams, nq, pillars, 4]
     eps = 1e-5
     depth = cam[..., 2:3]
     vis = (depth > eps).float()
     uv = cam[..., 0:2] / torch.clamp(depth, min=eps)
-    uv = uv / torch.tensor([img_hw[1], img_hw[0]], dtype=uv.dtype)
+    uv = uv / torch.tensor([img_hw[1], img_hw[0]], dtype=uv.dtype, device=dev)
     vis = vis * ((uv[..., 0:1] > 0) & (uv[..., 0:1] < 1) & (uv[..., 1:2] > 0) & (uv[..., 1:2] < 1)).float()
     seen = 1 - (1 - vis).prod(2)  # [cams, nq, 1]: any pillar visible
     bev_mask = seen / torch.clamp(seen.sum(0, keepdim=True), min=1e-4)

@@ -102,6 +102,17 @@ def main():
         # what the reference call site does around the plugin: permute -> rotate -> permute back (two extra copies)
         us = timeit(lambda: bt.rotate(hwc.permute(2, 0, 1).contiguous(), aa, cc, "bilinear").permute(1, 2, 0).contiguous())
         out[f"rotate_{tag}_bilinear_with_permutes"] = {"us": us}
+    # BEV point sampling (encoder prologue, encoder.py:168-259) at base size: one kernel vs the same math in eager torch
+    from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img
+
+    l2i = camera_ring_lidar2img(6).cuda()
+    pcr = (-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)
+    for tag, dt in (("f32", torch.float32), ("f16", torch.float16)):
+        us = timeit(lambda: bt.bev_point_sampling(200, 200, pcr, l2i, (928, 1600), 4, dtype=dt))
+        nbytes = (6 * 40000 * 8 + 6 * 40000) * (4 if dt == torch.float32 else 2)
+        out[f"bev_point_sampling_{tag}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+    us = timeit(lambda: bev_reference_points_cam((200, 200), l2i), n=10)
+    out["bev_point_sampling_eager_torch_f32"] = {"us": us}
     print(json.dumps(out))
 
 

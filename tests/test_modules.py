@@ -94,3 +94,33 @@ def test_base_tsa_module_on_gpu_matches_oracle_op():
         tsa.multi_scale_deformable_attn = _oracle_op
         want = tsa.forward_trt(q, ref2d, shapes)
     assert (got - want).abs().max().item() < 2e-5
+
+
+@pytest.mark.gpu
+def test_encoder_prologue_feeds_sca_on_gpu():
+    """rotate(prev_bev) + on-device point sampling + fused SCA, all through registry-bound ops, against the same chain
+    fed with the eager-torch geometry (workloads.bev_reference_points_cam) and the unfused SCA module."""
+    from bevformer_tensorrt_b200.modules import BEVFormerEncoderPrologueTRTP
+
+    torch.manual_seed(0)
+    pro = BEVFormerEncoderPrologueTRTP(rotate_center=(25, 25)).cuda()
+    query, value, ref_cam_host, mask_host, shapes = _tiny_sca_inputs(torch.float32, "cuda")
+    l2i = camera_ring_lidar2img(6).cuda()
+    hyb, ref_cam, bev_mask = pro.forward_trt(query, l2i, 50, 50, (928, 1600), torch.tensor([0.01, -0.02]).cuda(), 1.0)
+    assert hyb.shape == (2, 2500, 1, 2) and ref_cam.shape == (6, 1, 2500, 4, 2) and bev_mask.shape == (6, 2500, 1)
+    assert torch.allclose(hyb[0] - hyb[1], torch.tensor([0.01, -0.02]).cuda().expand(2500, 1, 2), atol=1e-6)
+    assert ((bev_mask > 0) != (mask_host > 0)).float().mean().item() < 1e-3
+    sca_f = SpatialCrossAttentionTRTP(num_levels=1, num_points=8, fused=True).cuda()
+    sca_u = SpatialCrossAttentionTRTP(num_levels=1, num_points=8).cuda()
+    sca_u.load_state_dict(sca_f.state_dict())
+    got = sca_f.forward_trt(query, value, ref_cam.clamp(-60000, 60000), bev_mask, shapes)
+    want = sca_u.forward_trt(query, value, ref_cam_host, mask_host, shapes)
+    bad = ((got - want).abs().amax(-1) > 1e-3).float().mean().item()
+    assert bad < 2e-3, bad  # identical but for queries whose visibility flips within rounding of an image border
+    # prev_bev rotation through the prologue keeps BEVFormer's [H*W, 1, C] layout and equals the planar op
+    prev = torch.randn(2500, 1, 256, device="cuda")
+    rot = pro.rotate_prev_bev(prev, torch.tensor(3.0, device="cuda"), 50, 50)
+    assert rot.shape == prev.shape
+    planar = bt.rotate(prev.view(50, 50, 256).permute(2, 0, 1).contiguous(), torch.tensor(3.0, device="cuda"),
+                       torch.tensor([25.0, 25.0], device="cuda"))
+    assert torch.equal(rot.view(50, 50, 256).permute(2, 0, 1), planar)
