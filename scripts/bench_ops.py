@@ -32,6 +32,20 @@ def timeit(fn, n=50, warm=5):
     return a.elapsed_time(b) / n * 1e3  # us
 
 
+def timeit_eager(fn, n=20, warm=3):
+    """Events around n eager calls (launch overhead included) for code that cannot be captured into a graph."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n * 1e3
+
+
 def main():
     peak = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     out = {}
@@ -111,7 +125,7 @@ def main():
         us = timeit(lambda: bt.bev_point_sampling(200, 200, pcr, l2i, (928, 1600), 4, dtype=dt))
         nbytes = (6 * 40000 * 8 + 6 * 40000) * (4 if dt == torch.float32 else 2)
         out[f"bev_point_sampling_{tag}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
-    us = timeit(lambda: bev_reference_points_cam((200, 200), l2i), n=10)
+    us = timeit_eager(lambda: bev_reference_points_cam((200, 200), l2i), n=10)  # builds tensors from lists: not capturable
     out["bev_point_sampling_eager_torch_f32"] = {"us": us}
     print(json.dumps(out))
 
