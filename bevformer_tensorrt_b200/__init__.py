@@ -33,6 +33,7 @@ from .functions import (  # noqa: E402
     multi_scale_deformable_attn2,
     multi_scale_deformable_attn_int8,
     multi_scale_deformable_attn_sca,
+    multi_scale_deformable_attn_sca_shared,
     point_sampling_trt,
     rotate,
     rotate2,
@@ -56,6 +57,7 @@ __all__ = [
     "multi_scale_deformable_attn2",
     "multi_scale_deformable_attn_int8",
     "multi_scale_deformable_attn_sca",
+    "multi_scale_deformable_attn_sca_shared",
     "point_sampling_trt",
     "rotate",
     "rotate2",

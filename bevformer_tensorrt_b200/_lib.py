@@ -46,6 +46,8 @@ SIGNATURES = {
     "b200_msda_i8": (_i, [_vp, _f, _vp, _vp, _i, _vp, _f, _vp, _f] + _MSDA_DIMS + [_vp, _f, _vp]),
     "b200_msda_sca_f32": (_i, [_vp] * 6 + _MSDA_DIMS + [_vp, _vp]),
     "b200_msda_sca_f16": (_i, [_vp] * 6 + _MSDA_DIMS + [_vp, _vp]),
+    "b200_msda_sca_shared_f32": (_i, [_vp] * 6 + _MSDA_DIMS + [_vp, _vp]),
+    "b200_msda_sca_shared_f16": (_i, [_vp] * 6 + _MSDA_DIMS + [_vp, _vp]),
     "b200_msda_debug_indices": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200_msda_set_f16_mode": (_i, [_i]),
     "b200_msda_enqueue": (_i, [ctypes.POINTER(TensorDesc), ctypes.POINTER(TensorDesc), ctypes.POINTER(_vp),

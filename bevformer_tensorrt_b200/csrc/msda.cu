@@ -42,6 +42,8 @@ struct MsdaParams {
   long long items;
   int ref_is_half;  // int8 path: dtype of reference_points
   // fused spatial-cross-attention epilogue (EPI = 1): accum[q, m*C + c] += bev_mask[b, q] * out[b, q, m, c]
+  // camera-loop form (EPI = 2): items are (q, head); offsets / logits are [Q, M, ...] shared by all B cameras (the
+  // reference repeats the query per camera, spatial_cross_attention.py:254); accum[q, m*C + c] = sum_b ... (plain store)
   const float *mask;
   float *accum;
   float scale_value, scale_offset, scale_weight, scale_out;
@@ -331,9 +333,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
   const long long it_raw = item0 + warp * IPW + lane / LPI;
   const bool active = it_raw < prm.items;
   const long long it = active ? it_raw : prm.items - 1;  // inactive lanes shadow the last item, never store
-  const long long bq = it / M;
-  const int m = static_cast<int>(it - bq * M);
-  const int b = static_cast<int>(bq / Q);
+  const long long bq0 = it / M;  // EPI < 2: b * Q + q; EPI == 2: q
+  const int m = static_cast<int>(it - bq0 * M);
   const T *off_item = static_cast<const T *>(prm.off) + it * NP * 2;
   const T *lg_item = static_cast<const T *>(prm.logits) + it * NP;
   T *out_item = static_cast<T *>(prm.out) + it * C + sub * VEC;
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
     // Fused SCA epilogue: a (camera, query) pair with bev_mask == 0 contributes exactly nothing, whatever it samples.
     // When that holds for every item of the warp (one query x 8 heads share the mask value) nothing is read at all —
     // for a camera ring about 4 of 5 warps leave here.
-    const float mk0 = __ldg(prm.mask + bq);
+    const float mk0 = __ldg(prm.mask + bq0);
     if (__ballot_sync(kFullMask, active && mk0 != 0.f) == 0u) return;
   }
 
@@ -366,6 +367,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
     }
     lvStart = incl - area;
   }
+  float lg[ROUNDS][4];
+  float sum = 0.f;
+  bool have_sm = false;  // warp-uniform
+  unsigned inr = 0;      // bit r*4+k: point in range (…Kernel.cu:674)
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+  const int num_b = EPI == 2 ? prm.B : 1;
+  for (int bi = 0; bi < num_b; ++bi) {
+  const int b = EPI == 2 ? bi : static_cast<int>(bq0 / Q);
+  const long long bq = EPI == 2 ? static_cast<long long>(bi) * Q + bq0 : bq0;
+  float mk = 1.f;
+  if (EPI == 2) {
+    mk = __ldg(prm.mask + bq);
+    if (__ballot_sync(kFullMask, active && mk != 0.f) == 0u) continue;  // this camera sees none of the warp's queries
+  }
   // Reference points of this item's (batch, query): 2G values, the same for every head (and every lane group that
   // shares the query) — a broadcast load.
   float rpx[4], rpy[4];
@@ -373,11 +391,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
 
   // ---- phase A: sampling positions of the points this lane owns (chunk c = r*LPI + sub), the bit-exact part
   float him[ROUNDS][4], wim[ROUNDS][4];
-  unsigned inr = 0;  // bit r*4+k: point in range (…Kernel.cu:674)
+  inr = 0;
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
     const int c = r * LPI + sub;
-    const bool have = c < NCH;
+    const bool have = c < NCH && (EPI != 2 || mk != 0.f);
     const int cc = have ? c : 0;
     const int lv = cc / CPL;
     const int H = __shfl_sync(kFullMask, lvH, lv), W = __shfl_sync(kFullMask, lvW, lv);
@@ -395,12 +413,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
   // Nothing of this warp's items lands inside any image (a camera that does not see these BEV queries): the result
   // is exactly 0 (= 0 / sum), and logits are never read.
   if (__ballot_sync(kFullMask, inr != 0u) == 0u) {
+    if (EPI == 2) continue;                            // next camera
     if (EPI == 0 && active) IO::store_zero(out_item);  // the fused epilogue adds nothing for invisible items
     return;
   }
 
-  // ---- phase B: softmax statistics over the item's NP logits (…Kernel.cu:642-648, :667-669)
-  float lg[ROUNDS][4];
+  // ---- phase B: softmax statistics over the item's NP logits (…Kernel.cu:642-648, :667-669); camera-independent,
+  // so the camera-loop form computes them when the first camera that sees the warp's queries turns up
+  if (EPI != 2 || !have_sm) {
+  have_sm = true;
   float mx = -INFINITY;
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
@@ -414,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
   }
 #pragma unroll
   for (int d = 1; d < LPI; d <<= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, d));
-  float sum = 0.f;
+  sum = 0.f;
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
 #pragma unroll
@@ -425,11 +446,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
   }
 #pragma unroll
   for (int d = 1; d < LPI; d <<= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
+  }
 
   // ---- phase C: gather
-  float acc[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
   const unsigned step_b = static_cast<unsigned>(M * C) * sizeof(T);  // bytes between horizontally adjacent pixels
   const char *vbase = reinterpret_cast<const char *>(static_cast<const T *>(prm.value) +
                                                      (static_cast<long long>(b) * prm.S * M + m) * C + sub * VEC);
@@ -459,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
         otop[k] = top | ((ok && lf && rt) ? 1u : 0u);
         obot[k] = top + ((ok && t && bt) ? static_cast<unsigned>(W) * step_b : 0u);
         const float hh = 1.f - lh, hw = 1.f - lw;
-        const float e = lg[r][k];
+        const float e = EPI == 2 ? lg[r][k] * mk : lg[r][k];  // bev_mask folded into the tap weights
         IO::pack_w(tw[k], (ok && t && lf) ? hh * hw * e : 0.f, (ok && t && rt) ? hh * lw * e : 0.f,
                    (ok && bt && lf) ? lh * hw * e : 0.f, (ok && bt && rt) ? lh * lw * e : 0.f);
       }
@@ -489,8 +508,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
     }
   }
 
+  }  // cameras
+
   if (EPI == 0) {
     if (active) IO::store(out_item, acc, 1.f / sum, prm);
+  } else if (EPI == 2) {
+    // one plain store per (query, head): the camera sum happened in registers, queries no camera sees get zeros
+    if (active) {
+      const float sc = have_sm ? 1.f / sum : 0.f;
+      float *dst = prm.accum + it * C + sub * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4)
+        *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i] * sc, acc[i + 1] * sc, acc[i + 2] * sc, acc[i + 3] * sc);
+    }
   } else {
     // Fused SCA epilogue (reference: slots = (queries * bev_mask).sum(0), spatial_cross_attention.py:270): the
     // per-camera output never goes to memory; visible items add their bev_mask-weighted result into the fp32 BEV
@@ -498,10 +528,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
     unsigned any = inr;
 #pragma unroll
     for (int d = 1; d < LPI; d <<= 1) any |= __shfl_xor_sync(kFullMask, any, d);
-    const float mk = __ldg(prm.mask + bq);
-    if (active && any != 0u && mk != 0.f) {
-      const float sc = mk / sum;
-      float *dst = prm.accum + ((bq - static_cast<long long>(b) * Q) * M + m) * C + sub * VEC;
+    const float mk1 = __ldg(prm.mask + bq0);
+    if (active && any != 0u && mk1 != 0.f) {
+      const float sc = mk1 / sum;
+      float *dst = prm.accum + ((bq0 - (bq0 / Q) * Q) * M + m) * C + sub * VEC;
 #pragma unroll
       for (int i = 0; i < VEC; i += 4)
         asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + i), "f"(acc[i] * sc),
@@ -760,6 +790,30 @@ int b200_msda_sca_f16(const void *value, const int32_t *spatial_shapes, const vo
                              nullptr);
   p.mask = bev_mask, p.accum = accum;
   return dispatch<__half, __half, 0, 1>(p, static_cast<cudaStream_t>(stream));
+}
+
+int b200_msda_sca_shared_f32(const float *value, const int32_t *spatial_shapes, const float *reference_points,
+                             const float *sampling_offsets, const float *attn_weight, const float *bev_mask,
+                             int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                             int num_point, int points_per_group, float *slots, void *stream) {
+  MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, points_per_group,
+                             nullptr);
+  p.mask = bev_mask, p.accum = slots;
+  p.items = static_cast<long long>(num_query) * num_heads;  // one item per (query, head); cameras are looped inside
+  return dispatch<float, float, 0, 2>(p, static_cast<cudaStream_t>(stream));
+}
+
+int b200_msda_sca_shared_f16(const void *value, const int32_t *spatial_shapes, const void *reference_points,
+                             const void *sampling_offsets, const void *attn_weight, const float *bev_mask, int batch,
+                             int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                             int num_point, int points_per_group, float *slots, void *stream) {
+  MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, points_per_group,
+                             nullptr);
+  p.mask = bev_mask, p.accum = slots;
+  p.items = static_cast<long long>(num_query) * num_heads;
+  return dispatch<__half, __half, 0, 2>(p, static_cast<cudaStream_t>(stream));
 }
 
 int b200_msda_debug_indices(int dtype, const int32_t *spatial_shapes, const void *reference_points,

@@ -15,9 +15,9 @@
 //   reference_points_cam[c, 0, q, d, :] = uv                                           (:251 permute(2, 1, 3, 0, 4))
 //   seen[c, q] = any_d vis;  bev_mask[c, q, 0] = seen / max(sum_c seen, 1e-4)          (:252-254)
 //
-// One thread owns one query: the camera matrices sit in shared memory, the D pillar points and the per-camera `seen`
-// bits in registers, and each camera's D x 2 coordinates leave as 128-bit stores (consecutive threads = consecutive
-// queries = contiguous output). The 4x4 product is summed left to right with separately rounded operations (no FMA),
+// One thread owns one (query, camera) pair — 240 000 threads at base size, a CTA = 64 queries x all cameras: the camera
+// matrices and the per-query `seen` bits sit in shared memory, and each thread's D x 2 coordinates leave as 128-bit
+// stores (consecutive threads = consecutive queries = contiguous output). The 4x4 product is summed left to right with separately rounded operations (no FMA),
 // which is bit-identical to oracle/point_sampling.py; the reference's comes from a batched matmul whose summation
 // order is the BLAS backend's, so against the reference itself parity is a tolerance (2e-5 relative where the depth is
 // well conditioned), and `vis` may differ for points within that rounding of an image border.
@@ -52,57 +52,56 @@ __device__ __forceinline__ unsigned short f2h_sat(float x) {  // finite-saturati
   return r;
 }
 
+constexpr int kQPerBlock = 64;
+
+// blockDim = (kQPerBlock, cams): thread (tx, c) projects the D pillar points of query blockIdx.x * 64 + tx into camera c.
 template <int D>
-__global__ void __launch_bounds__(128) point_sampling_kernel(const PsParams p) {
+__global__ void __launch_bounds__(kQPerBlock *kMaxCams) point_sampling_kernel(const PsParams p) {
   __shared__ float sm[kMaxCams * 16];
-  for (int i = threadIdx.x; i < p.cams * 16; i += blockDim.x) sm[i] = __ldg(p.lidar2img + i);
+  __shared__ unsigned seen_sm[kQPerBlock];  // bit c: camera c sees at least one pillar point of the query
+  const int tid = threadIdx.y * kQPerBlock + threadIdx.x;
+  for (int i = tid; i < p.cams * 16; i += kQPerBlock * blockDim.y) sm[i] = __ldg(p.lidar2img + i);
+  if (tid < kQPerBlock) seen_sm[tid] = 0;
   __syncthreads();
   const int Q = p.H * p.W;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= Q) return;
-  const int w = q % p.W, h = q / p.W;
-
-  float px[D], py[D], pz[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    float rx, ry, rz;
-    if (p.ref3d) {
-      const size_t o = (static_cast<size_t>(d) * Q + q) * 3;
-      if (p.out_half) {
-        const __half *r = static_cast<const __half *>(p.ref3d) + o;
-        rx = __half2float(r[0]), ry = __half2float(r[1]), rz = __half2float(r[2]);
-      } else {
-        const float *r = static_cast<const float *>(p.ref3d) + o;
-        rx = __ldg(r), ry = __ldg(r + 1), rz = __ldg(r + 2);
-      }
-    } else {
-      rx = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.W), 0.5f), p.W, w), static_cast<float>(p.W));
-      ry = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.H), 0.5f), p.H, h), static_cast<float>(p.H));
-      rz = __fdiv_rn(linspace_at(0.5f, __fsub_rn(p.z_span, 0.5f), D, d), p.z_span);
-    }
-    px[d] = __fadd_rn(__fmul_rn(rx, p.ext[0]), p.lo[0]);
-    py[d] = __fadd_rn(__fmul_rn(ry, p.ext[1]), p.lo[1]);
-    pz[d] = __fadd_rn(__fmul_rn(rz, p.ext[2]), p.lo[2]);
-  }
-
-  unsigned seen = 0;  // bit c: camera c sees at least one pillar point of this query
-  for (int c = 0; c < p.cams; ++c) {
+  const int q = blockIdx.x * kQPerBlock + threadIdx.x, c = threadIdx.y;
+  const bool live = q < Q;
+  if (live) {
+    const int w = q % p.W, h = q / p.W;
     const float *m = sm + c * 16;
     float uv[2 * D];
     bool any = false;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
+      float rx, ry, rz;
+      if (p.ref3d) {
+        const size_t o = (static_cast<size_t>(d) * Q + q) * 3;
+        if (p.out_half) {
+          const __half *r = static_cast<const __half *>(p.ref3d) + o;
+          rx = __half2float(r[0]), ry = __half2float(r[1]), rz = __half2float(r[2]);
+        } else {
+          const float *r = static_cast<const float *>(p.ref3d) + o;
+          rx = __ldg(r), ry = __ldg(r + 1), rz = __ldg(r + 2);
+        }
+      } else {
+        rx = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.W), 0.5f), p.W, w), static_cast<float>(p.W));
+        ry = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.H), 0.5f), p.H, h), static_cast<float>(p.H));
+        rz = __fdiv_rn(linspace_at(0.5f, __fsub_rn(p.z_span, 0.5f), D, d), p.z_span);
+      }
+      const float px = __fadd_rn(__fmul_rn(rx, p.ext[0]), p.lo[0]);
+      const float py = __fadd_rn(__fmul_rn(ry, p.ext[1]), p.lo[1]);
+      const float pz = __fadd_rn(__fmul_rn(rz, p.ext[2]), p.lo[2]);
       // left-to-right, separately rounded (what a plain 4-term dot product does; no FMA contraction)
-      const float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], px[d]), __fmul_rn(m[1], py[d])), __fmul_rn(m[2], pz[d])), m[3]);
-      const float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], px[d]), __fmul_rn(m[5], py[d])), __fmul_rn(m[6], pz[d])), m[7]);
-      const float cz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], px[d]), __fmul_rn(m[9], py[d])), __fmul_rn(m[10], pz[d])), m[11]);
+      const float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], px), __fmul_rn(m[1], py)), __fmul_rn(m[2], pz)), m[3]);
+      const float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], px), __fmul_rn(m[5], py)), __fmul_rn(m[6], pz)), m[7]);
+      const float cz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], px), __fmul_rn(m[9], py)), __fmul_rn(m[10], pz)), m[11]);
       const float eps = 1e-5f;
       const float den = fmaxf(cz, eps);
       const float u = __fdiv_rn(__fdiv_rn(cx, den), p.img_w), v = __fdiv_rn(__fdiv_rn(cy, den), p.img_h);
       any |= cz > eps && v > 0.f && v < 1.f && u < 1.f && u > 0.f;
       uv[2 * d] = u, uv[2 * d + 1] = v;
     }
-    seen |= any ? (1u << c) : 0u;
+    if (any) atomicOr(&seen_sm[threadIdx.x], 1u << c);
     const size_t o = (static_cast<size_t>(c) * Q + q) * (2 * D);
     if (p.out_half) {
       unsigned short *op = static_cast<unsigned short *>(p.ref_cam) + o;
@@ -114,8 +113,10 @@ __global__ void __launch_bounds__(128) point_sampling_kernel(const PsParams p) {
       for (int i = 0; i < 2 * D; ++i) op[i] = uv[i];
     }
   }
-  const float total = fmaxf(static_cast<float>(__popc(seen)), 1e-4f);
-  for (int c = 0; c < p.cams; ++c) {
+  __syncthreads();
+  if (live) {
+    const unsigned seen = seen_sm[threadIdx.x];
+    const float total = fmaxf(static_cast<float>(__popc(seen)), 1e-4f);
     const float wgt = __fdiv_rn((seen >> c) & 1u ? 1.f : 0.f, total);
     if (p.out_half)
       static_cast<__half *>(p.bev_mask)[static_cast<size_t>(c) * Q + q] = __float2half_rn(wgt);
@@ -149,17 +150,18 @@ extern "C" int b200_bev_point_sampling(const void *reference_points, const doubl
   p.z_span = static_cast<float>(pc_range[5] - pc_range[2]);
   p.img_w = static_cast<float>(image_w), p.img_h = static_cast<float>(image_h);
   const int Q = bev_h * bev_w;
-  const unsigned blocks = (Q + 127) / 128;
+  const unsigned blocks = (Q + kQPerBlock - 1) / kQPerBlock;
+  const dim3 threads(kQPerBlock, num_cams);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (num_points_in_pillar) {
-    case 1: point_sampling_kernel<1><<<blocks, 128, 0, s>>>(p); break;
-    case 2: point_sampling_kernel<2><<<blocks, 128, 0, s>>>(p); break;
-    case 3: point_sampling_kernel<3><<<blocks, 128, 0, s>>>(p); break;
-    case 4: point_sampling_kernel<4><<<blocks, 128, 0, s>>>(p); break;
-    case 5: point_sampling_kernel<5><<<blocks, 128, 0, s>>>(p); break;
-    case 6: point_sampling_kernel<6><<<blocks, 128, 0, s>>>(p); break;
-    case 7: point_sampling_kernel<7><<<blocks, 128, 0, s>>>(p); break;
-    default: point_sampling_kernel<8><<<blocks, 128, 0, s>>>(p); break;
+    case 1: point_sampling_kernel<1><<<blocks, threads, 0, s>>>(p); break;
+    case 2: point_sampling_kernel<2><<<blocks, threads, 0, s>>>(p); break;
+    case 3: point_sampling_kernel<3><<<blocks, threads, 0, s>>>(p); break;
+    case 4: point_sampling_kernel<4><<<blocks, threads, 0, s>>>(p); break;
+    case 5: point_sampling_kernel<5><<<blocks, threads, 0, s>>>(p); break;
+    case 6: point_sampling_kernel<6><<<blocks, threads, 0, s>>>(p); break;
+    case 7: point_sampling_kernel<7><<<blocks, threads, 0, s>>>(p); break;
+    default: point_sampling_kernel<8><<<blocks, threads, 0, s>>>(p); break;
   }
   return check_launch();
 }

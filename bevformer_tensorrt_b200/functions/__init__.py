@@ -12,6 +12,7 @@ from .multi_scale_deformable_attn import (
     multi_scale_deformable_attn2,
     multi_scale_deformable_attn_int8,
     multi_scale_deformable_attn_sca,
+    multi_scale_deformable_attn_sca_shared,
 )
 from .point_sampling import bev_point_sampling, get_reference_points_3d, point_sampling_trt
 from .rotate import rotate, rotate2, rotate_chw2, rotate_hwc, rotate_int8
@@ -29,6 +30,7 @@ TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn2)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_int8)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_sca)
+TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_sca_shared)
 
 TRT_FUNCTIONS.register_module(module=rotate)
 TRT_FUNCTIONS.register_module(module=rotate2)

@@ -173,6 +173,55 @@ def multi_scale_deformable_attn_sca(value, value_spatial_shapes, reference_point
     return accum
 
 
+def multi_scale_deformable_attn_sca_shared(value, value_spatial_shapes, reference_points, sampling_offsets,
+                                           attention_weights, bev_mask):
+    """Camera-shared fused SCA sampling. SpatialCrossAttention repeats the BEV query per camera before its
+    ``sampling_offsets`` / ``attention_weights`` Linear layers (spatial_cross_attention.py:254), so those two tensors
+    are ``bs`` identical copies in the plugin call; here they are passed ONCE:
+
+        value [bs, keys, heads, ch], reference_points [bs, nq, 1, 2G], bev_mask [bs, nq(, 1)]
+        sampling_offsets [1 | -, nq, heads, L*P*2], attention_weights [1 | -, nq, heads, L*P]
+
+    Returns slots float32 [nq, heads*ch] = sum_b bev_mask[b] * MSDA(value[b], ref[b], offsets, logits), every element
+    written exactly once (one item per (query, head), cameras looped in registers, softmax evaluated once)."""
+    if not value.is_cuda:
+        raise RuntimeError("multi_scale_deformable_attn_sca_shared: value must be a CUDA tensor (no CPU fallback exists)")
+    if value.dim() != 4:
+        raise ValueError("value must be [bs, num_keys, num_heads, channels]")
+    bs, num_keys, num_heads, channels = value.shape
+    dt = value.dtype
+    if dt not in (torch.float32, torch.float16):
+        raise _lib.B200OpsError("multi_scale_deformable_attn_sca_shared", 1)
+    num_levels = value_spatial_shapes.shape[0]
+    all_points = attention_weights.shape[-1]
+    if all_points % num_levels != 0:
+        raise ValueError("attention_weights last dim must be num_levels * num_points")
+    num_query = bev_mask.numel() // bs
+    points_per_group = reference_points.shape[-1] // 2
+    if sampling_offsets.numel() != num_query * num_heads * all_points * 2:
+        raise ValueError("sampling_offsets must be ONE copy: [num_query, num_heads, num_levels*num_points*2]")
+    if attention_weights.numel() != num_query * num_heads * all_points:
+        raise ValueError("attention_weights must be ONE copy: [num_query, num_heads, num_levels*num_points]")
+    if reference_points.numel() != bs * num_query * points_per_group * 2:
+        raise ValueError("reference_points does not match [bs, num_query, 1, 2*points_per_group]")
+    lib = _lib.load()
+    value = value.contiguous()
+    shapes = _shapes_i32(value_spatial_shapes, value.device)
+    ref = reference_points.to(dt).contiguous()
+    off = sampling_offsets.to(dt).contiguous()
+    w = attention_weights.to(dt).contiguous()
+    mask = bev_mask.reshape(bs, num_query).to(torch.float32).contiguous()
+    slots = torch.empty(num_query, num_heads * channels, dtype=torch.float32, device=value.device)
+    name = "b200_msda_sca_shared_f32" if dt == torch.float32 else "b200_msda_sca_shared_f16"
+    with torch.cuda.device(value.device):
+        st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
+                                mask.data_ptr(), bs, num_keys, num_heads, channels, num_levels, num_query,
+                                all_points // num_levels, points_per_group, slots.data_ptr(),
+                                _lib.current_stream_ptr())  # fmt: skip
+    _lib.check(name, st)
+    return slots
+
+
 def msda_sampling_indices(value_spatial_shapes, reference_points, sampling_offsets, num_heads):
     """Diagnostic: int32 [bs, nq, heads, L*P, 4] records {in_range, h_low, w_low, tap_mask} from the device code."""
     assert reference_points.is_cuda and reference_points.dtype in (torch.float32, torch.float16)

@@ -99,6 +99,24 @@ int b200_msda_sca_f16(const void *value, const int32_t *spatial_shapes, const vo
                       int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
                       int points_per_group, float *accum, void *stream);
 
+/* Camera-shared form of the same fused op. SpatialCrossAttention repeats the BEV query for every camera before the
+ * sampling_offsets / attention_weights Linear layers (spatial_cross_attention.py:254 `query.repeat(num_cams, 1, 1)`), so
+ * the [batch, ...] offsets and logits the plugin receives are `batch` identical copies. Here they are passed once:
+ *     sampling_offsets [num_query, heads, levels*points*2],  attn_weight [num_query, heads, levels*points]
+ *     value [batch, keys, heads, channels], reference_points [batch, num_query, 1, 2*G], bev_mask [batch, num_query]
+ *     slots[q, m*channels + c] = sum_b bev_mask[b, q] * MSDA(value[b], ref[b], offsets, logits)[q, m, c]   (plain store)
+ * One item per (query, head): the softmax is evaluated once, the cameras that see the query are looped in registers and
+ * every slot is written exactly once (no atomics, no pre-zeroed accumulator; queries no camera sees get zeros). The
+ * two Linear layers upstream shrink by `batch`x and 5/6 of the offsets/logits bytes disappear. Same shape limits. */
+int b200_msda_sca_shared_f32(const float *value, const int32_t *spatial_shapes, const float *reference_points,
+                             const float *sampling_offsets, const float *attn_weight, const float *bev_mask,
+                             int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                             int num_point, int points_per_group, float *slots, void *stream);
+int b200_msda_sca_shared_f16(const void *value, const int32_t *spatial_shapes, const void *reference_points,
+                             const void *sampling_offsets, const void *attn_weight, const float *bev_mask, int batch,
+                             int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                             int num_point, int points_per_group, float *slots, void *stream);
+
 /* Test/diagnostic entry: writes, for every (batch, query, head, level*point), the sampling-index record
  * {in_range, h_low, w_low, tap_mask} (4 x int32) computed by the same device code as the kernels above.
  * dtype: 0 = float inputs, 1 = __half inputs. Used by the bit-exact index parity tests. */

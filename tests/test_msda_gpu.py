@@ -354,3 +354,59 @@ def test_fused_sca_base_shapes_vs_plugin_op():
     got = bt.multi_scale_deformable_attn_sca(*ins, mask)
     assert (got - want).abs().max().item() < 1e-3
     assert got.abs().max().item() > 0.1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# camera-shared fused SCA: offsets / logits passed once (the reference repeats the query per camera,
+# spatial_cross_attention.py:254, so the plugin's [bs, ...] offsets / logits are bs identical copies)
+# ---------------------------------------------------------------------------------------------------------------
+def _shared_inputs(cfg, dist, seed, dtype):
+    value, shapes, ref, off, logits = make_msda_inputs(cfg, dist, seed, dtype)
+    off1, lg1 = off[:1].contiguous(), logits[:1].contiguous()
+    rep = (value, shapes, ref, off1.expand_as(off).contiguous(), lg1.expand_as(logits).contiguous())
+    return rep, (value, shapes, ref, off1, lg1)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 1e-3)])
+@pytest.mark.parametrize("name,dist", [("tiny_sca", "G"), ("small_sca", "edge"), ("small_sca", "U")])
+def test_shared_sca_matches_masked_camera_sum_of_oracle(name, dist, dtype, tol):
+    from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img
+
+    cfg = _cfg(name)
+    rep, shared = _shared_inputs(cfg, dist, 103, dtype)
+    if cfg.bev_hw[0] * cfg.bev_hw[1] == cfg.num_query:
+        _, mask = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(cfg.batch))
+    else:
+        mask = (torch.rand(cfg.batch, cfg.num_query, 1, generator=torch.Generator().manual_seed(3)) > 0.4).float()
+        mask[:, :5] = 0  # queries no camera sees must come out as exact zeros (nothing pre-zeroes the output)
+    per_cam = torch.from_numpy(_oracle_f32(rep))  # the plugin call with the repeated tensors
+    want = (per_cam.reshape(cfg.batch, cfg.num_query, -1) * mask).sum(0)
+    out = bt.multi_scale_deformable_attn_sca_shared(*_cuda(shared), mask.cuda())
+    assert out.dtype == torch.float32 and out.shape == want.shape
+    assert (out.cpu() - want).abs().max().item() < tol
+    unseen = (mask.sum(0)[:, 0] == 0)
+    assert unseen.any() and torch.equal(out.cpu()[unseen], torch.zeros_like(out.cpu()[unseen]))
+    # and it is the same function as the per-camera fused op on the repeated tensors
+    other = bt.multi_scale_deformable_attn_sca(*_cuda(rep), mask.cuda())
+    assert (out - other).abs().max().item() < (2e-6 if dtype == torch.float32 else 2e-4)
+    # offsets / logits with or without the leading singleton dimension
+    out2 = bt.multi_scale_deformable_attn_sca_shared(*_cuda(shared[:3]), shared[3][0].cuda(), shared[4][0].cuda(),
+                                                     mask.cuda())  # fmt: skip
+    assert torch.equal(out2, out)
+
+
+def test_shared_sca_base_shapes_and_errors():
+    from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img
+
+    cfg = CONFIGS["base_sca"]
+    rep, shared = _shared_inputs(cfg, "G", 7, torch.float16)
+    _, mask = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(6))
+    want = bt.multi_scale_deformable_attn_sca(*_cuda(rep), mask.cuda())
+    n0 = _lib.launch_count()
+    got = bt.multi_scale_deformable_attn_sca_shared(*_cuda(shared), mask.cuda())
+    assert _lib.launch_count() == n0 + 1  # one kernel, no memset
+    assert (got - want).abs().max().item() < 5e-4 and got.abs().max().item() > 0.1
+    with pytest.raises(ValueError):  # the repeated tensors are not accepted silently
+        bt.multi_scale_deformable_attn_sca_shared(*_cuda(rep), mask.cuda())
+    with pytest.raises(RuntimeError):
+        bt.multi_scale_deformable_attn_sca_shared(*shared, mask)
