@@ -42,7 +42,10 @@ from .functions import (  # noqa: E402
     rotate_int8,
 )
 
+from .host_pipeline import HostMSDA  # noqa: E402
+
 __all__ = [
+    "HostMSDA",
     "TRT_FUNCTIONS",
     "bev_point_sampling",
     "get_reference_points_3d",

@@ -34,16 +34,24 @@ struct PsParams {
   void *bev_mask;          // [cams, Q, 1]
   int cams, H, W, D, out_half;
   float lo[3], ext[3];     // pc_range[0:3], pc_range[3:6] - pc_range[0:3]
-  float z_span;            // Z of get_reference_points_3d (pc_range[5] - pc_range[2] at the call site, encoder.py:284)
+  float zs[kMaxPillars];   // linspace(0.5, Z - 0.5, D) / Z, Z = pc_range[5] - pc_range[2] (encoder.py:172-178, :284)
+  float step_x, step_y;    // linspace steps of the x / y grids (launch constants, evaluated on the host in float)
   float img_w, img_h;      // image_shape[1], image_shape[0] (true divisions, as the exported ONNX Div nodes)
 };
 
-// torch.linspace(start, end, steps)[i] for float (ATen RangeFactories: step in float, symmetric evaluation)
-__device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
-  if (steps == 1) return start;
-  const float step = __fdiv_rn(__fsub_rn(end, start), static_cast<float>(steps - 1));
+// torch.linspace(start, end, steps)[i] for float (ATen RangeFactories: step = (end - start) / (steps - 1) in float,
+// first half counted up from start, second half down from end). The step is a launch constant (host_linspace_step).
+__host__ __device__ __forceinline__ float linspace_at(float start, float end, float step, int steps, int i) {
+#ifdef __CUDA_ARCH__
   return i < steps / 2 ? __fadd_rn(start, __fmul_rn(step, static_cast<float>(i)))
                        : __fsub_rn(end, __fmul_rn(step, static_cast<float>(steps - i - 1)));
+#else
+  volatile float up = step * static_cast<float>(i), down = step * static_cast<float>(steps - i - 1);  // no host FMA
+  return i < steps / 2 ? start + up : end - down;
+#endif
+}
+static float host_linspace_step(float start, float end, int steps) {
+  return steps > 1 ? (end - start) / static_cast<float>(steps - 1) : 0.f;
 }
 
 __device__ __forceinline__ unsigned short f2h_sat(float x) {  // finite-saturating fp32 -> fp16
@@ -71,9 +79,15 @@ __global__ void __launch_bounds__(kQPerBlock *kMaxCams) point_sampling_kernel(co
     const float *m = sm + c * 16;
     float uv[2 * D];
     bool any = false;
+    // x, y of the pillar are the same for all D points; z comes from the host-evaluated table
+    float gx = 0.f, gy = 0.f;
+    if (!p.ref3d) {
+      gx = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.W), 0.5f), p.step_x, p.W, w), static_cast<float>(p.W));
+      gy = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.H), 0.5f), p.step_y, p.H, h), static_cast<float>(p.H));
+    }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      float rx, ry, rz;
+      float rx = gx, ry = gy, rz = p.zs[d];
       if (p.ref3d) {
         const size_t o = (static_cast<size_t>(d) * Q + q) * 3;
         if (p.out_half) {
@@ -83,10 +97,6 @@ __global__ void __launch_bounds__(kQPerBlock *kMaxCams) point_sampling_kernel(co
           const float *r = static_cast<const float *>(p.ref3d) + o;
           rx = __ldg(r), ry = __ldg(r + 1), rz = __ldg(r + 2);
         }
-      } else {
-        rx = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.W), 0.5f), p.W, w), static_cast<float>(p.W));
-        ry = __fdiv_rn(linspace_at(0.5f, __fsub_rn(static_cast<float>(p.H), 0.5f), p.H, h), static_cast<float>(p.H));
-        rz = __fdiv_rn(linspace_at(0.5f, __fsub_rn(p.z_span, 0.5f), D, d), p.z_span);
       }
       const float px = __fadd_rn(__fmul_rn(rx, p.ext[0]), p.lo[0]);
       const float py = __fadd_rn(__fmul_rn(ry, p.ext[1]), p.lo[1]);
@@ -147,7 +157,14 @@ extern "C" int b200_bev_point_sampling(const void *reference_points, const doubl
     p.lo[i] = static_cast<float>(pc_range[i]);
     p.ext[i] = static_cast<float>(pc_range[3 + i] - pc_range[i]);
   }
-  p.z_span = static_cast<float>(pc_range[5] - pc_range[2]);
+  {
+    const float Z = static_cast<float>(pc_range[5] - pc_range[2]), z_end = Z - 0.5f;
+    const float z_step = host_linspace_step(0.5f, z_end, num_points_in_pillar);
+    for (int d = 0; d < num_points_in_pillar; ++d)
+      p.zs[d] = (num_points_in_pillar == 1 ? 0.5f : linspace_at(0.5f, z_end, z_step, num_points_in_pillar, d)) / Z;
+    p.step_x = host_linspace_step(0.5f, static_cast<float>(bev_w) - 0.5f, bev_w);
+    p.step_y = host_linspace_step(0.5f, static_cast<float>(bev_h) - 0.5f, bev_h);
+  }
   p.img_w = static_cast<float>(image_w), p.img_h = static_cast<float>(image_h);
   const int Q = bev_h * bev_w;
   const unsigned blocks = (Q + kQPerBlock - 1) / kQPerBlock;

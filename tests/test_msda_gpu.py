@@ -410,3 +410,27 @@ def test_shared_sca_base_shapes_and_errors():
         bt.multi_scale_deformable_attn_sca_shared(*_cuda(rep), mask.cuda())
     with pytest.raises(RuntimeError):
         bt.multi_scale_deformable_attn_sca_shared(*shared, mask)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-buffer entry (bench.py's e2e leg): per-camera H2D / kernel / D2H pipeline
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_host_pipeline_equals_device_op(dtype):
+    cfg = _cfg("small_sca")
+    host = make_msda_inputs(cfg, "U", 5, dtype)
+    want = bt.multi_scale_deformable_attn(*_cuda(host)).cpu()
+    pinned = [t.pin_memory() if t.is_floating_point() else t for t in host]
+    pipe = bt.HostMSDA(depth=2)  # fewer slots than cameras: slots are recycled inside one call
+    out = pipe(*pinned)
+    pipe.synchronize()
+    assert out.is_pinned() and torch.equal(out, want)
+    # back-to-back calls into the same output buffer, different inputs in between
+    other = make_msda_inputs(cfg, "edge", 6, dtype)
+    pinned2 = [t.pin_memory() if t.is_floating_point() else t for t in other]
+    out2 = pipe(*pinned2)
+    out3 = pipe(*pinned, out=torch.empty_like(out).pin_memory())
+    pipe.synchronize()
+    assert torch.equal(out2, bt.multi_scale_deformable_attn(*_cuda(other)).cpu()) and torch.equal(out3, want)
+    with pytest.raises(RuntimeError):
+        pipe(*_cuda(host))
