@@ -113,14 +113,34 @@ __global__ void __launch_bounds__(kQPerBlock *kMaxCams) point_sampling_kernel(co
     }
     if (any) atomicOr(&seen_sm[threadIdx.x], 1u << c);
     const size_t o = (static_cast<size_t>(c) * Q + q) * (2 * D);
+    // vector stores: a thread's D (u, v) pairs are contiguous (8*D bytes fp32, 4*D bytes fp16) and consecutive threads
+    // are consecutive queries, so a warp writes one contiguous run
     if (p.out_half) {
-      unsigned short *op = static_cast<unsigned short *>(p.ref_cam) + o;
+      uint32_t pk[D];
 #pragma unroll
-      for (int i = 0; i < 2 * D; ++i) op[i] = f2h_sat(uv[i]);  // behind-camera points are ~1e8: saturate, not inf
+      for (int d = 0; d < D; ++d)  // behind-camera points are ~1e8: saturate, not inf
+        pk[d] = static_cast<uint32_t>(f2h_sat(uv[2 * d])) | (static_cast<uint32_t>(f2h_sat(uv[2 * d + 1])) << 16);
+      uint32_t *op = static_cast<uint32_t *>(p.ref_cam) + o / 2;
+      if (D % 4 == 0) {
+#pragma unroll
+        for (int d = 0; d < D; d += 4) *reinterpret_cast<uint4 *>(op + d) = make_uint4(pk[d], pk[d + 1], pk[d + 2], pk[d + 3]);
+      } else if (D % 2 == 0) {
+#pragma unroll
+        for (int d = 0; d < D; d += 2) *reinterpret_cast<uint2 *>(op + d) = make_uint2(pk[d], pk[d + 1]);
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) op[d] = pk[d];
+      }
     } else {
       float *op = static_cast<float *>(p.ref_cam) + o;
+      if (D % 2 == 0) {
 #pragma unroll
-      for (int i = 0; i < 2 * D; ++i) op[i] = uv[i];
+        for (int d = 0; d < D; d += 2)
+          *reinterpret_cast<float4 *>(op + 2 * d) = make_float4(uv[2 * d], uv[2 * d + 1], uv[2 * d + 2], uv[2 * d + 3]);
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) *reinterpret_cast<float2 *>(op + 2 * d) = make_float2(uv[2 * d], uv[2 * d + 1]);
+      }
     }
   }
   __syncthreads();
@@ -148,6 +168,7 @@ extern "C" int b200_bev_point_sampling(const void *reference_points, const doubl
     return B200_ERR_BAD_PARAM;
   if (dtype != 0 && dtype != 1) return B200_ERR_BAD_PARAM;
   if (num_cams > kMaxCams || num_points_in_pillar > kMaxPillars) return B200_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(reference_points_cam) % 16) return B200_ERR_UNSUPPORTED;  // 128-bit stores
   if (static_cast<long long>(bev_h) * bev_w >= (1ll << 28)) return B200_ERR_BAD_PARAM;
   PsParams p{};
   p.lidar2img = lidar2img, p.ref3d = reference_points, p.ref_cam = reference_points_cam, p.bev_mask = bev_mask;

@@ -247,7 +247,7 @@ int b200_rotate_debug_indices(const float *angle, const float *center, const int
  *   bev_mask              [num_cams, Q, 1]        seen / max(sum over cameras of seen, 1e-4)
  *   dtype                 0: float tensors, 1: __half tensors (reference_points in, both outputs; math stays FP32 and
  *                         coordinates of points behind a camera saturate to +-65504 instead of overflowing to inf)
- * num_cams <= 16, num_points_in_pillar <= 8, else B200_ERR_UNSUPPORTED.
+ * num_cams <= 16, num_points_in_pillar <= 8, reference_points_cam 16-byte aligned, else B200_ERR_UNSUPPORTED.
  * ---------------------------------------------------------------------------------------------------------- */
 int b200_bev_point_sampling(const void *reference_points, const double *pc_range, const float *lidar2img,
                             int num_cams, int image_h, int image_w, int bev_h, int bev_w, int num_points_in_pillar,
