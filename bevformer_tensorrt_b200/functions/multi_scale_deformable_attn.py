@@ -45,7 +45,7 @@ def _shapes_i32(value_spatial_shapes, device):
     return value_spatial_shapes.to(device=device, dtype=torch.int32).contiguous()
 
 
-def _msda_forward(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, use_h2):
+def _msda_forward(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, use_h2, out=None):
     dims = _check_inputs(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights)
     bs, _, num_heads, channels, _, num_query, _, _ = dims
     lib = _lib.load()
@@ -57,7 +57,10 @@ def _msda_forward(value, value_spatial_shapes, reference_points, sampling_offset
     ref = reference_points.to(dt).contiguous()
     off = sampling_offsets.to(dt).contiguous()
     w = attention_weights.to(dt).contiguous()
-    out = torch.empty(bs, num_query, num_heads, channels, dtype=dt, device=value.device)
+    if out is None:
+        out = torch.empty(bs, num_query, num_heads, channels, dtype=dt, device=value.device)
+    elif out.dtype != dt or not out.is_contiguous() or out.numel() != bs * num_query * num_heads * channels:
+        raise ValueError("out must be a contiguous [bs, num_query, num_heads, channels] tensor of value's dtype")
     if dt == torch.float32:
         name = "b200_msda_f32"
     else:
@@ -94,6 +97,13 @@ class _MultiScaleDeformableAttnFunction2(_MultiScaleDeformableAttnFunction):
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights):
         return _msda_forward(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, True)
+
+
+def multi_scale_deformable_attn_out(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights,
+                                    out):
+    """The plugin op writing into a caller-owned ``out`` (no allocation on the call path; used by HostMSDA, whose
+    device slots are fixed so that the stream-ordered allocator never has to synchronise)."""
+    return _msda_forward(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, False, out)
 
 
 _multi_scale_deformable_attn_gpu = _MultiScaleDeformableAttnFunction.apply
