@@ -54,6 +54,7 @@ SIGNATURES = {
                                ctypes.POINTER(_vp), _vp, _vp, _i]),
     "b200_msda_supports_format": (_i, [_i, ctypes.POINTER(TensorDesc), _i, _i]),
     "b200_dcn_workspace_size": (ctypes.c_size_t, [_i] * 13),
+    "b200_dcn_i8_workspace_size": (ctypes.c_size_t, [_i] * 15),
     "b200_dcn_set_fused": (_i, [_i]),
     "b200_dcn_pack_weights_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_dcn_f16_ex": (_i, [_vp] * 7 + [_i] * 16 + [_vp]),

@@ -229,6 +229,92 @@ static int dcn_forward(const T *input, const T *weight, const T *bias, const T *
   return B200_OK;
 }
 
+// ---- INT8 for the shapes the fused tensor-core kernel does not take (groups / deformable groups > 1, other channel
+// counts): dequantise into the workspace, run the FP16 gather + cuBLAS path (FP32 accumulation), requantise once.
+// A correctness path: every DCN of the BEVFormer backbones goes through dcn_fused_i8 instead.
+__global__ void dcn_i8_chw4_to_nchw_f16_kernel(const int8_t *in, float scale, __half *out, int C, long long plane,
+                                               long long total) {  // [N, C/4, plane, 4] -> [N, C, plane]
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = idx % plane, nc4 = idx / plane;
+    const long long n = nc4 / (C / 4), c4 = nc4 % (C / 4);
+    const uint32_t u = ldg32(in + idx * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      out[(n * C + c4 * 4 + i) * plane + pix] = __float2half_rn(static_cast<float>(static_cast<int8_t>(u >> (8 * i))) * scale);
+  }
+}
+__global__ void dcn_i8_to_f16_kernel(const int8_t *in, float scale, __half *out, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __float2half_rn(static_cast<float>(in[i]) * scale);
+}
+__global__ void dcn_bias_to_f16_kernel(const void *bias, int is_half, __half *out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = is_half ? static_cast<const __half *>(bias)[i] : __float2half_rn(static_cast<const float *>(bias)[i]);
+}
+__global__ void dcn_f16_to_i8_kernel(const __half *in, float inv_scale, int8_t *out, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<int8_t>(to_int8_sat(__half2float(in[i]) * inv_scale));
+}
+
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
+struct DcnI8Plan {  // byte offsets into the workspace
+  size_t x, w, off, mask, bias, out, col, total;
+};
+static DcnI8Plan dcn_i8_plan(int batch, int channels, int height, int width, int channels_out, int kh, int kw, int Ho,
+                             int Wo, int group, int dg) {
+  DcnI8Plan p{};
+  size_t o = 0;
+  p.x = o, o += align256(static_cast<size_t>(batch) * channels * height * width * 2);
+  p.w = o, o += align256(static_cast<size_t>(channels_out) * (channels / group) * kh * kw * 2);
+  p.off = o, o += align256(static_cast<size_t>(batch) * dg * 2 * kh * kw * Ho * Wo * 2);
+  p.mask = o, o += align256(static_cast<size_t>(batch) * dg * kh * kw * Ho * Wo * 2);
+  p.bias = o, o += align256(static_cast<size_t>(channels_out) * 2);
+  p.out = o, o += align256(static_cast<size_t>(batch) * channels_out * Ho * Wo * 2);
+  p.col = o, o += col_bytes(batch, channels, kh, kw, Ho, Wo, 2);
+  p.total = o;
+  return p;
+}
+
+static unsigned grid_for(long long n) { return static_cast<unsigned>(n / 256 + 1 < (1 << 20) ? n / 256 + 1 : (1 << 20)); }
+
+static int dcn_i8_unfused(const int8_t *input, float scale_i, const int8_t *weight, float scale_w, const void *bias,
+                          int bias_is_half, const int8_t *offset, float scale_off, const int8_t *mask, float scale_mask,
+                          int8_t *output, float scale_o, void *workspace, int batch, int channels, int height, int width,
+                          int channels_out, int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h,
+                          int dilation_w, int dilation_h, int Ho, int Wo, int group, int dg, void *cublas_handle,
+                          cudaStream_t s) {
+  if (group <= 0 || dg <= 0) return B200_ERR_BAD_PARAM;
+  if (channels % 4 || (channels / group) % 4 || channels % group || channels_out % group || channels % dg)
+    return B200_ERR_UNSUPPORTED;  // kCHW4 packs 4 channels; the reference exit(1)s on the group mismatches
+  const DcnI8Plan pl = dcn_i8_plan(batch, channels, height, width, channels_out, kernel_h, kernel_w, Ho, Wo, group, dg);
+  char *ws = static_cast<char *>(workspace);
+  __half *x = reinterpret_cast<__half *>(ws + pl.x), *w = reinterpret_cast<__half *>(ws + pl.w);
+  __half *off = reinterpret_cast<__half *>(ws + pl.off), *msk = reinterpret_cast<__half *>(ws + pl.mask);
+  __half *b = reinterpret_cast<__half *>(ws + pl.bias), *out = reinterpret_cast<__half *>(ws + pl.out);
+  const long long plane = static_cast<long long>(height) * width, kk = static_cast<long long>(kernel_h) * kernel_w;
+  const long long nx = static_cast<long long>(batch) * (channels / 4) * plane;
+  const long long nw = static_cast<long long>(channels_out) * (channels / group / 4) * kk;
+  const long long noff = static_cast<long long>(batch) * dg * 2 * kk * Ho * Wo, nout = static_cast<long long>(batch) * channels_out * Ho * Wo;
+  dcn_i8_chw4_to_nchw_f16_kernel<<<grid_for(nx), 256, 0, s>>>(input, scale_i, x, channels, plane, nx);
+  dcn_i8_chw4_to_nchw_f16_kernel<<<grid_for(nw), 256, 0, s>>>(weight, scale_w, w, channels / group, kk, nw);
+  dcn_i8_to_f16_kernel<<<grid_for(noff), 256, 0, s>>>(offset, scale_off, off, noff);
+  dcn_i8_to_f16_kernel<<<grid_for(noff / 2), 256, 0, s>>>(mask, scale_mask, msk, noff / 2);
+  if (bias) dcn_bias_to_f16_kernel<<<(channels_out + 255) / 256, 256, 0, s>>>(bias, bias_is_half, b, channels_out);
+  g_launch_count.fetch_add(bias ? 4 : 3, std::memory_order_relaxed);
+  int st = check_launch();
+  if (st != B200_OK) return st;
+  st = dcn_forward<__half>(x, w, bias ? b : nullptr, off, msk, out, ws + pl.col, batch, channels, height, width,
+                           channels_out, kernel_w, kernel_h, stride_w, stride_h, pad_w, pad_h, dilation_w, dilation_h,
+                           group, dg, cublas_handle, s);
+  if (st != B200_OK) return st;
+  dcn_f16_to_i8_kernel<<<grid_for(nout), 256, 0, s>>>(out, 1.f / scale_o, output, nout);
+  return check_launch();
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -246,6 +332,20 @@ size_t b200_dcn_workspace_size(int dtype, int batch, int channels, int height, i
   // argument here; 512 is the largest the fused path takes)
   const size_t fused = dtype == 0 ? 0 : dcn_fused_workspace_bytes(batch, channels, height, width, 512, kernel_h * kernel_w);
   return v1 > fused ? v1 : fused;
+}
+
+size_t b200_dcn_i8_workspace_size(int batch, int channels, int height, int width, int channels_out, int kernel_w,
+                                  int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                                  int dilation_h, int group, int deformable_group) {
+  if (stride_h <= 0 || stride_w <= 0 || group <= 0 || deformable_group <= 0) return 0;
+  const int Ho = (height + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
+  const int Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
+  if (Ho <= 0 || Wo <= 0 || batch <= 0 || channels <= 0 || channels_out <= 0) return 0;
+  const size_t fused = b200_dcn_workspace_size(1, batch, channels, height, width, kernel_w, kernel_h, stride_w, stride_h,
+                                               pad_w, pad_h, dilation_w, dilation_h);
+  const size_t unfused = dcn_i8_plan(batch, channels, height, width, channels_out, kernel_h, kernel_w, Ho, Wo, group,
+                                     deformable_group).total;
+  return fused > unfused ? fused : unfused;
 }
 
 int b200_dcn_set_fused(int enabled) {  // enabled < 0: query only
@@ -289,7 +389,7 @@ int b200_dcn_i8(const int8_t *input, float scale_i, const int8_t *weight, float 
                 void *workspace, int batch, int channels, int height, int width, int channels_out, int kernel_w,
                 int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w, int dilation_h, int group,
                 int deformable_group, int im2col_step, void *cublas_handle, void *stream) {
-  (void)im2col_step, (void)cublas_handle;
+  (void)im2col_step;
   if (!input || !weight || !offset || !mask || !output || !workspace) return B200_ERR_BAD_PARAM;
   if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || channels_out <= 0 || kernel_w <= 0 || kernel_h <= 0 ||
       stride_w <= 0 || stride_h <= 0 || dilation_w <= 0 || dilation_h <= 0 || !(scale_o > 0.f))
@@ -297,10 +397,14 @@ int b200_dcn_i8(const int8_t *input, float scale_i, const int8_t *weight, float 
   const int Ho = (height + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
   const int Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
   if (Ho <= 0 || Wo <= 0) return B200_ERR_BAD_PARAM;
-  // INT8 runs on the fused tensor-core path only (every DCN of the BEVFormer backbones qualifies)
-  if (!dcn_fused_supported(channels, channels_out, kernel_h * kernel_w, group, deformable_group) ||
-      reinterpret_cast<uintptr_t>(workspace) % 256 != 0)
-    return B200_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return B200_ERR_UNSUPPORTED;
+  // every DCN of the BEVFormer backbones takes the fused tensor-core path; other shapes dequantise into the workspace
+  // (sized by b200_dcn_i8_workspace_size) and run the gather + cuBLAS path
+  if (!dcn_fused_enabled() || !dcn_fused_supported(channels, channels_out, kernel_h * kernel_w, group, deformable_group))
+    return dcn_i8_unfused(input, scale_i, weight, scale_w, bias, bias_is_half, offset, scale_off, mask, scale_mask,
+                          output, scale_o, workspace, batch, channels, height, width, channels_out, kernel_w, kernel_h,
+                          stride_w, stride_h, pad_w, pad_h, dilation_w, dilation_h, Ho, Wo, group, deformable_group,
+                          cublas_handle, static_cast<cudaStream_t>(stream));
   return dcn_fused_i8(input, scale_i, weight, scale_w, bias, bias_is_half, offset, scale_off, mask, scale_mask, output,
                       scale_o, workspace, batch, channels, height, width, channels_out, kernel_w, kernel_h, stride_w,
                       stride_h, pad_w, pad_h, dilation_w, dilation_h, Ho, Wo, static_cast<cudaStream_t>(stream));

@@ -138,7 +138,9 @@ def modulated_deformable_conv2d_int8(input_chw4, scale_i, offset_q, scale_off, m
     """INT8 flavour of the plugin (…Conv2dPlugin.cpp:117-199 / launcher …Conv2dKernel.h:21-29): ``input_chw4`` int8
     [N, C/4, H, W, 4] and ``weight_chw4`` int8 [Co, C/4, kh, kw, 4] in TensorRT's kCHW4 layout
     (``functions.grid_sampler.pack_chw(x, 4)``), ``offset_q`` / ``mask_q`` int8 NCHW, per-tensor scales
-    (real = q*scale), ``bias`` float32/float16 or None. Returns int8 [N, Co, Ho, Wo] at ``scale_o``."""
+    (real = q*scale), ``bias`` float32/float16 or None. Returns int8 [N, Co, Ho, Wo] at ``scale_o``. Backbone shapes
+    run on the fused tensor-core kernel; other shapes (groups / deform_groups > 1, small channel counts) dequantise
+    into the workspace and take the gather + cuBLAS path."""
     assert input_chw4.is_cuda and input_chw4.dtype == torch.int8 and input_chw4.shape[-1] == 4
     (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
     n, c4, h, w, _ = input_chw4.shape
@@ -147,8 +149,11 @@ def modulated_deformable_conv2d_int8(input_chw4, scale_i, offset_q, scale_off, m
         raise ValueError("channels must be a multiple of 4 and match the packed tensors")
     ho = (h + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
     wo = (w + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    if tuple(offset_q.shape) != (n, deform_groups * 2 * kh * kw, ho, wo) or \
+            tuple(mask_q.shape) != (n, deform_groups * kh * kw, ho, wo):
+        raise ValueError("offset / mask must be [N, deform_groups*2*kh*kw, Ho, Wo] / [N, deform_groups*kh*kw, Ho, Wo]")
     lib = _lib.load()
-    ws_bytes = lib.b200_dcn_workspace_size(1, n, channels, h, w, kw, kh, sw, sh, pw, ph, dw, dh)
+    ws_bytes = lib.b200_dcn_i8_workspace_size(n, channels, h, w, co, kw, kh, sw, sh, pw, ph, dw, dh, groups, deform_groups)
     workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=input_chw4.device)
     out = torch.empty(n, co, ho, wo, dtype=torch.int8, device=input_chw4.device)
     x, wt, off, msk = (t.contiguous() for t in (input_chw4, weight_chw4, offset_q, mask_q))

@@ -302,9 +302,14 @@ int b200_dcn_f16_ex(const void *input, const void *weight, const void *bias, con
  * int8 kLINEAR, output int8 kLINEAR, per-tensor scales (real = q*scale); bias float (bias_is_half == 0), __half, or NULL.
  * Arithmetic: in-register dequantisation (int8 values are exact in FP16), FP16 tensor-core products with FP32
  * accumulation, one requantisation T2int8((acc*scale_i*scale_w + bias)/scale_o) — the reference requantises the
- * sampled columns to int8 first (:536-545). Runs on the fused path only: groups == deformable_groups == 1,
- * channels % 64 == 0, channels_out in {128, 256, 512}; B200_ERR_UNSUPPORTED otherwise. workspace: b200_dcn_workspace_size
- * with dtype 1. */
+ * sampled columns to int8 first (:536-545). Shapes of the fused path (groups == deformable_groups == 1,
+ * channels % 64 == 0, channels_out in {128, 256, 512}) run on tensor cores in one kernel; any other shape with
+ * channels % 4 == 0 and (channels / group) % 4 == 0 dequantises into the workspace and runs the gather + cuBLAS FP16
+ * path (FP32 accumulation), one requantisation at the end. workspace: b200_dcn_i8_workspace_size(...) bytes,
+ * 256-byte aligned. */
+size_t b200_dcn_i8_workspace_size(int batch, int channels, int height, int width, int channels_out, int kernel_w,
+                                  int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                                  int dilation_h, int group, int deformable_group);
 int b200_dcn_i8(const int8_t *input, float scale_i, const int8_t *weight, float scale_w, const void *bias, int bias_is_half,
                 const int8_t *offset, float scale_off, const int8_t *mask, float scale_mask, int8_t *output, float scale_o,
                 void *workspace, int batch, int channels, int height, int width, int channels_out, int kernel_w,

@@ -169,8 +169,32 @@ def test_int8_matches_dequant_oracle(case, bias_dtype):
     assert got.dtype == torch.int8 and tuple(got.shape) == real.shape
     err = np.abs(got.cpu().numpy().astype(np.float32) * sout - real).max()
     assert err <= 0.75 * sout, (err, sout)  # half a step from the requantisation + fp16 column rounding
-    # unsupported shapes are a status, not a crash
-    with pytest.raises(_lib.B200OpsError):
+    # tensors that do not match the declared deform_groups are rejected before anything is launched
+    with pytest.raises(ValueError):
         bt.modulated_deformable_conv2d_int8(pack_chw(xq, 4).cuda(), si, oq.cuda(), so_, mq.cuda(), sm,
                                             pack_chw(wq, 4).cuda(), sw, None, sout, x.shape[1], kw["stride"],
-                                            kw["padding"], kw["dilation"], 1, 2)  # deform_groups = 2: not on the fused path
+                                            kw["padding"], kw["dilation"], 1, 2)
+
+
+@pytest.mark.parametrize("case", ["k3_s1_p1_g2_dg2", "k3_s2_p1_g1_dg1", "k3_s1_p2_d2_g1_dg4", "k3x5_s1_p1_g1_dg1",
+                                  "backbone_like"])  # fmt: skip
+def test_int8_unfused_shapes_match_dequant_oracle(case):
+    """INT8 for the shapes the fused kernel does not take (groups / deformable groups > 1, small or odd channel
+    counts): dequantise -> gather + cuBLAS FP16 path -> one requantisation."""
+    from bevformer_tensorrt_b200.functions.grid_sampler import pack_chw
+    from bevformer_tensorrt_b200.workloads import quantize_per_tensor
+
+    x, off, mask, w, b, kw = make_dcn_inputs(case)
+    xq, si = quantize_per_tensor(x)
+    oq, so_ = quantize_per_tensor(off)
+    mq, sm = quantize_per_tensor(mask)
+    wq, sw = quantize_per_tensor(w)
+    real = odcn.modulated_deformable_conv2d(xq.float().numpy() * si, oq.float().numpy() * so_, mq.float().numpy() * sm,
+                                            wq.float().numpy() * sw, b.numpy(), **kw)
+    sout = float(np.abs(real).max()) / 127.0
+    got = bt.modulated_deformable_conv2d_int8(
+        pack_chw(xq, 4).cuda(), si, oq.cuda(), so_, mq.cuda(), sm, pack_chw(wq, 4).cuda(), sw, b.cuda(), sout,
+        x.shape[1], kw["stride"], kw["padding"], kw["dilation"], kw["groups"], kw["deform_groups"])
+    assert got.dtype == torch.int8 and tuple(got.shape) == real.shape
+    err = np.abs(got.cpu().numpy().astype(np.float32) * sout - real).max()
+    assert err <= 0.75 * sout, (err, sout)
