@@ -73,15 +73,39 @@ class Plugin final : public IPluginV2DynamicExt {
         return (d.type == DataType::kFLOAT || d.type == DataType::kHALF) && d.type == io[1].type;
       return d.type == img.type;
     }
-    // grid sampler / DCN: fp32 or fp16, linear, every tensor the same type (the packed kCHW2 / kCHW4 variants of the
-    // reference map to b200_grid_sample_f16_chw2 / _i8_chw4 and are negotiated the same way when enabled)
-    const bool ok_type = io[pos].type == DataType::kFLOAT || io[pos].type == DataType::kHALF;
-    return ok_type && io[pos].format == TensorFormat::kLINEAR && io[pos].type == io[0].type;
+    const PluginTensorDesc &d = io[pos], &x = io[0];
+    if (op_ == Op::kGridSampler2D) {  // gridSamplerPlugin.cpp:168-194: …TRT2 negotiates kCHW2 for FP16; INT8 is kCHW4
+      if (pos != 0) return d.type == x.type && d.format == x.format;
+      if (d.type == DataType::kINT8) return d.format == TensorFormat::kCHW4;
+      if (d.type == DataType::kHALF) return d.format == (v2_ ? TensorFormat::kCHW2 : TensorFormat::kLINEAR);
+      return d.type == DataType::kFLOAT && d.format == TensorFormat::kLINEAR;
+    }
+    // DCN (…Conv2dPlugin.cpp:213-250): fp32 / fp16 linear everywhere; INT8: input and weight kCHW4, offset / mask /
+    // output int8 linear, bias fp32 or fp16 linear. (The reference's kCHW2 FP16 variant is not offered: TensorRT
+    // reformats to linear in front of the plugin.)
+    const bool int8_ok = x.dims.d[1] % 4 == 0 && (io[nbIn].dims.d[1] / a_.groups) % 4 == 0;
+    if (pos == 0) {
+      if (d.type == DataType::kINT8) return d.format == TensorFormat::kCHW4 && int8_ok;
+      return (d.type == DataType::kFLOAT || d.type == DataType::kHALF) && d.format == TensorFormat::kLINEAR;
+    }
+    if (x.type == DataType::kINT8) {
+      if (nbIn == 5 && pos == 4)
+        return (d.type == DataType::kFLOAT || d.type == DataType::kHALF) && d.format == TensorFormat::kLINEAR;
+      if (pos == 3) return d.type == DataType::kINT8 && d.format == TensorFormat::kCHW4;
+      return d.type == DataType::kINT8 && d.format == TensorFormat::kLINEAR;  // offset, mask, output
+    }
+    (void)nbOut;
+    return d.type == x.type && d.format == TensorFormat::kLINEAR;
   }
-  void configurePlugin(const DynamicPluginTensorDesc *, int32_t, const DynamicPluginTensorDesc *, int32_t) noexcept override {}
+  void configurePlugin(const DynamicPluginTensorDesc *, int32_t nbIn, const DynamicPluginTensorDesc *, int32_t) noexcept override {
+    nb_inputs_ = nbIn;  // DCN: 4 inputs without bias, 5 with (…Conv2dPlugin.cpp:297-299)
+  }
   size_t getWorkspaceSize(const PluginTensorDesc *in, int32_t, const PluginTensorDesc *, int32_t) const noexcept override {
     if (op_ != Op::kDCN) return 0;  // MSDA / grid sampler / rotate need none (…Plugin.cpp:64-69)
     const Dims &x = in[0].dims, &w = in[3].dims;
+    if (in[0].type == DataType::kINT8)
+      return b200_dcn_i8_workspace_size(x.d[0], x.d[1], x.d[2], x.d[3], w.d[0], w.d[3], w.d[2], a_.stride[1], a_.stride[0],
+                                        a_.pad[1], a_.pad[0], a_.dil[1], a_.dil[0], a_.groups, a_.deform_groups);
     return b200_dcn_workspace_size(in[0].type == DataType::kHALF, x.d[0], x.d[1], x.d[2], x.d[3], w.d[3], w.d[2],
                                    a_.stride[1], a_.stride[0], a_.pad[1], a_.pad[0], a_.dil[1], a_.dil[0]);
   }
@@ -111,10 +135,25 @@ class Plugin final : public IPluginV2DynamicExt {
         return b200_grid_sample_f32(static_cast<float *>(outputs[0]), static_cast<const float *>(inputs[0]),
                                     static_cast<const float *>(inputs[1]), od, id, gd, 4, a_.interp, a_.padding, a_.align,
                                     stream);
+      if (in[0].type == DataType::kINT8)  // kCHW4, scales from the tensor descriptors (gridSamplerPlugin.cpp:114-116)
+        return b200_grid_sample_i8_chw4(static_cast<int8_t *>(outputs[0]), out[0].scale,
+                                        static_cast<const int8_t *>(inputs[0]), in[0].scale,
+                                        static_cast<const int8_t *>(inputs[1]), in[1].scale, od, id, gd, 4, a_.interp,
+                                        a_.padding, a_.align, stream);
+      if (in[0].format == TensorFormat::kCHW2)
+        return b200_grid_sample_f16_chw2(outputs[0], inputs[0], inputs[1], od, id, gd, 4, a_.interp, a_.padding, a_.align,
+                                         stream);
       return b200_grid_sample_f16(outputs[0], inputs[0], inputs[1], od, id, gd, 4, a_.interp, a_.padding, a_.align, stream);
     }
     const Dims &x = in[0].dims, &w = in[3].dims;  // inputs: x, offset, mask, weight[, bias] (…Conv2dPlugin.cpp:117-160)
     const void *bias = nb_inputs_ == 5 ? inputs[4] : nullptr;
+    if (in[0].type == DataType::kINT8)  // scales: input, weight, offset, mask, output (…Conv2dPlugin.cpp:161-199)
+      return b200_dcn_i8(static_cast<const int8_t *>(inputs[0]), in[0].scale, static_cast<const int8_t *>(inputs[3]),
+                         in[3].scale, bias, nb_inputs_ == 5 && in[4].type == DataType::kHALF,
+                         static_cast<const int8_t *>(inputs[1]), in[1].scale, static_cast<const int8_t *>(inputs[2]),
+                         in[2].scale, static_cast<int8_t *>(outputs[0]), out[0].scale, workspace, x.d[0], x.d[1], x.d[2],
+                         x.d[3], w.d[0], w.d[3], w.d[2], a_.stride[1], a_.stride[0], a_.pad[1], a_.pad[0], a_.dil[1],
+                         a_.dil[0], a_.groups, a_.deform_groups, x.d[0], nullptr, stream);
     if (in[0].type == DataType::kFLOAT)
       return b200_dcn_f32(static_cast<const float *>(inputs[0]), static_cast<const float *>(inputs[3]),
                           static_cast<const float *>(bias), static_cast<const float *>(inputs[1]),
