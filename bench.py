@@ -283,9 +283,15 @@ def run_e2e(args, cfg, host):
 
     td = {"f16": torch.float16, "f32": torch.float32, "i8": torch.float16}[args.dtype]
     value, shapes, ref, off, logits = host
-    pinned = [value.to(td).pin_memory(), ref.to(td).pin_memory(), off.to(td).pin_memory(), logits.to(td).pin_memory()]
+    # staging buffers from cudaHostAlloc (bt.empty_pinned): tensor.pin_memory() measured 40-49 GB/s on this box
+    # depending on where its pages were first touched, cudaHostAlloc 55 GB/s every time (profiles/r01_micro_h2d_bw.json)
+    pinned = []
+    for t in (value, ref, off, logits):
+        h = bt.empty_pinned(t.shape, td)
+        h.copy_(t.to(td))
+        pinned.append(h)
     shapes_d = shapes.cuda()
-    out_host = torch.empty(cfg.batch, cfg.num_query, cfg.num_heads, cfg.channels, dtype=td).pin_memory()
+    out_host = bt.empty_pinned((cfg.batch, cfg.num_query, cfg.num_heads, cfg.channels), td)
     h2d = sum(t.numel() * t.element_size() for t in pinned)
     d2h = out_host.numel() * out_host.element_size()
 

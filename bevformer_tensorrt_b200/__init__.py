@@ -42,10 +42,11 @@ from .functions import (  # noqa: E402
     rotate_int8,
 )
 
-from .host_pipeline import HostMSDA  # noqa: E402
+from .host_pipeline import HostMSDA, empty_pinned  # noqa: E402
 
 __all__ = [
     "HostMSDA",
+    "empty_pinned",
     "TRT_FUNCTIONS",
     "bev_point_sampling",
     "get_reference_points_3d",

@@ -11,9 +11,42 @@ pipelined call is bound by the larger of the two copy directions (H2D: 467 MB pe
 
 No CPU fallback: the kernels are the sm_100a ones behind ``multi_scale_deformable_attn``.
 """
+import ctypes
+import math
+
 import torch
 
 from .functions.multi_scale_deformable_attn import multi_scale_deformable_attn_out
+
+_cudart = None
+_live = {}  # data_ptr -> keeps the host allocations of empty_pinned alive until the process exits
+
+
+def empty_pinned(shape, dtype=torch.float16):
+    """Page-locked host tensor straight from ``cudaHostAlloc``. Measured on the B200 box (scripts/micro/numa_pin.py):
+    55 GB/s host-to-device from such a buffer wherever the calling thread runs, against 40-49 GB/s from
+    ``tensor.pin_memory()``, whose staging copy lets the first-touch NUMA node of the pages vary. Use it for the
+    staging buffers handed to ``HostMSDA`` (the memory lives until the process exits)."""
+    global _cudart
+    if _cudart is None:
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                _cudart = ctypes.CDLL(name)
+                break
+            except OSError:
+                continue
+        else:
+            raise ImportError("libcudart not found: empty_pinned needs the CUDA runtime")
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    nbytes = max(1, math.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    ptr = ctypes.c_void_p()
+    err = _cudart.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(nbytes), ctypes.c_uint(0))
+    if err != 0 or not ptr.value:
+        raise MemoryError(f"cudaHostAlloc({nbytes}) failed with error {err}")
+    buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+    t = torch.frombuffer(buf, dtype=dtype, count=math.prod(shape)).view(shape)
+    _live[ptr.value] = buf
+    return t
 
 
 class HostMSDA:

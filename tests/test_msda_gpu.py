@@ -420,7 +420,15 @@ def test_host_pipeline_equals_device_op(dtype):
     cfg = _cfg("small_sca")
     host = make_msda_inputs(cfg, "U", 5, dtype)
     want = bt.multi_scale_deformable_attn(*_cuda(host)).cpu()
-    pinned = [t.pin_memory() if t.is_floating_point() else t for t in host]
+    pinned = []
+    for t in host:  # staging buffers from cudaHostAlloc (the recommended way), shapes stay a plain tensor
+        if t.is_floating_point():
+            h = bt.empty_pinned(t.shape, t.dtype)
+            assert h.is_pinned() and h.shape == t.shape and h.dtype == t.dtype
+            h.copy_(t)
+            pinned.append(h)
+        else:
+            pinned.append(t)
     pipe = bt.HostMSDA(depth=2)  # fewer slots than cameras: slots are recycled inside one call
     out = pipe(*pinned)
     pipe.synchronize()
