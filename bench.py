@@ -51,7 +51,9 @@ def parse():
     ap.add_argument("--wire", default="f16", choices=["f16", "f32"], help="N>1: dtype of the accumulator on the wire")
     ap.add_argument("--unfused", action="store_true", help="N>1: plugin op + torch camera-sum instead of the fused kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="N>1: do not capture the sharded step into a CUDA graph")
+    ap.add_argument("--graph", action="store_true",
+                    help="N>1: capture the sharded step (kernels + NCCL all-reduce) into a CUDA graph. Off by default: "
+                         "on this image (torch 2.11 / NCCL 2.28.9) the capture of the collective hung at N=2")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other distribution / INT8) legs")
     return ap.parse_args()
 
@@ -278,6 +280,23 @@ def run_single(args, cfg, peak, peak_src):
     return out, fn, dev, host
 
 
+class stdout_to_stderr:
+    """File-descriptor level redirect of stdout (fd 1) into stderr (fd 2) for the duration of the block — catches
+    output written by native libraries (NCCL's banner), not only Python's print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def run_e2e(args, cfg, host):
     """Public-API call with pinned host buffers: H2D of the step's inputs + kernel + D2H of the result, per step."""
     import bevformer_tensorrt_b200 as bt
@@ -383,7 +402,7 @@ def run_multi(args, cfg, peak, peak_src):
         sampler.step()
     torch.cuda.synchronize()
     graphed = False
-    if not args.no_graph:
+    if args.graph:
         # the whole step (memset, kernels, wire conversion, all-reduce) as one CUDA graph; eager fallback if the capture
         # or its check fails on any rank (all ranks take the same branch: the flag is all-reduced)
         want = sampler.step().clone()
@@ -525,17 +544,10 @@ def main():
     if world > 1:
         # NCCL prints its version banner to stdout at communicator creation when the box sets NCCL_DEBUG=VERSION; the
         # contract is ONE JSON line on stdout, so everything the run itself emits goes to stderr until the line is ready
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
+        with stdout_to_stderr():
             out = run_multi(args, cfg, peak, peak_src)
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
         if out is not None:
-            print(json.dumps(out))
+            print(json.dumps(out), flush=True)
         return
 
     out, fn, dev, host = run_single(args, cfg, peak, peak_src)

@@ -175,3 +175,19 @@ def test_tensorrt_plugin_shell_compiles_against_the_mock_api():
     for name in ("MultiScaleDeformableAttnTRT", "MultiScaleDeformableAttnTRT2", "GridSampler2DTRT", "GridSampler2DTRT2",
                  "ModulatedDeformableConv2dTRT", "ModulatedDeformableConv2dTRT2"):  # fmt: skip
         assert f'"{name}"' in text
+
+
+def test_bench_stdout_redirect_keeps_native_output_off_stdout():
+    """bench.py at N>1 must print exactly one JSON line on stdout although NCCL writes a banner to fd 1."""
+    code = (
+        "import importlib.util, os, sys\n"
+        f"spec = importlib.util.spec_from_file_location('bench', {os.path.join(ROOT, 'bench.py')!r})\n"
+        "bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)\n"
+        "with bench.stdout_to_stderr():\n"
+        "    os.write(1, b'native banner\\n'); print('python inside')\n"
+        "print('{\"only\": 1}', flush=True)\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == '{"only": 1}'
+    assert "native banner" in r.stderr and "python inside" in r.stderr
