@@ -179,6 +179,9 @@ def test_tensorrt_plugin_shell_compiles_against_the_mock_api():
 
 def test_bench_stdout_redirect_keeps_native_output_off_stdout():
     """bench.py at N>1 must print exactly one JSON line on stdout although NCCL writes a banner to fd 1."""
+    import subprocess
+    import sys
+
     code = (
         "import importlib.util, os, sys\n"
         f"spec = importlib.util.spec_from_file_location('bench', {os.path.join(ROOT, 'bench.py')!r})\n"
