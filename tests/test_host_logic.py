@@ -194,3 +194,38 @@ def test_bench_stdout_redirect_keeps_native_output_off_stdout():
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip() == '{"only": 1}'
     assert "native banner" in r.stderr and "python inside" in r.stderr
+
+
+def test_reference_points_3d_matches_reference_golden_on_cpu():
+    """get_reference_points_3d is plain tensor construction: on the CPU it reproduces the reference's tensor bit for
+    bit (the GPU-side consumers are covered by tests/test_point_sampling_gpu.py)."""
+    from tests.helpers import GOLDEN, POINT_SAMPLING_CASES
+
+    z = np.load(os.path.join(GOLDEN, "point_sampling_ref.npz"))
+    for case, (H, W, D, _, pc_range) in POINT_SAMPLING_CASES.items():
+        got = bt.get_reference_points_3d(H, W, pc_range[5] - pc_range[2], D, device="cpu")
+        assert got.shape == (1, D, H * W, 3)
+        assert np.array_equal(got.numpy().reshape(-1), z[f"{case}_ref3d"].reshape(-1)), case
+
+
+def test_rotate_recognises_channels_last_views_only():
+    from bevformer_tensorrt_b200.functions.rotate import _is_hwc_view
+
+    bev = torch.zeros(50 * 46, 1, 64)
+    assert _is_hwc_view(bev.view(50, 46, 64).permute(2, 0, 1))           # BEVFormer's call-site expression
+    assert not _is_hwc_view(bev.view(50, 46, 64).permute(2, 0, 1).contiguous())
+    assert not _is_hwc_view(torch.zeros(64, 50, 46))
+    assert not _is_hwc_view(torch.zeros(50, 46, 64).permute(2, 1, 0))     # transposed spatial dims: not [H, W, C] memory
+    assert not _is_hwc_view(torch.zeros(50, 46, 128)[:, :, ::2].permute(2, 0, 1))  # strided channels
+
+
+def test_cpu_tensors_are_refused_by_the_new_ops():
+    for call in (lambda: bt.rotate(torch.zeros(4, 5, 5), torch.tensor(1.0), torch.tensor([2.0, 2.0])),
+                 lambda: bt.rotate_hwc(torch.zeros(5, 5, 4), torch.tensor(1.0), torch.tensor([2.0, 2.0])),
+                 lambda: bt.point_sampling_trt(torch.zeros(1, 4, 9, 3), (-1, -1, -1, 1, 1, 1), torch.eye(4)[None], (8, 8)),
+                 lambda: bt.bev_point_sampling(3, 3, (-1, -1, -1, 1, 1, 1), torch.eye(4)[None], (8, 8)),
+                 lambda: bt.multi_scale_deformable_attn_sca_shared(torch.zeros(1, 4, 1, 32), torch.tensor([[2, 2]]),
+                                                                   torch.zeros(1, 3, 1, 2), torch.zeros(3, 1, 8),
+                                                                   torch.zeros(3, 1, 4), torch.zeros(1, 3))):  # fmt: skip
+        with pytest.raises(RuntimeError):
+            call()
