@@ -405,25 +405,27 @@ def run_multi(args, cfg, peak, peak_src):
     if args.graph:
         # the whole step (memset, kernels, wire conversion, all-reduce) as one CUDA graph; eager fallback if the capture
         # or its check fails on any rank (all ranks take the same branch: the flag is all-reduced)
+        # Every rank issues the same collectives in the same order whatever happens locally: capture (records, does not
+        # communicate) -> agree on success -> replay + compare -> agree again.
         want = sampler.step().clone()
         ok = torch.ones(1, device="cuda")
         try:
             sampler.capture()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] rank {rank}: CUDA-graph capture of the sharded step failed, running eager: {e}", file=sys.stderr)
+            ok.zero_()
+        graph, sampler._graph = sampler._graph, None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() > 0 and graph is not None:
+            sampler._graph = graph
             got = sampler.step()
             torch.cuda.synchronize()
             if not torch.allclose(got, want, atol=2e-3, rtol=1e-3):
                 ok.zero_()
-        except Exception as e:  # noqa: BLE001
-            print(f"[bench] rank {rank}: CUDA-graph capture of the sharded step failed, running eager: {e}", file=sys.stderr)
-            ok.zero_()
-        sampler_graph = sampler._graph
-        sampler._graph = None
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        graphed = bool(ok.item() > 0) and sampler_graph is not None
-        if graphed:
-            sampler._graph = sampler_graph
-            for _ in range(3):
-                sampler.step()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            graphed = bool(ok.item() > 0)
+            if not graphed:
+                sampler._graph = None
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
