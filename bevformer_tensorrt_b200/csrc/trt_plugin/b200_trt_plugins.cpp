@@ -5,7 +5,7 @@
 // Same plugin names / versions / input orders / attributes as the reference, so an ONNX graph exported by the
 // reference's symbolic() functions resolves to these plugins unchanged:
 //   MultiScaleDeformableAttnTRT, MultiScaleDeformableAttnTRT2   (multiScaleDeformableAttnPlugin.cpp:19-23, :345-346)
-//   GridSampler2DTRT, GridSampler2DTRT2                           (gridSamplerPlugin.cpp:20-26, :558-561)
+//   GridSampler2DTRT, GridSampler2DTRT2, GridSampler3DTRT, GridSampler3DTRT2   (gridSamplerPlugin.cpp:20-26, :558-561)
 //   ModulatedDeformableConv2dTRT, ModulatedDeformableConv2dTRT2   (modulatedDeformableConv2dPlugin.cpp:19-23, :515-516)
 //   RotateTRT, RotateTRT2                                         (rotatePlugin.cpp:19-21, :216-330)
 // enqueue() forwards to the C ABI (include/b200_bev_ops.h); nothing is computed here.
@@ -23,7 +23,7 @@ using namespace nvinfer1;
 
 static_assert(sizeof(b200_tensor_desc) == sizeof(PluginTensorDesc), "b200_tensor_desc must mirror PluginTensorDesc");
 
-enum class Op { kMSDA, kGridSampler2D, kDCN, kRotate };
+enum class Op { kMSDA, kGridSampler2D, kGridSampler3D, kDCN, kRotate };
 
 struct Attrs {  // serialised verbatim (the reference serialises the same fields: gridSamplerPlugin.cpp:157-166,
                 // modulatedDeformableConv2dPlugin.cpp:200-211; MSDA serialises nothing, …Plugin.cpp:142-146)
@@ -51,6 +51,9 @@ class Plugin final : public IPluginV2DynamicExt {
       o.d[0] = in[0].d[0], o.d[1] = in[3].d[1], o.d[2] = in[0].d[2], o.d[3] = in[0].d[3];
     } else if (op_ == Op::kGridSampler2D) {  // [in.d0, in.d1, grid.d2, grid.d3] (gridSamplerPlugin.cpp:85-96)
       o.d[0] = in[0].d[0], o.d[1] = in[0].d[1], o.d[2] = in[1].d[2], o.d[3] = in[1].d[3];
+    } else if (op_ == Op::kGridSampler3D) {  // [in.d0, in.d1, grid.d2, grid.d3, grid.d4]
+      o.nbDims = 5;
+      o.d[0] = in[0].d[0], o.d[1] = in[0].d[1], o.d[2] = in[1].d[2], o.d[3] = in[1].d[3], o.d[4] = in[1].d[4];
     } else {  // [in.d0, weight.d0, offset.d2, offset.d3] (…Conv2dPlugin.cpp:60-66)
       o.d[0] = in[0].d[0], o.d[1] = in[3].d[0], o.d[2] = in[1].d[2], o.d[3] = in[1].d[3];
     }
@@ -74,6 +77,10 @@ class Plugin final : public IPluginV2DynamicExt {
       return d.type == img.type;
     }
     const PluginTensorDesc &d = io[pos], &x = io[0];
+    if (op_ == Op::kGridSampler3D) {  // 5-D: fp32 / fp16 linear only (gridSamplerPlugin.cpp:187-189)
+      if (pos != 0) return d.type == x.type && d.format == x.format;
+      return (d.type == DataType::kFLOAT || d.type == DataType::kHALF) && d.format == TensorFormat::kLINEAR;
+    }
     if (op_ == Op::kGridSampler2D) {  // gridSamplerPlugin.cpp:168-194: …TRT2 negotiates kCHW2 for FP16; INT8 is kCHW4
       if (pos != 0) return d.type == x.type && d.format == x.format;
       if (d.type == DataType::kINT8) return d.format == TensorFormat::kCHW4;
@@ -128,6 +135,15 @@ class Plugin final : public IPluginV2DynamicExt {
                               in[0].scale, inputs[1], inputs[2], in[1].type == DataType::kHALF, dims, a_.interp, stream);
       return 1;
     }
+    if (op_ == Op::kGridSampler3D) {
+      int id[5], gd[5], od[5];
+      for (int i = 0; i < 5; ++i) id[i] = in[0].dims.d[i], gd[i] = in[1].dims.d[i], od[i] = out[0].dims.d[i];
+      if (in[0].type == DataType::kFLOAT)
+        return b200_grid_sample_f32(static_cast<float *>(outputs[0]), static_cast<const float *>(inputs[0]),
+                                    static_cast<const float *>(inputs[1]), od, id, gd, 5, a_.interp, a_.padding, a_.align,
+                                    stream);
+      return b200_grid_sample_f16(outputs[0], inputs[0], inputs[1], od, id, gd, 5, a_.interp, a_.padding, a_.align, stream);
+    }
     if (op_ == Op::kGridSampler2D) {
       int id[4], gd[4], od[4];
       for (int i = 0; i < 4; ++i) id[i] = in[0].dims.d[i], gd[i] = in[1].dims.d[i], od[i] = out[0].dims.d[i];
@@ -170,6 +186,7 @@ class Plugin final : public IPluginV2DynamicExt {
     switch (op_) {
       case Op::kMSDA: return v2_ ? "MultiScaleDeformableAttnTRT2" : "MultiScaleDeformableAttnTRT";
       case Op::kGridSampler2D: return v2_ ? "GridSampler2DTRT2" : "GridSampler2DTRT";
+      case Op::kGridSampler3D: return v2_ ? "GridSampler3DTRT2" : "GridSampler3DTRT";
       case Op::kRotate: return v2_ ? "RotateTRT2" : "RotateTRT";
       default: return v2_ ? "ModulatedDeformableConv2dTRT2" : "ModulatedDeformableConv2dTRT";
     }
@@ -200,7 +217,7 @@ class Plugin final : public IPluginV2DynamicExt {
 class Creator final : public IPluginCreator {
  public:
   Creator(Op op, bool v2) : op_(op), v2_(v2) {
-    if (op == Op::kGridSampler2D) {
+    if (op == Op::kGridSampler2D || op == Op::kGridSampler3D) {
       fields_ = {{"interpolation_mode", nullptr, PluginFieldType::kINT32, 1},
                  {"padding_mode", nullptr, PluginFieldType::kINT32, 1},
                  {"align_corners", nullptr, PluginFieldType::kINT32, 1}};
@@ -277,6 +294,8 @@ B200_REGISTER(MsdaCreator, Op::kMSDA, false);
 B200_REGISTER(MsdaCreator2, Op::kMSDA, true);
 B200_REGISTER(GridSampler2DCreator, Op::kGridSampler2D, false);
 B200_REGISTER(GridSampler2DCreator2, Op::kGridSampler2D, true);
+B200_REGISTER(GridSampler3DCreator, Op::kGridSampler3D, false);
+B200_REGISTER(GridSampler3DCreator2, Op::kGridSampler3D, true);
 B200_REGISTER(DcnCreator, Op::kDCN, false);
 B200_REGISTER(DcnCreator2, Op::kDCN, true);
 B200_REGISTER(RotateCreator, Op::kRotate, false);

@@ -173,7 +173,8 @@ def test_tensorrt_plugin_shell_compiles_against_the_mock_api():
     assert r.returncode == 0, r.stderr
     text = open(src).read()
     for name in ("MultiScaleDeformableAttnTRT", "MultiScaleDeformableAttnTRT2", "GridSampler2DTRT", "GridSampler2DTRT2",
-                 "ModulatedDeformableConv2dTRT", "ModulatedDeformableConv2dTRT2"):  # fmt: skip
+                 "GridSampler3DTRT", "GridSampler3DTRT2", "ModulatedDeformableConv2dTRT", "ModulatedDeformableConv2dTRT2",
+                 "RotateTRT", "RotateTRT2"):  # fmt: skip
         assert f'"{name}"' in text
 
 
@@ -229,3 +230,25 @@ def test_cpu_tensors_are_refused_by_the_new_ops():
                                                                    torch.zeros(3, 1, 4), torch.zeros(1, 3))):  # fmt: skip
         with pytest.raises(RuntimeError):
             call()
+
+
+def test_tensorrt_plugin_shell_behaviour_through_the_mock_api(tmp_path):
+    """Builds tests/mock_trt/shell_harness.cpp (the shells + the mock plugin API + libb200_bev_ops.so) and runs it: creator
+    names / fields, create -> serialise -> deserialise -> clone round trips, output dimensions, the format negotiation
+    tables of all five plugins, workspace sizes, and enqueue() forwarding (bad arguments -> status). No GPU needed."""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    cuda_lib = "/usr/local/cuda/lib64"
+    exe = str(tmp_path / "shell_harness")
+    cmd = ["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "tests", "mock_trt"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "mock_trt", "shell_harness.cpp"), "-L", lib_dir, "-lb200_bev_ops", "-L", cuda_lib,
+           f"-Wl,-rpath,{lib_dir}", f"-Wl,-rpath,{cuda_lib}", "-o", exe]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert r.stdout.startswith("OK ") and int(r.stdout.split()[1]) > 100
