@@ -252,3 +252,23 @@ def test_tensorrt_plugin_shell_behaviour_through_the_mock_api(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr + r.stdout
     assert r.stdout.startswith("OK ") and int(r.stdout.split()[1]) > 100
+
+
+def test_c_header_is_plain_c_and_the_example_host_runs(tmp_path):
+    """include/b200_bev_ops.h must be usable from C (the drop-in boundary is a C ABI): examples/minimal_host.c is
+    compiled as strict C99 and run; it exercises version, format negotiation and argument validation without a GPU."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "minimal_host")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "minimal_host.c"), "-L", lib_dir, "-lb200_bev_ops", "-L", "/usr/local/cuda/lib64",
+           f"-Wl,-rpath,{lib_dir}", "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "accepted for all six tensors" in r.stdout and "status 2" in r.stdout
