@@ -113,6 +113,14 @@ def test_onnx_symbolic_names_are_the_reference_plugin_names():
     n, a, k = gs._GridSampler2D.symbolic(G(), 1, 2, 0, 1, True)
     assert n == "GridSampler2DTRT" and k == {"interpolation_mode_i": 0, "padding_mode_i": 1, "align_corners_i": True}
     assert gs._GridSampler3D2.symbolic(G(), 1, 2, 0, 0, False)[0] == "GridSampler3DTRT2"
+    rot = importlib.import_module("bevformer_tensorrt_b200.functions.rotate")
+    n, a, k = rot._Rotate.symbolic(G(), 1, 2, 3, 1)  # rotate.py:9-10: g.op("RotateTRT", img, angle, center, interpolation_i=…)
+    assert n == "RotateTRT" and a == (1, 2, 3) and k == {"interpolation_i": 1}
+    assert rot._Rotate2.symbolic(G(), 1, 2, 3, 0)[0] == "RotateTRT2"
+    dcn = importlib.import_module("bevformer_tensorrt_b200.functions.modulated_deformable_conv2d")
+    names = {c.symbolic(G(), 1, 2, 3, 4, 5, 1, 1, 1, 1, 1)[0] for c in vars(dcn).values()
+             if isinstance(c, type) and hasattr(c, "symbolic") and c.__module__ == dcn.__name__}
+    assert names == {"ModulatedDeformableConv2dTRT", "ModulatedDeformableConv2dTRT2"}
 
 
 def test_workload_generators():
