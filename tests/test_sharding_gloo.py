@@ -87,7 +87,7 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])  # 4: cameras AND query tiles are split (two tiles per camera)
 def test_world_size_2_gloo_matches_single_process(world):
     sock = socket.socket()
     sock.bind(("127.0.0.1", 0))
@@ -106,7 +106,7 @@ def test_world_size_2_gloo_matches_single_process(world):
 
 def test_single_process_sampler_equals_masked_camera_sum():
     (value, shapes, ref, off, logits, mask), want = _full_reference()
-    for world in (1, 4):
+    for world in (1, 3, 4, 8):
         total = torch.zeros_like(want)
         for rank in range(world):
             s = ShardedSCASampler(plan_units(6, CFG.num_query, world)[rank], CFG.num_query, _oracle_op)
