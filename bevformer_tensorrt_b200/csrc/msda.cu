@@ -29,7 +29,9 @@ constexpr int kThreads = 256;
 #endif
 constexpr int kMinBlocks = B200_MSDA_MIN_BLOCKS;  // 3: registers capped at 85, 24 resident warps per SM
 
-static int g_f16_mode = 0;  // exact by default; 1 = mixed FHFMA (opt-in, see Io<__half, 1>)
+// exact by default; 1 = mixed FHFMA (opt-in, see Io<__half, 1>). Atomic: enqueue may be called from several host
+// threads (SURVEY §8(b) threading), the setter from another.
+static std::atomic<int> g_f16_mode{0};
 
 struct MsdaParams {
   const void *value;
@@ -47,6 +49,7 @@ struct MsdaParams {
   const float *mask;
   float *accum;
   float scale_value, scale_offset, scale_weight, scale_out;
+  int4 *trace;  // DBG instantiations: per (item, point) sampling-index record {in_range, h_low, w_low, tap_mask}
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -307,7 +310,7 @@ __device__ __forceinline__ void load_ref<float>(const float *p, int G, float (&p
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxChunks = 64;
 
-template <typename T, typename R, int C, int ROUNDS, int MODE, int EPI>
+template <typename T, typename R, int C, int ROUNDS, int MODE, int EPI, bool DBG = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const MsdaParams prm) {
   using IO = Io<T, MODE>;
   constexpr int VEC = IO::kVec;
@@ -481,6 +484,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
         const float e = EPI == 2 ? lg[r][k] * mk : lg[r][k];  // bev_mask folded into the tap weights
         IO::pack_w(tw[k], (ok && t && lf) ? hh * hw * e : 0.f, (ok && t && rt) ? hh * lw * e : 0.f,
                    (ok && bt && lf) ? lh * hw * e : 0.f, (ok && bt && rt) ? lh * lw * e : 0.f);
+        if (DBG && active && c < NCH) {
+          // the index record of THIS kernel's own arithmetic (parity tests compare it bit for bit with the oracle);
+          // points the early-outs above never reach are out of range = the all-zero record the host pre-fills
+          const int tm = ((t && lf) ? 1 : 0) | ((t && rt) ? 2 : 0) | ((bt && lf) ? 4 : 0) | ((bt && rt) ? 8 : 0);
+          prm.trace[it * NP + c * 4 + k] = ok ? make_int4(1, h_low, w_low, tm) : make_int4(0, 0, 0, 0);
+        }
       }
     }
     const unsigned vm = __ballot_sync(kFullMask, ((inr >> (r * 4)) & 0xfu) != 0u);
@@ -604,6 +613,8 @@ __global__ void __launch_bounds__(kThreads) msda_generic_kernel(const MsdaParams
         const float e = expf(load_as_float<T>(logits, it * NP + k, prm.scale_weight) - mx);
         sum += e;
         const PointRec pr = point_record(rx, ry, ox, oy, H, W);
+        if (prm.trace != nullptr && c == 0)
+          prm.trace[it * NP + k] = pr.in_range ? make_int4(1, pr.h_low, pr.w_low, tap_mask_of(pr, H, W)) : make_int4(0, 0, 0, 0);
         if (!pr.in_range) continue;
         const int tm = tap_mask_of(pr, H, W);
         const long long stp = static_cast<long long>(M) * C;
@@ -662,6 +673,12 @@ static int launch_gather(const MsdaParams &p, cudaStream_t s) {
   constexpr int IPB = (32 / LPI) * (kThreads / 32);
   const long long blocks = (p.items + IPB - 1) / IPB;
   if (blocks > 0x7fffffffll) return B200_ERR_BAD_PARAM;
+  if constexpr (EPI == 0 && MODE == 0) {
+    if (p.trace != nullptr) {
+      msda_gather_kernel<T, R, C, ROUNDS, MODE, 0, true><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(p);
+      return check_launch();
+    }
+  }
   msda_gather_kernel<T, R, C, ROUNDS, MODE, EPI><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(p);
   return check_launch();
 }
@@ -719,11 +736,7 @@ using namespace b200;
 
 extern "C" {
 
-int b200_msda_set_f16_mode(int mode) {
-  const int prev = g_f16_mode;
-  g_f16_mode = mode ? 1 : 0;
-  return prev;
-}
+int b200_msda_set_f16_mode(int mode) { return g_f16_mode.exchange(mode ? 1 : 0); }
 
 int b200_msda_f32(const float *value, const int32_t *spatial_shapes, const float *reference_points,
                   const float *sampling_offsets, const float *attn_weight, int batch, int spatial_size, int num_heads,
@@ -742,8 +755,8 @@ int b200_msda_f16(const void *value, const int32_t *spatial_shapes, const void *
   const MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
                                    spatial_size, num_heads, channels, num_levels, num_query, num_point,
                                    points_per_group, out);
-  return g_f16_mode ? dispatch<__half, __half, 1>(p, static_cast<cudaStream_t>(stream))
-                    : dispatch<__half, __half, 0>(p, static_cast<cudaStream_t>(stream));
+  return g_f16_mode.load(std::memory_order_relaxed) ? dispatch<__half, __half, 1>(p, static_cast<cudaStream_t>(stream))
+                                                   : dispatch<__half, __half, 0>(p, static_cast<cudaStream_t>(stream));
 }
 
 int b200_msda_f16_h2(const void *value, const int32_t *spatial_shapes, const void *reference_points,
@@ -814,6 +827,54 @@ int b200_msda_sca_shared_f16(const void *value, const int32_t *spatial_shapes, c
   p.mask = bev_mask, p.accum = slots;
   p.items = static_cast<long long>(num_query) * num_heads;
   return dispatch<__half, __half, 0, 2>(p, static_cast<cudaStream_t>(stream));
+}
+
+// The production kernels with the trace switch on: same template, same index arithmetic, plus one record per point.
+static int trace_prologue(int32_t *records, long long n, cudaStream_t s) {
+  if (!records || n <= 0) return B200_ERR_BAD_PARAM;
+  return cudaMemsetAsync(records, 0, static_cast<size_t>(n) * 16, s) == cudaSuccess ? B200_OK : B200_ERR_LAUNCH;
+}
+
+int b200_msda_f32_trace(const float *value, const int32_t *spatial_shapes, const float *reference_points,
+                        const float *sampling_offsets, const float *attn_weight, int batch, int spatial_size,
+                        int num_heads, int channels, int num_levels, int num_query, int num_point,
+                        int points_per_group, float *out, int32_t *records, void *stream) {
+  MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, points_per_group, out);
+  const int st = trace_prologue(records, p.items * num_levels * num_point, static_cast<cudaStream_t>(stream));
+  if (st != B200_OK) return st;
+  p.trace = reinterpret_cast<int4 *>(records);
+  return dispatch<float, float, 0>(p, static_cast<cudaStream_t>(stream));
+}
+
+int b200_msda_f16_trace(const void *value, const int32_t *spatial_shapes, const void *reference_points,
+                        const void *sampling_offsets, const void *attn_weight, int batch, int spatial_size,
+                        int num_heads, int channels, int num_levels, int num_query, int num_point,
+                        int points_per_group, void *out, int32_t *records, void *stream) {
+  MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, points_per_group, out);
+  const int st = trace_prologue(records, p.items * num_levels * num_point, static_cast<cudaStream_t>(stream));
+  if (st != B200_OK) return st;
+  p.trace = reinterpret_cast<int4 *>(records);
+  return dispatch<__half, __half, 0>(p, static_cast<cudaStream_t>(stream));
+}
+
+int b200_msda_i8_trace(const int8_t *value, float scale_value, const int32_t *spatial_shapes,
+                       const void *reference_points, int ref_is_half, const int8_t *sampling_offsets,
+                       float scale_offset, const int8_t *attn_weight, float scale_weight, int batch, int spatial_size,
+                       int num_heads, int channels, int num_levels, int num_query, int num_point, int points_per_group,
+                       int8_t *out, float scale_out, int32_t *records, void *stream) {
+  if (channels % 4 != 0 || num_point % 4 != 0) return B200_ERR_UNSUPPORTED;
+  if (!(scale_out > 0.f)) return B200_ERR_BAD_PARAM;
+  MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
+                             spatial_size, num_heads, channels, num_levels, num_query, num_point, points_per_group, out);
+  p.scale_value = scale_value, p.scale_offset = scale_offset, p.scale_weight = scale_weight, p.scale_out = scale_out;
+  p.ref_is_half = ref_is_half;
+  const int st = trace_prologue(records, p.items * num_levels * num_point, static_cast<cudaStream_t>(stream));
+  if (st != B200_OK) return st;
+  p.trace = reinterpret_cast<int4 *>(records);
+  return ref_is_half ? dispatch<int8_t, __half, 0>(p, static_cast<cudaStream_t>(stream))
+                     : dispatch<int8_t, float, 0>(p, static_cast<cudaStream_t>(stream));
 }
 
 int b200_msda_debug_indices(int dtype, const int32_t *spatial_shapes, const void *reference_points,

@@ -6,6 +6,8 @@ weight, bias=None, stride=1, padding=0, dilation=1, groups=1, deform_groups=1)``
 
 The reference's forward calls mmcv's ``modulated_deform_conv_forward`` (:84-104); here it calls the sm_100a path behind
 the C ABI. Inference only."""
+import weakref
+
 import torch
 from torch.autograd import Function
 from torch.nn.modules.utils import _pair
@@ -52,23 +54,35 @@ def _forward(input, offset, mask, weight, bias, stride, padding, dilation, group
     return out
 
 
-_PACKED = {}  # (weight storage ptr, version, shape) -> weights permuted for the fused kernel (constant at inference)
+_PACKED = {}  # id(weight) -> (weakref to the weight, its _version, packed copy); entries die with their weight
+
+
+def _pack(lib, weight):
+    co, c, kh, kw = weight.shape
+    packed = torch.empty_like(weight, memory_format=torch.contiguous_format)
+    with torch.cuda.device(weight.device):
+        _lib.check("b200_dcn_pack_weights_f16",
+                   lib.b200_dcn_pack_weights_f16(weight.data_ptr(), packed.data_ptr(), co, c, kh, kw,
+                                                 _lib.current_stream_ptr()))  # fmt: skip
+    return packed
 
 
 def _packed_weight(lib, weight):
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
+    """Weights permuted for the fused kernel. The permutation is constant at inference, so it is cached — but only for
+    long-lived tensors the caller owns (``nn.Parameter`` / registered buffers, i.e. tensors that are not the result of
+    a cast or ``.contiguous()`` made for this call), and the entry is tied to that tensor OBJECT by a weak reference:
+    a freed weight takes its entry with it, so a new tensor that lands on the same address can never see stale packed
+    weights. In-place updates are caught by ``_version``. Temporaries are packed on every call (a 1.2 MB kernel)."""
+    cacheable = isinstance(weight, torch.nn.Parameter) or getattr(weight, "_b200_cache_packed", False)
+    if not cacheable or not weight.is_contiguous() or weight.dtype != torch.float16:
+        return _pack(lib, weight.to(torch.float16).contiguous())
+    key = id(weight)
     hit = _PACKED.get(key)
-    if hit is None:
-        if len(_PACKED) > 256:
-            _PACKED.clear()
-        co, c, kh, kw = weight.shape
-        hit = torch.empty_like(weight, memory_format=torch.contiguous_format)
-        with torch.cuda.device(weight.device):
-            _lib.check("b200_dcn_pack_weights_f16",
-                       lib.b200_dcn_pack_weights_f16(weight.data_ptr(), hit.data_ptr(), co, c, kh, kw,
-                                                     _lib.current_stream_ptr()))  # fmt: skip
-        _PACKED[key] = hit
-    return hit
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
+        return hit[2]
+    packed = _pack(lib, weight)
+    _PACKED[key] = (weakref.ref(weight, lambda _r, k=key: _PACKED.pop(k, None)), weight._version, packed)
+    return packed
 
 
 def _forward_fused_f16(lib, input, offset, mask, weight, bias, stride, padding, dilation, out_hw):
@@ -83,7 +97,7 @@ def _forward_fused_f16(lib, input, offset, mask, weight, bias, stride, padding, 
         x = input
     else:
         x = input.contiguous()
-    wp = _packed_weight(lib, weight.contiguous())
+    wp = _packed_weight(lib, weight)
     offset, mask = offset.to(dt).contiguous(), mask.to(dt).contiguous()
     bias_t = bias.to(dt).contiguous() if bias is not None else None
     ws_bytes = lib.b200_dcn_workspace_size(1, n, c, h, w, kw, kh, stride[1], stride[0], padding[1], padding[0],

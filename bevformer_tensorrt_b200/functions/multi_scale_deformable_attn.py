@@ -249,3 +249,37 @@ def msda_sampling_indices(value_spatial_shapes, reference_points, sampling_offse
                                                  _lib.current_stream_ptr())  # fmt: skip
     _lib.check("b200_msda_debug_indices", st)
     return rec
+
+
+def msda_trace(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, scales=None):
+    """The production MSDA kernel with its trace switch on. Returns ``(out, records)``: ``out`` as the plugin op computes
+    it and int32 records [bs, nq, heads, L*P, 4] = {in_range, h_low, w_low, tap_mask} written by the gather kernel itself
+    while it samples (C entries b200_msda_{f32,f16,i8}_trace). ``scales`` = (scale_value, scale_offset, scale_weight,
+    scale_out) selects the INT8 kernel (int8 value / offsets / logits, float or half reference points)."""
+    assert value.is_cuda
+    dims = _check_inputs(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights)
+    bs, _, num_heads, channels, num_levels, num_query, num_point, _ = dims
+    lib = _lib.load()
+    dt = value.dtype
+    value = value.contiguous()
+    shapes = _shapes_i32(value_spatial_shapes, value.device)
+    out = torch.empty(bs, num_query, num_heads, channels, dtype=dt, device=value.device)
+    rec = torch.empty(bs, num_query, num_heads, num_levels * num_point, 4, dtype=torch.int32, device=value.device)
+    with torch.cuda.device(value.device):
+        if dt == torch.int8:
+            sv, so, sw, sout = (float(x) for x in scales)
+            ref = reference_points.contiguous()
+            off, w = sampling_offsets.contiguous(), attention_weights.contiguous()
+            name = "b200_msda_i8_trace"
+            st = lib.b200_msda_i8_trace(value.data_ptr(), sv, shapes.data_ptr(), ref.data_ptr(),
+                                        int(ref.dtype == torch.float16), off.data_ptr(), so, w.data_ptr(), sw, *dims,
+                                        out.data_ptr(), sout, rec.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
+        elif dt in (torch.float32, torch.float16):
+            ref, off, w = (t.to(dt).contiguous() for t in (reference_points, sampling_offsets, attention_weights))
+            name = "b200_msda_f32_trace" if dt == torch.float32 else "b200_msda_f16_trace"
+            st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
+                                    *dims, out.data_ptr(), rec.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
+        else:
+            raise _lib.B200OpsError("msda_trace", 1)
+    _lib.check(name, st)
+    return out, rec

@@ -19,14 +19,14 @@ import torch
 from .functions.multi_scale_deformable_attn import multi_scale_deformable_attn_out
 
 _cudart = None
-_live = {}  # data_ptr -> keeps the host allocations of empty_pinned alive until the process exits
 
 
 def empty_pinned(shape, dtype=torch.float16):
     """Page-locked host tensor straight from ``cudaHostAlloc``. Measured on the B200 box (scripts/micro/numa_pin.py):
     55 GB/s host-to-device from such a buffer wherever the calling thread runs, against 40-49 GB/s from
     ``tensor.pin_memory()``, whose staging copy lets the first-touch NUMA node of the pages vary. Use it for the
-    staging buffers handed to ``HostMSDA`` (the memory lives until the process exits)."""
+    staging buffers handed to ``HostMSDA``. The allocation is owned by the returned tensor's storage: ``cudaFreeHost``
+    runs when the last tensor / view over it is garbage-collected."""
     global _cudart
     if _cudart is None:
         for name in ("libcudart.so.12", "libcudart.so"):
@@ -43,10 +43,13 @@ def empty_pinned(shape, dtype=torch.float16):
     err = _cudart.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(nbytes), ctypes.c_uint(0))
     if err != 0 or not ptr.value:
         raise MemoryError(f"cudaHostAlloc({nbytes}) failed with error {err}")
-    buf = (ctypes.c_char * nbytes).from_address(ptr.value)
-    t = torch.frombuffer(buf, dtype=dtype, count=math.prod(shape)).view(shape)
-    _live[ptr.value] = buf
-    return t
+    address, cudart = ptr.value, _cudart
+
+    class _PinnedBytes(ctypes.c_char * nbytes):  # torch.frombuffer holds the exporting object; its death frees the pages
+        def __del__(self):
+            cudart.cudaFreeHost(ctypes.c_void_p(address))
+
+    return torch.frombuffer(_PinnedBytes.from_address(address), dtype=dtype, count=math.prod(shape)).view(shape)
 
 
 class HostMSDA:

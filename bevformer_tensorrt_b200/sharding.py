@@ -8,6 +8,7 @@ and ONE collective (all-reduce, NCCL over NVLink on GPUs / gloo in the CPU tests
 6 cameras do not divide 4 or 8 ranks, hence query tiles: the unit count is lcm-friendly (12 units for 4 ranks,
 24 for 8) so every rank gets the same amount of work.
 """
+import ctypes
 import math
 from dataclasses import dataclass
 from typing import Callable, List, Sequence
@@ -194,3 +195,178 @@ class ShardedSCASampler:
         if do_reduce and self._wire is not None:
             self.accum.copy_(self._wire)
         return self.accum
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Round 2: camera-group x query-tile grid with an owner-sliced reduce-scatter (the step's only inter-GPU traffic)
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class GridShard:
+    """One rank's place in the (camera group, query tile) grid.
+
+    ``world = A * T``: the cameras are split into ``A`` groups (A divides the camera count), the queries into ``T``
+    tiles; rank ``r`` = (group ``r // T``, tile ``r % T``) samples cameras ``[cam0, cam1)`` for queries ``[q0, q1)``
+    into a partial accumulator ``[q1 - q0, heads*ch]``. The ``A`` ranks that share a tile (``peers``, ordered by camera
+    group) reduce-scatter their partials: this rank ends up owning the final sum of rows ``[own0, own1)`` (a slice of its
+    tile). Every BEV query is owned by exactly one rank; the consumer (``output_proj``, spatial_cross_attention.py:273) is
+    query-parallel, so no all-gather follows."""
+
+    rank: int
+    world: int
+    groups: int  # A
+    tiles: int  # T
+    cam0: int
+    cam1: int
+    q0: int
+    q1: int
+    peers: tuple  # global ranks sharing this tile, index = camera group
+    own0: int
+    own1: int
+
+    @property
+    def my_index(self):
+        return self.peers.index(self.rank)
+
+
+def _edges(n: int, parts: int, align: int, lo: int = 0):
+    return [lo + min(n, ((n * t // parts + align - 1) // align) * align) for t in range(parts)] + [lo + n]
+
+
+def choose_camera_groups(num_cams: int, world: int) -> int:
+    """Smallest A > 1 dividing both the camera count and the world size (least inter-GPU traffic: a rank sends
+    (A-1)/A of its tile), A = 1 (pure query split, no exchange at all) when world == 1 or nothing divides."""
+    for a in range(2, num_cams + 1):
+        if num_cams % a == 0 and world % a == 0:
+            return a
+    return 1
+
+
+def plan_grid(num_cams: int, num_query: int, world: int, align: int = 8, groups: int = None) -> List[GridShard]:
+    if world < 1 or num_cams < 1 or num_query < 1:
+        raise ValueError("world_size, num_cams and num_query must be positive")
+    A = choose_camera_groups(num_cams, world) if groups is None else groups
+    if num_cams % A or world % A:
+        raise ValueError(f"{A} camera groups do not divide {num_cams} cameras / {world} ranks")
+    T = world // A
+    qe = _edges(num_query, T, align)
+    per = num_cams // A
+    shards = []
+    for r in range(world):
+        g, t = divmod(r, T)
+        q0, q1 = qe[t], qe[t + 1]
+        oe = _edges(q1 - q0, A, align if align % 4 == 0 else 4, q0)
+        shards.append(GridShard(r, world, A, T, g * per, (g + 1) * per, q0, q1, tuple(gg * T + t for gg in range(A)),
+                                oe[g], oe[g + 1]))
+    return shards
+
+
+class GroupedSCASampler:
+    """One rank of the camera-group x query-tile grid: local fused sampling into a partial accumulator, then the
+    reduce-scatter inside the camera group. ``step()`` returns this rank's OWNED rows ``[own1 - own0, heads*ch]``.
+
+    exchange = "peer"  : ``b200_sca_peer_reduce`` — our kernel pulls the peers' partials over NVLink peer memory (torch
+                         symmetric memory supplies the mapped pointers); no NCCL call in the step.
+             = "nccl"  : ``reduce_scatter_tensor`` on the camera group's communicator (all-reduce + slice on gloo, which
+                         has no reduce-scatter) — the library baseline and the CPU-test path.
+    ``fused_sca(value, shapes, ref, off, logits, mask, accum)`` is the product kernel; the CPU tests inject a checker."""
+
+    def __init__(self, shard: GridShard, width: int, fused_sca: Callable, exchange: str = "nccl", out_dtype=torch.float32):
+        self.shard, self.width, self.fused_sca, self.exchange = shard, width, fused_sca, exchange
+        self.out_dtype = out_dtype
+        self.rows = shard.q1 - shard.q0
+        self.local = None
+        self.partial = None  # [2][rows_max, width] fp32 (peer) or [rows, width] (nccl)
+        self.out = None
+        self.group = None
+        self.epoch = 0
+        self._peer = None
+
+    # -- setup ---------------------------------------------------------------------------------------------------
+    def load(self, value, shapes, ref, off, logits, bev_mask, device):
+        s = self.shard
+        sl, cs = slice(s.q0, s.q1), slice(s.cam0, s.cam1)
+        self.shapes = shapes.to(device)
+        self.local = tuple(t.to(device).contiguous() for t in (value[cs], ref[cs, sl], off[cs, sl], logits[cs, sl],
+                                                               bev_mask[cs, sl]))  # fmt: skip
+        self.out = torch.empty(s.own1 - s.own0, self.width, dtype=self.out_dtype, device=device)
+        return self
+
+    def connect(self, all_shards: Sequence[GridShard], device):
+        """Collective: every rank calls it with the full plan. Builds the camera-group communicators ("nccl") or the
+        symmetric-memory window ("peer")."""
+        import torch.distributed as dist
+
+        s = self.shard
+        if s.groups == 1 or not (dist.is_available() and dist.is_initialized()):
+            self.exchange = "none"
+            self.partial = torch.zeros(self.rows, self.width, dtype=torch.float32, device=device)
+            return self
+        if self.exchange == "peer":
+            import torch.distributed._symmetric_memory as symm_mem
+
+            rows_max = max(x.q1 - x.q0 for x in all_shards)
+            n = 2 * rows_max * self.width + 64  # two partial buffers + the flag row (uint32 viewed as float bits)
+            buf = symm_mem.empty(n, dtype=torch.float32, device=device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            torch.cuda.synchronize(device)
+            dist.barrier()
+            stride = rows_max * self.width * 4
+            base = [int(hdl.buffer_ptrs[r]) for r in s.peers]
+            self._peer = {"buf": buf, "hdl": hdl, "rows_max": rows_max,
+                          "part": [[b + k * stride for b in base] for k in (0, 1)],
+                          "flags": [b + 2 * stride for b in base]}
+            self.partial = [buf[k * rows_max * self.width:(k + 1) * rows_max * self.width][: self.rows * self.width]
+                            .view(self.rows, self.width) for k in (0, 1)]  # fmt: skip
+        else:
+            tiles = sorted({x.peers for x in all_shards})
+            for peers in tiles:  # every rank creates every group, in the same order
+                g = dist.new_group(list(peers))
+                if peers == s.peers:
+                    self.group = g
+            self.partial = torch.zeros(self.rows, self.width, dtype=torch.float32, device=device)
+        return self
+
+    # -- one step ------------------------------------------------------------------------------------------------
+    def compute(self, accum):
+        v, r, o, w, m = self.local
+        self.fused_sca(v, self.shapes, r, o, w, m, accum)
+
+    def step(self):
+        s = self.shard
+        if self.exchange == "peer":
+            return self._step_peer()
+        self.partial.zero_()
+        self.compute(self.partial)
+        lo, hi = s.own0 - s.q0, s.own1 - s.q0
+        if self.exchange == "none":
+            self.out.copy_(self.partial[lo:hi])
+            return self.out
+        import torch.distributed as dist
+
+        equal = (s.own1 - s.own0) * s.groups == self.rows  # reduce_scatter_tensor needs equal slices
+        if dist.get_backend(self.group) == "nccl" and equal and self.out_dtype == torch.float32:
+            dist.reduce_scatter_tensor(self.out, self.partial, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(self.partial, op=dist.ReduceOp.SUM, group=self.group)
+            self.out.copy_(self.partial[lo:hi])
+        return self.out
+
+    def _step_peer(self):
+        from . import _lib
+
+        s, p = self.shard, self._peer
+        k = self.epoch & 1
+        self.epoch += 1
+        self.compute(self.partial[k])
+        n = len(s.peers)
+        parts = (ctypes.c_void_p * n)(*p["part"][k])
+        flags = (ctypes.c_void_p * n)(*p["flags"])
+        nxt = self.partial[1 - k]
+        with torch.cuda.device(self.out.device):
+            st = _lib.load().b200_sca_peer_reduce(parts, flags, n, s.my_index, self.epoch,
+                                                  (s.own0 - s.q0) * self.width, (s.own1 - s.own0) * self.width,
+                                                  self.out.data_ptr(), int(self.out_dtype == torch.float16),
+                                                  nxt.data_ptr(), nxt.numel(), _lib.current_stream_ptr())  # fmt: skip
+        _lib.check("b200_sca_peer_reduce", st)
+        return self.out

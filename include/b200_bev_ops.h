@@ -117,9 +117,43 @@ int b200_msda_sca_shared_f16(const void *value, const int32_t *spatial_shapes, c
                              int spatial_size, int num_heads, int channels, int num_levels, int num_query,
                              int num_point, int points_per_group, float *slots, void *stream);
 
-/* Test/diagnostic entry: writes, for every (batch, query, head, level*point), the sampling-index record
- * {in_range, h_low, w_low, tap_mask} (4 x int32) computed by the same device code as the kernels above.
- * dtype: 0 = float inputs, 1 = __half inputs. Used by the bit-exact index parity tests. */
+/* Multi-GPU SCA (not in the reference, which runs spatial_cross_attention.py:270's camera sum on one
+ * GPU): reduce-scatter of the fp32 BEV accumulator inside a camera group, over NVLink PEER MEMORY — no NCCL call.
+ * The `group_size` ranks of a camera group hold partial sums partials[r][rows*width] (their own cameras only, written
+ * by b200_msda_sca_*) for the same query tile; this rank owns floats [first_elem, first_elem + num_elems) of the tile.
+ * The kernel (1) publishes step `epoch` into every peer's flag row flags[r][my_index] (release, system scope) and waits
+ * until flags[my_index][r] >= epoch for all peers (acquire) — stream order guarantees the local partial is final when
+ * the kernel starts; (2) out[i] = sum_r partials[r][first_elem + i], peers read directly over NVLink; (3) zero-fills
+ * `zero_next` (the local partial buffer of the NEXT step; partials are double-buffered by step parity).
+ *   partials / flags: HOST arrays of `group_size` DEVICE pointers (peer-mapped: torch symmetric memory / cudaIpc);
+ *   flags[r] is uint32[8], zero-initialised; epoch starts at 1 and increases by 1 per step on every rank;
+ *   out: float (out_is_half == 0) or __half [num_elems]; element counts are multiples of 4. */
+int b200_sca_peer_reduce(const void *const *partials, void *const *flags, int group_size, int my_index,
+                         unsigned int epoch, long long first_elem, long long num_elems, void *out, int out_is_half,
+                         float *zero_next, long long zero_elems, void *stream);
+
+/* Trace entries: b200_msda_f32 / _f16 / _i8 with the production kernel's trace switch on (the same kernel template,
+ * compiled with one extra store): besides `out` they write, for every (batch, query, head, level*point), the
+ * sampling-index record {in_range, h_low, w_low, tap_mask} (4 x int32; all-zero when the point is out of range) that
+ * THE GATHER KERNEL ITSELF computed on its way to the taps. `records` must hold batch*num_query*num_heads*num_levels*
+ * num_point*4 int32; it is zero-filled on `stream` first. These are what the bit-exact index parity tests compare with
+ * the oracle (reference arithmetic: …Kernel.cu:657-674, :138-172). */
+int b200_msda_f32_trace(const float *value, const int32_t *spatial_shapes, const float *reference_points,
+                        const float *sampling_offsets, const float *attn_weight, int batch, int spatial_size,
+                        int num_heads, int channels, int num_levels, int num_query, int num_point,
+                        int points_per_group, float *out, int32_t *records, void *stream);
+int b200_msda_f16_trace(const void *value, const int32_t *spatial_shapes, const void *reference_points,
+                        const void *sampling_offsets, const void *attn_weight, int batch, int spatial_size,
+                        int num_heads, int channels, int num_levels, int num_query, int num_point,
+                        int points_per_group, void *out, int32_t *records, void *stream);
+int b200_msda_i8_trace(const int8_t *value, float scale_value, const int32_t *spatial_shapes,
+                       const void *reference_points, int ref_is_half, const int8_t *sampling_offsets,
+                       float scale_offset, const int8_t *attn_weight, float scale_weight, int batch, int spatial_size,
+                       int num_heads, int channels, int num_levels, int num_query, int num_point, int points_per_group,
+                       int8_t *out, float scale_out, int32_t *records, void *stream);
+
+/* Stand-alone diagnostic: the same records from a small index-only kernel (no value / logits needed; shares the
+ * point_record() device function with the generic fallback kernel). dtype: 0 = float inputs, 1 = __half inputs. */
 int b200_msda_debug_indices(int dtype, const int32_t *spatial_shapes, const void *reference_points,
                             const void *sampling_offsets, int batch, int num_heads, int num_levels, int num_query,
                             int num_point, int points_per_group, int32_t *records, void *stream);

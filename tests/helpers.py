@@ -56,6 +56,22 @@ def make_grid_sampler_inputs(N, C, Hi, Wi, Ho, Wo, seed=0, depth=None, span=15.0
     return inp, grid.contiguous()
 
 
+def make_rotation_grid(H, W, angle_deg, shift=(0.0, 0.0)):
+    """The prev-BEV warp grid of BASELINE configs[3]: output pixel centres rotated by ``angle_deg`` about the image
+    centre (plus a translation in pixels), normalised to [-1, 1] and scaled x10 — the plugin's [-10, 10] convention
+    (onnx_ops.py:226-232 builds the same grid x10). Returns float32 [1, 2, H, W] (x plane, y)."""
+    import math
+
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
+    c, s_ = math.cos(math.radians(angle_deg)), math.sin(math.radians(angle_deg))
+    sx = c * (xs - cx) - s_ * (ys - cy) + cx + shift[0]
+    sy = s_ * (xs - cx) + c * (ys - cy) + cy + shift[1]
+    gx = ((sx + 0.5) / W * 2 - 1) * 10
+    gy = ((sy + 0.5) / H * 2 - 1) * 10
+    return torch.stack([gx, gy], 0)[None].contiguous()
+
+
 ROTATE_CASES = {
     # name: (C, H, W, angle_deg, (center_x, center_y))
     "bev_small": (8, 50, 50, 1.7, (25.0, 25.0)),        # prev_bev alignment: a few degrees about the BEV centre

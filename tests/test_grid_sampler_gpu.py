@@ -14,7 +14,7 @@ from bevformer_tensorrt_b200.functions.grid_sampler import pack_chw, unpack_chw
 from bevformer_tensorrt_b200.workloads import quantize_per_tensor
 from oracle import REF_LIB
 from oracle import grid_sampler as ogs
-from tests.helpers import GOLDEN, make_grid_sampler_inputs
+from tests.helpers import GOLDEN, make_grid_sampler_inputs, make_rotation_grid
 
 pytestmark = pytest.mark.gpu
 
@@ -144,6 +144,75 @@ def test_fp32_matches_reference_kernel(interp, pad, align):
     torch.cuda.synchronize()
     got = bt.grid_sampler(inp, grid, interp, pad, align)
     assert (got - out).abs().max().item() < 1e-5, (interp, pad, align)
+
+
+def _ref_call(name, *args):
+    import ctypes
+
+    lib = ctypes.CDLL(REF_LIB)
+    getattr(lib, name)(*args, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+
+
+def test_base_shape_fp16_config4_vs_oracle_and_reference_kernel():
+    """BASELINE configs[3], FP16 leg: prev-BEV warp [1,256,200,200] through a rotation grid, bilinear / zeros /
+    align_corners=False, every output element vs the CPU oracle (reference FP32 formulas, gridSamplerKernel.cu:666-795,
+    on the fp16-rounded tensors); kLINEAR and kCHW2 entries; the reference's own __half / __half2 kernels
+    (:797-1080, coordinates in half precision) are run beside it on the same tensors and reported."""
+    import ctypes
+
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 256, 200, 200, generator=g).half()
+    grid = make_rotation_grid(200, 200, 3.7, (2.25, -1.5)).half()
+    want = ogs.grid_sample_2d(x.float().numpy(), grid.float().numpy(), 0, 0, False)
+    tol = 1e-3 + np.abs(want).max() * 2.0**-11
+    xd, gd = x.cuda(), grid.cuda()
+    got = bt.grid_sampler(xd, gd, "bilinear", "zeros", False)
+    e = np.abs(got.float().cpu().numpy() - want).max()
+    assert e < tol, e
+    g2 = grid.permute(0, 2, 3, 1).unsqueeze(1).contiguous().cuda()
+    out2 = bt.grid_sampler_chw2(pack_chw(x, 2).cuda(), g2, 256, "bilinear", "zeros", False)
+    assert torch.equal(unpack_chw(out2.cpu(), 256), got.cpu())
+    if os.path.exists(REF_LIB):
+        theirs = torch.empty_like(got)
+        dims = lambda t: (ctypes.c_int * 4)(*t.shape)  # noqa: E731
+        _ref_call("ref_grid_sample", 1, ctypes.c_void_p(theirs.data_ptr()), ctypes.c_void_p(xd.data_ptr()),
+                  ctypes.c_void_p(gd.data_ptr()), dims(theirs), dims(xd), dims(gd), 4, 0, 0, 0)
+        e_ref = np.abs(theirs.float().cpu().numpy() - want).max()
+        print(f"\n[grid sampler base fp16] ours {e:.3e}  reference __half kernel {e_ref:.3e} (vs fp32 formulas)")
+        assert e <= e_ref + 1e-6
+
+
+def test_base_shape_int8_config4_vs_dequant_oracle_and_reference_kernel():
+    """BASELINE configs[3], INT8 leg: kCHW4 int8 input [1,256,200,200] and grid with per-tensor scales; ours vs the
+    fp32 formulas on the dequantised tensors (at most half an output step: one requantisation), next to the reference's
+    grid_sample_int8 (gridSamplerKernel.cu:2010-2043, :1082-1268: weights quantised to int8 at 1/127, dp4a)."""
+    import ctypes
+
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(1, 256, 200, 200, generator=g)
+    grid = make_rotation_grid(200, 200, -2.9, (-1.75, 3.0))
+    iq, si = quantize_per_tensor(x)
+    gq, sg = quantize_per_tensor(grid)
+    real = ogs.grid_sample_2d(iq.float().numpy() * si, gq.float().numpy() * sg, 0, 0, False)
+    so = float(np.abs(real).max()) / 127.0
+    g4 = torch.zeros(1, 1, 200, 200, 4, dtype=torch.int8)
+    g4[:, 0, :, :, 0], g4[:, 0, :, :, 1] = gq[:, 0], gq[:, 1]
+    x4, g4d = pack_chw(iq, 4).cuda(), g4.cuda()
+    out4 = bt.grid_sampler_int8(x4, si, g4d, sg, so, 256, "bilinear", "zeros", False)
+    got = unpack_chw(out4.cpu(), 256).float().numpy() * so
+    e = np.abs(got - real).max()
+    assert e <= 0.5 * so + 1e-6, (e, so)
+    if os.path.exists(REF_LIB):
+        theirs4 = torch.empty_like(out4)
+        d4 = lambda *s: (ctypes.c_int * 4)(*s)  # noqa: E731
+        _ref_call("ref_grid_sample_int8", ctypes.c_void_p(theirs4.data_ptr()), ctypes.c_float(so),
+                  ctypes.c_void_p(x4.data_ptr()), ctypes.c_float(si), ctypes.c_void_p(g4d.data_ptr()),
+                  ctypes.c_float(sg), d4(1, 256, 200, 200), d4(1, 256, 200, 200), d4(1, 2, 200, 200), 4, 0, 0, 0)
+        e_ref = np.abs(unpack_chw(theirs4.cpu(), 256).float().numpy() * so - real).max()
+        print(f"\n[grid sampler base int8] ours {e / so:.3f} LSB  reference grid_sample_int8 {e_ref / so:.3f} LSB")
+        assert e <= e_ref + 1e-6
+        assert e_ref < 4 * so  # sanity: the reference kernel ran on the same tensors and landed in the neighbourhood
 
 
 def test_error_behaviour():

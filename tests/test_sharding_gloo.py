@@ -10,8 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from bevformer_tensorrt_b200.sharding import (ShardedSCASampler, group_cameras, plan_chunk_bounds, plan_chunked,
-                                              plan_units)
+from bevformer_tensorrt_b200.sharding import (GroupedSCASampler, ShardedSCASampler, choose_camera_groups, group_cameras,
+                                              plan_chunk_bounds, plan_chunked, plan_grid, plan_units)
 from bevformer_tensorrt_b200.workloads import MSDAConfig, bev_reference_points_cam, camera_ring_lidar2img, make_msda_inputs
 
 CFG = MSDAConfig("shard_case", 6, 20 * 20, 8, 32, ((12, 20), (6, 10)), 8, 4, (20, 20))
@@ -112,3 +112,83 @@ def test_single_process_sampler_equals_masked_camera_sum():
             s = ShardedSCASampler(plan_units(6, CFG.num_query, world)[rank], CFG.num_query, _oracle_op)
             total += s.load(value, shapes, ref, off, logits, mask, "cpu").step(reduce=False)
         assert (total - want).abs().max() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: camera-group x query-tile grid, owner-sliced reduce-scatter
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 6, 8, 12])
+def test_grid_plan_covers_and_owns_every_query_once(world):
+    plan = plan_grid(6, 40000, world)
+    A = choose_camera_groups(6, world)
+    assert len(plan) == world and all(s.groups == A and s.groups * s.tiles == world for s in plan)
+    cover = np.zeros((6, 40000), np.int32)
+    owned = np.zeros(40000, np.int32)
+    for s in plan:
+        cover[s.cam0 : s.cam1, s.q0 : s.q1] += 1
+        owned[s.own0 : s.own1] += 1
+        assert s.q0 <= s.own0 <= s.own1 <= s.q1 and s.rank in s.peers and len(s.peers) == A
+        assert (s.own0 - s.q0) % 4 == 0  # float4 granularity of the exchange kernel at width 256
+        for r in s.peers:  # the ranks of a camera group share the query tile
+            assert (plan[r].q0, plan[r].q1) == (s.q0, s.q1)
+    assert (cover == 1).all() and (owned == 1).all()
+    loads = [(s.cam1 - s.cam0) * (s.q1 - s.q0) for s in plan]
+    assert max(loads) - min(loads) <= 8 * 6
+
+
+def test_grid_plan_traffic_is_minimal_for_even_worlds():
+    for world in (2, 4, 8):
+        assert choose_camera_groups(6, world) == 2  # pairs: a rank sends half of its tile, 1/world of the accumulator
+    assert choose_camera_groups(6, 3) == 3 and choose_camera_groups(6, 5) == 1 and choose_camera_groups(6, 1) == 1
+    with pytest.raises(ValueError):
+        plan_grid(6, 40000, 8, groups=3)
+
+
+def _oracle_fused(value, shapes, ref, off, logits, mask, accum):
+    out = _oracle_op(value, shapes, ref, off, logits)
+    accum += (out.reshape(value.shape[0], accum.shape[0], -1) * mask).sum(0)
+    return accum
+
+
+def _grid_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    (value, shapes, ref, off, logits, mask), want = _full_reference()
+    plan = plan_grid(6, CFG.num_query, world)
+    s = plan[rank]
+    smp = GroupedSCASampler(s, want.shape[1], _oracle_fused).load(value, shapes, ref, off, logits, mask, "cpu")
+    smp.connect(plan, "cpu")
+    errs = []
+    for _ in range(3):  # repeated steps: the partial is re-zeroed, the result does not drift
+        got = smp.step()
+        errs.append(float((got - want[s.own0 : s.own1]).abs().max()))
+    q.put((rank, max(errs), float(want[s.own0 : s.own1].abs().max()), got.shape[0]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_grid_sampler_gloo_matches_single_process(world):
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grid_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert sum(r[3] for r in res) == CFG.num_query  # the owned slices tile the BEV
+    for rank, err, mag, _ in res:
+        assert err < 1e-5, (rank, err, mag)
+    assert max(r[2] for r in res) > 0.01
+
+
+def test_grid_sampler_single_rank_is_the_fused_op():
+    (value, shapes, ref, off, logits, mask), want = _full_reference()
+    plan = plan_grid(6, CFG.num_query, 1)
+    smp = GroupedSCASampler(plan[0], want.shape[1], _oracle_fused).load(value, shapes, ref, off, logits, mask, "cpu")
+    smp.connect(plan, "cpu")
+    assert (smp.step() - want).abs().max() < 1e-5
