@@ -40,6 +40,7 @@ from .functions import (  # noqa: E402
     rotate_chw2,
     rotate_hwc,
     rotate_int8,
+    set_msda_v2,
 )
 
 from .host_pipeline import HostMSDA, empty_pinned  # noqa: E402
@@ -68,5 +69,6 @@ __all__ = [
     "rotate_chw2",
     "rotate_hwc",
     "rotate_int8",
+    "set_msda_v2",
 ]
 __version__ = "0.1.0"

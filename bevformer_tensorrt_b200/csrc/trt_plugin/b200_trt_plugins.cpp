@@ -108,7 +108,9 @@ class Plugin final : public IPluginV2DynamicExt {
     nb_inputs_ = nbIn;  // DCN: 4 inputs without bias, 5 with (…Conv2dPlugin.cpp:297-299)
   }
   size_t getWorkspaceSize(const PluginTensorDesc *in, int32_t, const PluginTensorDesc *, int32_t) const noexcept override {
-    if (op_ != Op::kDCN) return 0;  // MSDA / grid sampler / rotate need none (…Plugin.cpp:64-69)
+    if (op_ == Op::kMSDA)  // the reference asks for 0 (…Plugin.cpp:64-69); the v2 kernels want room for the packed value stack
+      return b200_msda_enqueue_workspace_size(reinterpret_cast<const b200_tensor_desc *>(in));
+    if (op_ != Op::kDCN) return 0;  // grid sampler / rotate need none
     const Dims &x = in[0].dims, &w = in[3].dims;
     if (in[0].type == DataType::kINT8)
       return b200_dcn_i8_workspace_size(x.d[0], x.d[1], x.d[2], x.d[3], w.d[0], w.d[3], w.d[2], a_.stride[1], a_.stride[0],

@@ -352,13 +352,30 @@ class GroupedSCASampler:
             self.out.copy_(self.partial[lo:hi])
         return self.out
 
-    def _step_peer(self):
+    def exchange_only(self):
+        """The exchange without the sampling launch (bench.py's breakdown). Collective: every rank calls it equally often."""
+        s = self.shard
+        if self.exchange == "peer":
+            return self._step_peer(compute=False)
+        if self.exchange == "none":
+            return self.out
+        import torch.distributed as dist
+
+        if dist.get_backend(self.group) == "nccl" and (s.own1 - s.own0) * s.groups == self.rows and \
+                self.out_dtype == torch.float32:
+            dist.reduce_scatter_tensor(self.out, self.partial, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(self.partial, op=dist.ReduceOp.SUM, group=self.group)
+        return self.out
+
+    def _step_peer(self, compute=True):
         from . import _lib
 
         s, p = self.shard, self._peer
         k = self.epoch & 1
         self.epoch += 1
-        self.compute(self.partial[k])
+        if compute:
+            self.compute(self.partial[k])
         n = len(s.peers)
         parts = (ctypes.c_void_p * n)(*p["part"][k])
         flags = (ctypes.c_void_p * n)(*p["flags"])
