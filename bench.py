@@ -32,6 +32,32 @@ sys.path.insert(0, ROOT)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 WORKLOAD = "base_sca"
+WORKLOAD_TEXT = ("base_sca: MultiScaleDeformableAttn 200x200 BEV (40000 queries), 6 cams, 4 levels "
+                 "[[116,200],[58,100],[29,50],[15,25]], 8 heads x 32 ch, 4x8 points (BASELINE configs[2])")
+DIST_TEXT = {"U": "U: reference unit-test distribution (all points in range, worst case)",
+             "G": "G: camera-ring geometry (~1/6 of camera x query pairs visible)"}
+
+
+def workload_config(dist, gpus=1, flush=False):
+    """The `config` object BOTH arms print, built from the same arguments so that the driver's comparison sees one
+    configuration: workload, input distribution, how L2 is treated between timed steps, and the parallelism."""
+    return {"workload": WORKLOAD_TEXT, "distribution": DIST_TEXT[dist],
+            "l2": "flushed between launches (256 MiB memset)" if flush else
+                  "no flush: the step's inputs (590 MB fp16) are larger than the 126 MB L2",
+            "parallelism": "1 GPU" if gpus <= 1 else f"camera-group x query-tile shard over {gpus} GPUs"}
+
+
+def load_workloads():
+    """bevformer_tensorrt_b200/workloads.py loaded BY PATH (it needs torch only). The reference arm generates its inputs
+    through this so that its process never imports the product package and never maps the product's .so."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("b200_workloads_standalone",
+                                                  os.path.join(ROOT, "bevformer_tensorrt_b200", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def parse():
@@ -43,17 +69,16 @@ def parse():
     ap.add_argument("--dist", default="U", choices=["U", "G"], help="input distribution (SURVEY §8(d) config 3)")
     ap.add_argument("--dtype", default="f16", choices=["f16", "f32", "i8"])
     ap.add_argument("--f16-mode", type=int, default=None, help="0 exact fp32 FMA, 1 mixed FHFMA (library default)")
+    ap.add_argument("--round1-kernel", action="store_true", help="run csrc/msda.cu instead of the second-generation path")
     ap.add_argument("--flush-l2", action="store_true", help="write a 256 MiB buffer between timed launches")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-sample-cams", type=int, default=1)
-    ap.add_argument("--cpu-repeats", type=int, default=2)
-    ap.add_argument("--chunks", type=int, default=1, help="N>1: query chunks whose all-reduce overlaps the next chunk")
-    ap.add_argument("--wire", default="f16", choices=["f16", "f32"], help="N>1: dtype of the accumulator on the wire")
-    ap.add_argument("--unfused", action="store_true", help="N>1: plugin op + torch camera-sum instead of the fused kernel")
+    ap.add_argument("--cpu-repeats", type=int, default=3)
+    ap.add_argument("--ref-queries", type=int, default=5000,
+                    help="--impl reference: BEV queries per step (all 6 cameras each); bounded so K steps stay short")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the same-box GPU baseline of the reference's kernels")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: reduce-scatter inside the camera group by our NVLink peer-memory kernel, or by NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true",
-                    help="N>1: capture the sharded step (kernels + NCCL all-reduce) into a CUDA graph. Off by default: "
-                         "on this image (torch 2.11 / NCCL 2.28.9) the capture of the collective hung at N=2")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other distribution / INT8) legs")
     return ap.parse_args()
 
@@ -118,64 +143,116 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # CPU baseline (the only place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_baseline(cfg, dist, sample_cams, repeats):
+def cpu_baseline(cfg, dist, nq, repeats):
+    """Same bounded sample as --impl reference: all cameras x `nq` of the BEV queries, all host threads."""
     from bevformer_tensorrt_b200.workloads import make_msda_inputs
     from oracle import msda as omsda
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     value, shapes, ref, off, logits = make_msda_inputs(cfg, dist, 0, torch.float32)
-    c = min(sample_cams, cfg.batch)
-    v, r, o, w = value[:c].contiguous(), ref[:c].contiguous(), off[:c].contiguous(), logits[:c].contiguous()
-    omsda.msda_torch_port(v[:, :, :, :], shapes, r[:, :2000], o[:, :2000], w[:, :2000])  # warm-up on a slice
+    nq = min(nq, cfg.num_query)
+    r, o, w = ref[:, :nq].contiguous(), off[:, :nq].contiguous(), logits[:, :nq].contiguous()
+    omsda.msda_torch_port(value, shapes, r[:, :256], o[:, :256], w[:, :256])  # warm-up on a slice
     times = []
     for _ in range(max(1, repeats)):
         t0 = time.perf_counter()
-        omsda.msda_torch_port(v, shapes, r, o, w)
+        omsda.msda_torch_port(value, shapes, r, o, w)
         times.append(time.perf_counter() - t0)
     t = sorted(times)[len(times) // 2]
-    # one BEV query spans all cfg.batch cameras; the sample covered c of them
-    qps = cfg.num_query * (c / cfg.batch) / t
-    return {"value": qps, "unit": "BEV queries/s", "cores": cores, "kind": "port",
-            "sample": f"{c} of {cfg.batch} cameras x {cfg.num_query} queries, fp32, distribution {dist}, "
+    return {"value": nq / t, "unit": "BEV queries/s", "cores": cores, "kind": "port",
+            "sample": f"all {cfg.batch} cameras x {nq} of {cfg.num_query} BEV queries, fp32, distribution {dist}, "
                       f"median of {len(times)} calls ({t:.3f} s/call), torch {torch.__version__} "
                       f"multi_scale_deformable_attn_pytorch restated (oracle/msda.py)"}  # fmt: skip
 
 
 def run_reference(args):
-    from bevformer_tensorrt_b200.workloads import CONFIGS
-
+    """The reference's CPU implementation of the path (multi_scale_deformable_attn_pytorch, det2trt/models/utils/
+    trt_ops.py:4-85, restated in oracle/msda.py — kind "port") on all host cores. A step = ALL 6 cameras x a fixed slice
+    of the 40000 BEV queries (bounded sample, ~2 s), so that --steps K --warmup W are honoured as given and the printed
+    ms_per_step is the true duration of a step. Never imports the product package."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = CONFIGS[WORKLOAD]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    from bevformer_tensorrt_b200.workloads import make_msda_inputs
+    wl = load_workloads()
     from oracle import msda as omsda
 
-    value, shapes, ref, off, logits = make_msda_inputs(cfg, args.dist, 0, torch.float32)
-    c = min(args.cpu_sample_cams, cfg.batch)
-    v, r, o, w = value[:c].contiguous(), ref[:c].contiguous(), off[:c].contiguous(), logits[:c].contiguous()
-    steps, warm = min(args.steps, 5), min(args.warmup, 1)
+    assert "bevformer_tensorrt_b200" not in sys.modules
+    cfg = wl.CONFIGS[WORKLOAD]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    value, shapes, ref, off, logits = wl.make_msda_inputs(cfg, args.dist, 0, torch.float32)
+    nq = min(cfg.num_query, args.ref_queries)
+    r, o, w = ref[:, :nq].contiguous(), off[:, :nq].contiguous(), logits[:, :nq].contiguous()
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     for _ in range(warm):
-        omsda.msda_torch_port(v, shapes, r, o, w)
+        omsda.msda_torch_port(value, shapes, r, o, w)
     t0 = time.perf_counter()
     for _ in range(steps):
-        omsda.msda_torch_port(v, shapes, r, o, w)
+        omsda.msda_torch_port(value, shapes, r, o, w)
     dt = (time.perf_counter() - t0) / steps
-    qps = cfg.num_query * (c / cfg.batch) / dt
-    sample = (f"each step = {c} of {cfg.batch} cameras x {cfg.num_query} queries (bounded sample), fp32, "
-              f"{steps} steps after {warm} warm-up (requested {args.steps}/{args.warmup}, capped to keep the CPU run short)")  # fmt: skip
+    qps = nq / dt  # one BEV query spans all 6 cameras, and all 6 were processed
+    sample = (f"each step = all {cfg.batch} cameras x {nq} of {cfg.num_query} BEV queries (bounded sample of the frame), "
+              f"fp32, {steps} steps after {warm} warm-up, torch {torch.__version__} on {cores} host threads; "
+              "multi_scale_deformable_attn_pytorch restated (oracle/msda.py)")
     print(json.dumps({
         "impl": "reference", "metric": "BEV queries/s (BEVFormer-base shapes)", "value": qps, "unit": "BEV queries/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3 * (cfg.batch / c),
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD}: MSDA 200x200 BEV, 6 cams, 4 levels, 8 heads x 32 ch, 4x8 points",
-                   "distribution": args.dist},
+        "config": workload_config(args.dist, args.gpus, args.flush_l2),
         "cpu_baseline": {"value": qps, "unit": "BEV queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "BEV queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
     }))  # fmt: skip
+
+
+def ref_gpu_baseline(cfg, host, dist, peak):
+    """Same-box GPU baseline: the reference's OWN CUDA kernels (oracle/_ref = its .cu files compiled unmodified) timed on
+    the same device tensors with the same CUDA-event method: ms_deformable_im2col_cuda<float>, <__half>, _h2 and
+    _int8<float|__half2> (…Kernel.cu:1106-1218). Baseline only — nothing here is on the product path."""
+    from oracle import REF_LIB
+    from oracle import msda as omsda
+
+    if not os.path.exists(REF_LIB):
+        return {"unavailable": "oracle/_ref/libref_kernels.so not built (needs /root/reference at build time)"}
+    from bevformer_tensorrt_b200.workloads import quantize_per_tensor
+
+    rk = omsda.RefKernels()
+    value, shapes, ref, off, logits = host
+    out = {"what": "reference kernels of TensorRT/plugin/multi_scale_deformable_attn compiled unmodified for sm_100a, "
+                   f"distribution {dist}, CUDA events, mean of 10 launches after 2 warm-up"}
+    sh = shapes.cuda()
+
+    def t(fn, n=10, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    for variant, td, eb in (("f32", torch.float32, 4), ("f16", torch.float16, 2), ("f16_h2", torch.float16, 2)):
+        dev = [x.to(td).cuda() for x in (value, ref, off, logits)]
+        ms = t(lambda: rk.msda(dev[0], sh, dev[1], dev[2], dev[3], variant=variant))
+        out[f"ms_deformable_im2col_cuda_{variant}"] = {
+            "kernel_ms": ms, "bev_queries_per_s": cfg.num_query / (ms * 1e-3),
+            "roofline_frac": cfg.algorithmic_bytes(eb) / (ms * 1e-3) / 1e9 / peak}
+        del dev
+    vq, sv = quantize_per_tensor(value)
+    oq, so = quantize_per_tensor(off)
+    wq, sw = quantize_per_tensor(logits)
+    for rdt, tag in ((torch.float32, "int8_float_ref"), (torch.float16, "int8_half2_ref")):
+        dev = [vq.cuda(), ref.to(rdt).cuda(), oq.cuda(), wq.cuda()]
+        ms = t(lambda: rk.msda_i8(dev[0], sv, sh, dev[1], dev[2], so, dev[3], sw, 1.6 / 127.0))
+        out[f"ms_deformable_im2col_cuda_{tag}"] = {
+            "kernel_ms": ms, "bev_queries_per_s": cfg.num_query / (ms * 1e-3),
+            "roofline_frac": cfg.algorithmic_bytes(1, 4 if rdt == torch.float32 else 2) / (ms * 1e-3) / 1e9 / peak}
+    torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -222,6 +299,10 @@ def run_single(args, cfg, peak, peak_src):
 
     if args.f16_mode is not None:
         _lib.load().b200_msda_set_f16_mode(args.f16_mode)
+    import bevformer_tensorrt_b200 as bt
+
+    v2_on = not args.round1_kernel
+    bt.set_msda_v2(v2_on)
     torch.cuda.set_device(0)
     host = make_msda_inputs(cfg, args.dist, 0, torch.float32)
     fn, eb, rb, dev = make_op(args.dtype, host)
@@ -262,17 +343,15 @@ def run_single(args, cfg, peak, peak_src):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"f16": "f16 storage, f32 index math + accumulate", "f32": "f32", "i8": "i8 storage, f32 math"}[args.dtype],
         "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD}: MultiScaleDeformableAttn 200x200 BEV (40000 queries), 6 cams, 4 levels "
-                               "[[116,200],[58,100],[29,50],[15,25]], 8 heads x 32 ch, 4x8 points (BASELINE configs[2])",
-                   "distribution": {"U": "U: reference unit-test distribution (all points in range, worst case)",
-                                    "G": "G: camera-ring geometry (~1/6 of camera x query pairs visible)"}[args.dist],
-                   "l2": "flushed between launches (256 MiB memset)" if args.flush_l2 else
-                         "no flush: the step's inputs (590 MB fp16) are larger than the 126 MB L2",
-                   "parallelism": "1 GPU"},
+        "config": workload_config(args.dist, 1, args.flush_l2),
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(f"{args.dtype}_{args.dist}"), "kernel": "msda_gather_kernel",
+                     "traffic": ncu_traffic(f"{args.dtype}_{args.dist}"),
+                     "traffic_source": "static: dram__bytes_read+write per launch from the committed ncu --set full "
+                                       "capture of this kernel/config (profiles/ncu_traffic.json), not re-measured in this run",
+                     "kernel": ("msda_pack_kernel + msda_v2_kernel: the op's two launches, timed together (pack pre-pass "
+                                "included in the denominator)") if args.dtype in ("f16", "i8") and v2_on else "msda_gather_kernel",
                      "kernel_ms": k_ms, "kernel_ms_min": per[0],
                      "algorithmic_bytes": alg, "peak_source": peak_src},
         "wall_s": wall,
@@ -370,62 +449,143 @@ def run_e2e(args, cfg, host):
                     "copy of out, pipelined per camera over 3 streams; CUDA events around the steps, the end event waits for all 3 streams"}  # fmt: skip
 
 
+def other_ops_legs(hbm_peak_gbs):
+    """The other two plugins of the path under the same clock (CUDA events per launch, mean of 30 after 5 warm-up):
+    grid sampler prev-BEV warp [1,256,200,200] (BASELINE configs[3]) FP16 / kCHW2 / INT8-kCHW4 against the HBM roofline
+    (inputs 10-41 MB: L2-resident between launches, stated), DCNv2 R101 stage-3 layer [6,256,58,100] 3x3 FP16 / INT8
+    against the measured SUSTAINED bf16 tensor peak (the one dense contraction on the path)."""
+    import bevformer_tensorrt_b200 as bt
+    from bevformer_tensorrt_b200.functions.grid_sampler import pack_chw
+
+    pk = {}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tens = float(pk.get("bf16_tflops_sustained", 1400.0))
+    tens_src = "measured bf16_tflops_sustained" if "bf16_tflops_sustained" in pk else "fallback 1400 TFLOP/s sustained"
+    out = {}
+    H = W = 200
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(1, 256, H, W, device="cuda", generator=g)
+    th = 0.05
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, H, device="cuda"), torch.linspace(-1, 1, W, device="cuda"), indexing="ij")
+    grid = torch.stack([xs * 0.9988 - ys * th, xs * th + ys * 0.9988], 0)[None].contiguous() * 10
+
+    def leg(fn, nbytes, note):
+        _, per = time_kernel(fn, 30, 5)
+        us = sum(per) / len(per) * 1e3
+        return {"kernel_us": us, "algorithmic_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / hbm_peak_gbs,
+                "note": note}
+
+    l2note = "tensors are L2-resident between launches (smaller than the 126 MB L2): an on-chip-warm figure"
+    xh, gh = x.half(), grid.half()
+    out["grid_sampler_f16_base"] = leg(lambda: bt.grid_sampler(xh, gh, "bilinear", "zeros", False), 41120000, l2note)
+    x2, g2 = pack_chw(xh, 2), gh.permute(0, 2, 3, 1).unsqueeze(1).contiguous()
+    out["grid_sampler_f16_chw2_base"] = leg(lambda: bt.grid_sampler_chw2(x2, g2, 256, "bilinear", "zeros", False),
+                                            41120000, l2note)
+    xi = torch.randint(-127, 127, (1, 64, H, W, 4), dtype=torch.int8, device="cuda")
+    gi = torch.zeros(1, 1, H, W, 4, dtype=torch.int8, device="cuda")
+    gi[..., 0] = (grid[0, 0] * 12.7).round().clamp(-127, 127).to(torch.int8)
+    gi[..., 1] = (grid[0, 1] * 12.7).round().clamp(-127, 127).to(torch.int8)
+    out["grid_sampler_i8_chw4_base"] = leg(
+        lambda: bt.grid_sampler_int8(xi, 0.03, gi, 10 / 127, 0.03, 256, "bilinear", "zeros", False), 20640000, l2note)
+
+    xd = torch.randn(6, 256, 58, 100, device="cuda", generator=g)
+    off = torch.randn(6, 18, 58, 100, device="cuda", generator=g) * 2
+    mask = torch.sigmoid(torch.randn(6, 9, 58, 100, device="cuda", generator=g))
+    w = torch.nn.Parameter(torch.randn(256, 256, 3, 3, device="cuda", generator=g).half() / 48, requires_grad=False)
+    b = torch.randn(256, device="cuda", generator=g).half()
+    flops = 2 * 256 * 2304 * 5800 * 6
+
+    def dleg(fn, note):
+        _, per = time_kernel(fn, 30, 5)
+        us = sum(per) / len(per) * 1e3
+        return {"kernel_us": us, "tflops": flops / (us * 1e-6) / 1e12, "tensor_frac": flops / (us * 1e-6) / 1e12 / tens,
+                "peak_tflops": tens, "peak_source": tens_src, "note": note}
+
+    a16 = [xd.half(), off.half(), mask.half()]
+    out["dcn_f16_base"] = dleg(lambda: bt.modulated_deformable_conv2d(*a16, w, b, 1, 1, 1, 1, 1),
+                               "plugin op on NCHW input; NCHW->NHWC pre-pass + fused tcgen05 implicit GEMM; packed weights cached (constant at inference)")
+    xcl = a16[0].contiguous(memory_format=torch.channels_last)
+    out["dcn_f16_base_channels_last"] = dleg(lambda: bt.modulated_deformable_conv2d(xcl, a16[1], a16[2], w, b, 1, 1, 1, 1, 1),
+                                             "channels-last input consumed in place: the fused kernel only")
+    xq = torch.randint(-127, 127, (6, 64, 58, 100, 4), dtype=torch.int8, device="cuda")
+    wq = torch.randint(-127, 127, (256, 64, 3, 3, 4), dtype=torch.int8, device="cuda")
+    oq = torch.randint(-127, 127, (6, 18, 58, 100), dtype=torch.int8, device="cuda")
+    mq = torch.randint(0, 127, (6, 9, 58, 100), dtype=torch.int8, device="cuda")
+    out["dcn_i8_base"] = dleg(lambda: bt.modulated_deformable_conv2d_int8(xq, 0.02, oq, 0.03, mq, 1 / 127, wq, 0.001, b, 0.05, 256,
+                                                                          1, 1, 1, 1, 1),
+                              "INT8 kCHW4 plugin op: pre-passes + fused tcgen05 kernel, one requantisation")
+    return out
+
+
 def run_multi(args, cfg, peak, peak_src):
+    """N > 1: camera-group x query-tile grid (sharding.plan_grid). Every rank runs ONE fused sampling launch (its cameras x
+    its query tile, bev_mask camera-sum folded in) and ONE exchange launch: the reduce-scatter of the BEV accumulator
+    inside its camera group, by our own kernel over NVLink peer memory (--exchange peer, default) or by NCCL
+    reduce_scatter (--exchange nccl, the library baseline). Every rank ends up owning the final rows of 1/N of the BEV
+    queries (the consumer, output_proj, is query-parallel)."""
     import torch.distributed as dist
 
     import bevformer_tensorrt_b200 as bt
     from bevformer_tensorrt_b200 import _lib
-    from bevformer_tensorrt_b200.sharding import ShardedSCASampler, plan_chunk_bounds, plan_chunked
+    from bevformer_tensorrt_b200.sharding import GroupedSCASampler, plan_grid
     from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img, make_msda_inputs
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
     td = torch.float16 if args.dtype != "f32" else torch.float32
     value, shapes, ref, off, logits = make_msda_inputs(cfg, args.dist, 0, td)
     if args.dist == "G":
         _, bev_mask = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(cfg.batch))
     else:
         # distribution U has every sampling point of every camera in range, i.e. every camera "sees" every query: the
-        # matching visibility weights are 1/6 everywhere, so N>1 does exactly the work of the N=1 step (strong scaling)
+        # matching visibility weights are 1/6 everywhere, so N>1 does exactly the work of the N=1 fused step
         bev_mask = torch.full((cfg.batch, cfg.num_query, 1), 1.0 / cfg.batch)
-    wire = torch.float16 if (td == torch.float16 and args.wire == "f16") else None
-    plan = plan_chunked(cfg.batch, cfg.num_query, world, args.chunks)
-    sampler = ShardedSCASampler([chunk[rank] for chunk in plan], cfg.num_query, bt.multi_scale_deformable_attn,
-                                fused_sca=None if args.unfused else bt.multi_scale_deformable_attn_sca,
-                                chunk_bounds=plan_chunk_bounds(plan), wire_dtype=wire).load(
-        value, shapes, ref, off, logits, bev_mask.to(td), torch.device("cuda", local))
-    del value, ref, off, logits
+    width = cfg.num_heads * cfg.channels
+    plan = plan_grid(cfg.batch, cfg.num_query, world)
+    shard = plan[rank]
+    exchange = args.exchange
+    smp = GroupedSCASampler(shard, width, bt.multi_scale_deformable_attn_sca, exchange=exchange).load(
+        value, shapes, ref, off, logits, bev_mask.to(td), dev)
+    ok = torch.ones(1, device=dev)
+    try:
+        smp.connect(plan, dev)
+    except Exception as e:  # noqa: BLE001 — symmetric memory unavailable: every rank falls back to NCCL together
+        print(f"[bench] rank {rank}: peer-memory window failed ({type(e).__name__}: {e}); using NCCL reduce_scatter", file=sys.stderr)
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0:
+        exchange = "nccl"
+        smp = GroupedSCASampler(shard, width, bt.multi_scale_deformable_attn_sca, exchange="nccl").load(
+            value, shapes, ref, off, logits, bev_mask.to(td), dev).connect(plan, dev)
 
     for _ in range(max(3, args.warmup)):
-        sampler.step()
+        smp.step()
     torch.cuda.synchronize()
-    graphed = False
-    if args.graph:
-        # the whole step (memset, kernels, wire conversion, all-reduce) as one CUDA graph; eager fallback if the capture
-        # or its check fails on any rank (all ranks take the same branch: the flag is all-reduced)
-        # Every rank issues the same collectives in the same order whatever happens locally: capture (records, does not
-        # communicate) -> agree on success -> replay + compare -> agree again.
-        want = sampler.step().clone()
-        ok = torch.ones(1, device="cuda")
-        try:
-            sampler.capture()
-        except Exception as e:  # noqa: BLE001
-            print(f"[bench] rank {rank}: CUDA-graph capture of the sharded step failed, running eager: {e}", file=sys.stderr)
-            ok.zero_()
-        graph, sampler._graph = sampler._graph, None
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if ok.item() > 0 and graph is not None:
-            sampler._graph = graph
-            got = sampler.step()
-            torch.cuda.synchronize()
-            if not torch.allclose(got, want, atol=2e-3, rtol=1e-3):
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            graphed = bool(ok.item() > 0)
-            if not graphed:
-                sampler._graph = None
+    # ---- correctness of the sharded result on hardware: owned slices gathered on rank 0 vs the single-GPU fused op
+    got = smp.step().float().clone()
+    rows_max = max(x.own1 - x.own0 for x in plan)
+    pad = torch.zeros(rows_max, width, device=dev)
+    pad[: got.shape[0]] = got
+    gathered = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, gathered, dst=0)
+    max_abs_vs_1gpu = None
+    if rank == 0:
+        full = [t.to(dev) for t in (value, shapes, ref, off, logits)]
+        want = bt.multi_scale_deformable_attn_sca(*full, bev_mask.to(dev))
+        err = 0.0
+        for x, g in zip(plan, gathered):
+            err = max(err, (g[: x.own1 - x.own0] - want[x.own0 : x.own1]).abs().max().item())
+        max_abs_vs_1gpu = err
+        del full, want
+    del value, ref, off, logits
+    torch.cuda.empty_cache()
+
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -434,7 +594,7 @@ def run_multi(args, cfg, peak, peak_src):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(args.steps):
-            sampler.step()
+            smp.step()
         b.record()
         torch.cuda.synchronize()
         dist.barrier()
@@ -443,43 +603,36 @@ def run_multi(args, cfg, peak, peak_src):
         launches = _lib.launch_count() - n0
         t0 = time.perf_counter()
         while time.perf_counter() - t0 < 0.7:
-            sampler.step(reduce=False)
+            smp.step()
         torch.cuda.synchronize()
-    # compute-only and reduce-only breakdown (reported separately)
+    # breakdown (reported separately): the local sampling launch alone, the exchange alone
+    scratch = torch.zeros(shard.q1 - shard.q0, width, device=dev)
     a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a2.record()
     for _ in range(20):
-        sampler.step(reduce=False)
+        smp.compute(scratch)
     b2.record()
     torch.cuda.synchronize()
     ms_compute = a2.elapsed_time(b2) / 20
     dist.barrier()
     a3, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a3.record()
-    red_buf = sampler._wire if sampler._wire is not None else sampler.accum
     for _ in range(20):
-        dist.all_reduce(red_buf)
+        smp.exchange_only()
     b3.record()
     torch.cuda.synchronize()
-    ms_reduce = a3.elapsed_time(b3) / 20
+    ms_exchange = a3.elapsed_time(b3) / 20
     # end to end: every step copies this rank's shard of the inputs from pinned host memory, runs the sharded step and
-    # (rank 0) reads the reduced BEV accumulator back to pinned host memory
-    pinned = [[t.cpu().pin_memory() for t in grp[1:]] for _, _, _, loc in sampler.chunks for grp in loc]
-    pinned_value = {id(grp[0]): grp[0].cpu().pin_memory() for _, _, _, loc in sampler.chunks for grp in loc}
-    dev = [grp for _, _, _, loc in sampler.chunks for grp in loc]
-    out_host = torch.empty_like(sampler.accum, device="cpu").pin_memory()
-    h2d = sum(t.numel() * t.element_size() for p_ in pinned for t in p_) + sum(
-        t.numel() * t.element_size() for t in pinned_value.values())
+    # reads this rank's owned rows of the BEV accumulator back to pinned host memory
+    pinned = [t.cpu().pin_memory() for t in smp.local]
+    out_host = torch.empty_like(smp.out, device="cpu").pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in pinned)
+    d2h = out_host.numel() * out_host.element_size()
 
     def e2e_step():
-        for vid, hv in pinned_value.items():
-            next(g[0] for g in dev if id(g[0]) == vid).copy_(hv, non_blocking=True)
-        for g, hp in zip(dev, pinned):
-            for d_t, h_t in zip(g[1:], hp):
-                d_t.copy_(h_t, non_blocking=True)
-        sampler.step()
-        if rank == 0:
-            out_host.copy_(sampler.accum, non_blocking=True)
+        for d_t, h_t in zip(smp.local, pinned):
+            d_t.copy_(h_t, non_blocking=True)
+        out_host.copy_(smp.step(), non_blocking=True)
 
     for _ in range(2):
         e2e_step()
@@ -493,12 +646,12 @@ def run_multi(args, cfg, peak, peak_src):
     torch.cuda.synchronize()
     dist.barrier()
     ms_e2e = a4.elapsed_time(b4) / args.e2e_steps
-    t = torch.tensor([ms, ms_compute, ms_reduce, ms_e2e], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms, ms_compute, ms_exchange, ms_e2e], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_compute, ms_reduce, ms_e2e = t.tolist()
-    hb = torch.tensor([float(h2d)], device="cuda", dtype=torch.float64)
+    ms, ms_compute, ms_exchange, ms_e2e = t.tolist()
+    hb = torch.tensor([float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
     dist.all_reduce(hb, op=dist.ReduceOp.SUM)
-    h2d_total = int(hb.item())
+    h2d_total, d2h_total = int(hb[0].item()), int(hb[1].item())
     eb = 2 if td == torch.float16 else 4
     alg = cfg.algorithmic_bytes(eb)
     out = None
@@ -509,23 +662,25 @@ def run_multi(args, cfg, peak, peak_src):
             "unit": "BEV queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 storage, f32 index math + accumulate" if eb == 2 else "f32", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: MSDA 200x200 BEV, 6 cams, 4 levels, 8 heads x 32 ch, 4x8 points, "
-                                   "sharded per (camera, query tile); bev_mask camera-sum fused into the kernel; NCCL "
-                                   f"all-reduce of the BEV accumulator [40000,256] (fp32 on each rank, "
-                                   f"{'fp16' if wire is not None else 'fp32'} on the wire) in {len(plan)} query chunk(s)",
-                       "distribution": args.dist, "parallelism": f"camera-shard x{world}",
-                       "cuda_graph": graphed,
-                       "l2": "no flush: per-rank inputs exceed L2 only for N<=4; value stack is L2-resident by design"},
+            "config": workload_config(args.dist, world, False),
+            "sharding": {"camera_groups": shard.groups, "query_tiles": shard.tiles,
+                         "per_rank": f"{shard.cam1 - shard.cam0} cameras x {shard.q1 - shard.q0} queries, one fused "
+                                     "sampling launch (bev_mask camera-sum folded in) into an fp32 partial accumulator",
+                         "exchange": {"peer": "b200_sca_peer_reduce: reduce-scatter inside the camera group by our kernel over "
+                                              "NVLink peer memory (torch symmetric-memory window); no NCCL call in the step",
+                                      "nccl": "NCCL reduce_scatter_tensor on the camera group's communicator",
+                                      "none": "no exchange (one camera group)"}[smp.exchange],
+                         "result": f"every rank owns the final fp32 rows of {shard.own1 - shard.own0} BEV queries"},
+            "max_abs_vs_1gpu": max_abs_vs_1gpu,
             "gpu_launches": int(launches), "clocks": clk.summary(),
-            "breakdown_ms": {"step": ms, "local_kernels_and_camera_sum": ms_compute, "all_reduce_only": ms_reduce},
+            "breakdown_ms": {"step": ms, "local_sampling_launch": ms_compute, "exchange_only": ms_exchange},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "msda_gather_kernel (per-GPU share, local compute only)",
                          "algorithmic_bytes": alg, "peak_source": peak_src},
             "e2e": {"value": cfg.num_query / (ms_e2e * 1e-3), "unit": "BEV queries/s", "h2d_bytes_per_step": h2d_total,
-                    "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e,
-                    "steps": args.e2e_steps,
+                    "d2h_bytes_per_step": d2h_total, "ms_per_step": ms_e2e, "steps": args.e2e_steps,
                     "note": "per rank: pinned host -> device copy of its shard (value, ref, offsets, logits, bev_mask) + "
-                            "sharded step; rank 0 copies the reduced accumulator to pinned host memory"},
+                            "sharded step + device -> pinned host copy of the rows it owns"},
         }  # fmt: skip
     dist.destroy_process_group()
     return out
@@ -533,12 +688,12 @@ def run_multi(args, cfg, peak, peak_src):
 
 def main():
     args = parse()
+    if args.impl == "reference":  # before anything of the product is imported
+        run_reference(args)
+        return
     from bevformer_tensorrt_b200.workloads import CONFIGS
 
     cfg = CONFIGS[WORKLOAD]
-    if args.impl == "reference":
-        run_reference(args)
-        return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device. The product path has no CPU fallback; run under gpurun.")
     peak, peak_src = hbm_peak()
@@ -559,34 +714,39 @@ def main():
         sec = {}
         from bevformer_tensorrt_b200 import _lib
 
-        for dtype, dist_name, mode in (("f16", "G", None), ("f16", "U", 0), ("i8", "U", None), ("i8", "G", None),
-                                       ("f32", "U", None)):  # fmt: skip
-            if dtype == args.dtype and dist_name == args.dist and mode is None:
+        import bevformer_tensorrt_b200 as bt
+
+        # (dtype, distribution, second-generation path on?) — the *_round1_kernel legs run csrc/msda.cu on the same
+        # tensors (A/B of the rework); f32 has only the round-1 kernel
+        for dtype, dist_name, v2 in (("f16", "G", True), ("i8", "U", True), ("i8", "G", True), ("f16", "U", False),
+                                     ("f16", "G", False), ("i8", "U", False), ("i8", "G", False), ("f32", "U", True)):  # fmt: skip
+            if dtype == args.dtype and dist_name == args.dist and v2:
                 continue
             from bevformer_tensorrt_b200.workloads import make_msda_inputs
 
             h = make_msda_inputs(cfg, dist_name, 0, torch.float32)
-            prev = _lib.load().b200_msda_set_f16_mode(mode) if mode is not None else None
+            prev = bt.set_msda_v2(v2)
             f2, eb, rb, _d = make_op(dtype, h)
             _, per = time_kernel(f2, 30, 5)
-            if prev is not None:
-                _lib.load().b200_msda_set_f16_mode(prev)
+            bt.set_msda_v2(prev)
             k = sum(per) / len(per)
             alg = cfg.algorithmic_bytes(eb, rb)
-            key = f"{dtype}_{dist_name}" + ("" if mode is None else f"_mode{mode}")
+            key = f"{dtype}_{dist_name}" + ("" if v2 else "_round1_kernel")
             sec[key] = {"kernel_ms": k, "bev_queries_per_s": cfg.num_query / (k * 1e-3),
                         "roofline_frac": alg / (k * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg}
             del f2, _d, h
             torch.cuda.empty_cache()
         # fused SCA sampling (MSDA + bev_mask camera-sum into the fp32 BEV accumulator): what the
-        # sharded N>1 path runs per rank, timed here on one GPU for reference (includes zeroing the accumulator)
-        import bevformer_tensorrt_b200 as bt
+        # sharded N>1 path runs per rank, timed here on one GPU (includes zeroing the accumulator). Each distribution
+        # gets ITS OWN visibility weights: U -> every camera sees every query (1/6 everywhere: the same sampling work as
+        # the plugin op, this is the same-work N=1 anchor of the scaling curve); G -> the camera ring's bev_mask.
         from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img, make_msda_inputs
 
-        _, bm = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(cfg.batch))
-        bm = bm.cuda()
+        _, ring = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(cfg.batch))
+        masks = {"U": torch.full((cfg.batch, cfg.num_query, 1), 1.0 / cfg.batch).cuda(), "G": ring.cuda()}
         for dist_name in ("U", "G"):
             h = [t.cuda() for t in make_msda_inputs(cfg, dist_name, 0, torch.float16)]
+            bm = masks[dist_name]
             acc = torch.zeros(cfg.num_query, cfg.num_heads * cfg.channels, device="cuda")
 
             def fused():
@@ -595,8 +755,11 @@ def main():
 
             _, per = time_kernel(fused, 30, 5)
             k = sum(per) / len(per)
-            sec[f"f16_{dist_name}_fused_sca"] = {"kernel_ms": k, "bev_queries_per_s": cfg.num_query / (k * 1e-3),
-                                                 "note": "zero 41 MB accumulator + fused kernel; no per-camera output"}
+            sec[f"f16_{dist_name}_fused_sca_{'uniform' if dist_name == 'U' else 'ring'}_mask"] = {
+                "kernel_ms": k, "bev_queries_per_s": cfg.num_query / (k * 1e-3),
+                "note": "zero the 41 MB fp32 accumulator + fused kernel; no per-camera output; "
+                        + ("uniform 1/6 visibility = same sampling work as the plugin op (N=1 anchor of the scaling curve)"
+                           if dist_name == "U" else "camera-ring bev_mask")}
             # camera-shared form: offsets / logits passed once (the reference repeats the query per camera, so the
             # plugin's six copies are identical), cameras looped in registers, one plain store per slot
             hs = [h[0], h[1], h[2], h[3][:1].contiguous(), h[4][:1].contiguous()]
@@ -608,9 +771,15 @@ def main():
                                                   "roofline_frac": sb / (k * 1e-3) / 1e9 / peak,
                                                   "note": "offsets/logits once for all cameras; single kernel, no memset"}
             del h, hs
+        torch.cuda.empty_cache()
+        sec.update(other_ops_legs(peak))
         out["secondary"] = sec
+    if not args.no_ref_gpu:
+        del fn, dev
+        torch.cuda.empty_cache()
+        out["ref_gpu_baseline"] = ref_gpu_baseline(cfg, host, args.dist, peak)
     if not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(cfg, args.dist, args.cpu_sample_cams, args.cpu_repeats)
+        out["cpu_baseline"] = cpu_baseline(cfg, args.dist, args.ref_queries, args.cpu_repeats)
     print(json.dumps(out))
 
 

@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    r = subprocess.run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcublas"], capture_output=True, text=True)
+    r = subprocess.run([NVCC, *ARCH, "-shared", "-o", LIB, *objs], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB

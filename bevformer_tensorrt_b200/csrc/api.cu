@@ -30,7 +30,7 @@ unsigned long long b200_launch_count(void) { return g_launch_count.load(std::mem
 int b200_msda_enqueue(const b200_tensor_desc *in, const b200_tensor_desc *out, const void *const *inputs,
                       void *const *outputs, void *workspace, void *stream, int use_h2) {
   // The reference asks for 0 workspace bytes (…Plugin.cpp:64-69). A host that lends b200_msda_enqueue_workspace_size()
-  // bytes gets the second-generation FP16 / INT8 kernels (msda_v2.cu); workspace == NULL keeps the round-1 kernels.
+  // bytes gets the second-generation INT8 kernels (msda_v2.cu); workspace == NULL keeps the round-1 kernels.
   if (!in || !out || !inputs || !outputs) return B200_ERR_BAD_PARAM;
   const int batch = in[0].dims.d[0], spatial = in[0].dims.d[1], heads = in[0].dims.d[2], ch = in[0].dims.d[3];
   const int levels = in[1].dims.d[0];
@@ -42,22 +42,15 @@ int b200_msda_enqueue(const b200_tensor_desc *in, const b200_tensor_desc *out, c
       return b200_msda_f32(static_cast<const float *>(inputs[0]), shapes, static_cast<const float *>(inputs[2]),
                            static_cast<const float *>(inputs[3]), static_cast<const float *>(inputs[4]), batch,
                            spatial, heads, ch, levels, Q, P, G, static_cast<float *>(outputs[0]), stream);
-    case 1: {  // kHALF
-      const size_t ws = workspace ? b200_msda_workspace_size(1, batch, spatial, heads, ch, levels, P, G) : 0;
-      if (ws) {
-        const int st = b200_msda_f16_ws(inputs[0], shapes, inputs[2], inputs[3], inputs[4], batch, spatial, heads, ch,
-                                        levels, Q, P, G, outputs[0], workspace, ws, nullptr, stream);
-        if (st != B200_ERR_UNSUPPORTED) return st;
-      }
+    case 1:  // kHALF
       if (use_h2 && ch % 2 == 0)
         return b200_msda_f16_h2(inputs[0], shapes, inputs[2], inputs[3], inputs[4], batch, spatial, heads, ch, levels,
                                 Q, P, G, outputs[0], stream);
       return b200_msda_f16(inputs[0], shapes, inputs[2], inputs[3], inputs[4], batch, spatial, heads, ch, levels, Q, P,
                            G, outputs[0], stream);
-    }
     case 2: {  // kINT8; reference points stay fp16 or fp32 (…Plugin.cpp:168-176)
       if (in[2].type != 0 && in[2].type != 1) return B200_ERR_UNSUPPORTED;
-      const size_t ws = workspace ? b200_msda_workspace_size(2, batch, spatial, heads, ch, levels, P, G) : 0;
+      const size_t ws = workspace ? b200_msda_i8_workspace_size(batch, spatial, heads, ch, levels, P, G) : 0;
       if (ws) {
         const int st = b200_msda_i8_ws(static_cast<const int8_t *>(inputs[0]), in[0].scale, shapes, inputs[2],
                                        in[2].type == 1, static_cast<const int8_t *>(inputs[3]), in[3].scale,
@@ -81,10 +74,9 @@ size_t b200_msda_enqueue_workspace_size(const b200_tensor_desc *in) {
   if (!in) return 0;
   const int levels = in[1].dims.d[0];
   if (levels <= 0) return 0;
-  const int dtype = in[0].type == 1 ? 1 : (in[0].type == 2 ? 2 : 0);
-  if (!dtype) return 0;
-  return b200_msda_workspace_size(dtype, in[0].dims.d[0], in[0].dims.d[1], in[0].dims.d[2], in[0].dims.d[3], levels,
-                                  in[4].dims.d[3] / levels, in[2].dims.d[3] / 2);
+  if (in[0].type != 2) return 0;  // kINT8 only
+  return b200_msda_i8_workspace_size(in[0].dims.d[0], in[0].dims.d[1], in[0].dims.d[2], in[0].dims.d[3], levels,
+                                     in[4].dims.d[3] / levels, in[2].dims.d[3] / 2);
 }
 
 int b200_msda_supports_format(int pos, const b200_tensor_desc *io, int nb_inputs, int nb_outputs) {

@@ -16,24 +16,24 @@ from torch.autograd import Function
 
 from .. import _lib
 
-# Second-generation path (csrc/msda_v2.cu: pack pre-pass + tensor-core / dp2a gather) for FP16 and INT8 at channels == 32
-# and 16 <= levels*points <= 32 — every SpatialCrossAttention call of BEVFormer. Other shapes (TSA, decoder: 4 points)
-# and FP32 run the round-1 kernel (csrc/msda.cu). B200_MSDA_V2=0 or set_msda_v2(False) forces the round-1 kernel (A/B).
+# Second-generation INT8 path (csrc/msda_v2.cu: pack pre-pass + 128-byte-run gather with dp2a) at channels == 32 and
+# 16 <= levels*points <= 32 — every SpatialCrossAttention call of BEVFormer. Other shapes (TSA, decoder: 4 points) and the
+# FP16 / FP32 ops run the round-1 kernel (csrc/msda.cu). B200_MSDA_V2=0 or set_msda_v2(False) forces the round-1 kernel.
 _V2 = {"enabled": os.environ.get("B200_MSDA_V2", "1") != "0"}
 
 
 def set_msda_v2(enabled: bool) -> bool:
-    """Enables / disables the second-generation MSDA path; returns the previous setting."""
+    """Enables / disables the second-generation INT8 MSDA path; returns the previous setting."""
     prev, _V2["enabled"] = _V2["enabled"], bool(enabled)
     return prev
 
 
-def _v2_workspace(lib, dtype_code, dims, device):
-    """Workspace tensor for the v2 path, or None when the shape is outside its envelope (or v2 is switched off)."""
+def _v2_workspace(lib, dims, device):
+    """Workspace tensor for the INT8 v2 path, or None when the shape is outside its envelope (or v2 is switched off)."""
     if not _V2["enabled"]:
         return None
     bs, num_keys, num_heads, channels, num_levels, _, num_point, ppg = dims
-    n = lib.b200_msda_workspace_size(dtype_code, bs, num_keys, num_heads, channels, num_levels, num_point, ppg)
+    n = lib.b200_msda_i8_workspace_size(bs, num_keys, num_heads, channels, num_levels, num_point, ppg)
     return torch.empty(n, dtype=torch.uint8, device=device) if n else None
 
 
@@ -87,15 +87,8 @@ def _msda_forward(value, value_spatial_shapes, reference_points, sampling_offset
     else:
         name = "b200_msda_f16_h2" if use_h2 and channels % 2 == 0 else "b200_msda_f16"
     with torch.cuda.device(value.device):
-        ws = _v2_workspace(lib, 1, dims, value.device) if dt == torch.float16 else None
-        st = 1
-        if ws is not None:
-            st = lib.b200_msda_f16_ws(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
-                                      *dims, out.data_ptr(), ws.data_ptr(), ws.numel(), None, _lib.current_stream_ptr())
-            name = "b200_msda_f16_ws" if st != 1 else name
-        if st == 1:  # outside the v2 envelope (or misaligned views): the round-1 kernel takes every shape
-            st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
-                                    *dims, out.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
+        st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
+                                *dims, out.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
     _lib.check(name, st)
     return out
 
@@ -171,7 +164,7 @@ def multi_scale_deformable_attn_int8(value_q, scale_value, value_spatial_shapes,
     w = weights_q.contiguous()
     out = torch.empty(bs, num_query, num_heads, channels, dtype=torch.int8, device=value_q.device)
     with torch.cuda.device(value_q.device):
-        ws = _v2_workspace(lib, 2, dims, value_q.device)
+        ws = _v2_workspace(lib, dims, value_q.device)
         st = 1
         if ws is not None:
             st = lib.b200_msda_i8_ws(value_q.data_ptr(), float(scale_value), shapes.data_ptr(), ref.data_ptr(),
@@ -213,15 +206,8 @@ def multi_scale_deformable_attn_sca(value, value_spatial_shapes, reference_point
             raise ValueError("accum must be a contiguous float32 [num_query, heads*channels] tensor")
     name = "b200_msda_sca_f32" if dt == torch.float32 else "b200_msda_sca_f16"
     with torch.cuda.device(value.device):
-        ws = _v2_workspace(lib, 1, dims, value.device) if dt == torch.float16 else None
-        st = 1
-        if ws is not None:
-            st = lib.b200_msda_sca_f16_ws(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(),
-                                          w.data_ptr(), mask.data_ptr(), *dims, accum.data_ptr(), ws.data_ptr(),
-                                          ws.numel(), _lib.current_stream_ptr())  # fmt: skip
-        if st == 1:
-            st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
-                                    mask.data_ptr(), *dims, accum.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
+        st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
+                                mask.data_ptr(), *dims, accum.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
         if st == 1:
             # shapes neither fused kernel takes (channels != 32, more than 64 points): plugin op + masked camera sum
             out = _msda_forward(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, False)
@@ -319,7 +305,7 @@ def msda_trace(value, value_spatial_shapes, reference_points, sampling_offsets, 
             ref = reference_points.contiguous()
             off, w = sampling_offsets.contiguous(), attention_weights.contiguous()
             name, st = "b200_msda_i8_trace", 1
-            ws = _v2_workspace(lib, 2, dims, value.device)
+            ws = _v2_workspace(lib, dims, value.device)
             if ws is not None:  # the kernel the plugin op runs for this shape is the one that is traced
                 st = lib.b200_msda_i8_ws(value.data_ptr(), sv, shapes.data_ptr(), ref.data_ptr(),
                                          int(ref.dtype == torch.float16), off.data_ptr(), so, w.data_ptr(), sw, *dims,
@@ -331,15 +317,9 @@ def msda_trace(value, value_spatial_shapes, reference_points, sampling_offsets, 
                                             out.data_ptr(), sout, rec.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
         elif dt in (torch.float32, torch.float16):
             ref, off, w = (t.to(dt).contiguous() for t in (reference_points, sampling_offsets, attention_weights))
-            name, st = ("b200_msda_f32_trace" if dt == torch.float32 else "b200_msda_f16_trace"), 1
-            ws = _v2_workspace(lib, 1, dims, value.device) if dt == torch.float16 else None
-            if ws is not None:
-                st = lib.b200_msda_f16_ws(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(),
-                                          w.data_ptr(), *dims, out.data_ptr(), ws.data_ptr(), ws.numel(), rec.data_ptr(),
-                                          _lib.current_stream_ptr())  # fmt: skip
-            if st == 1:
-                st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
-                                        *dims, out.data_ptr(), rec.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
+            name = "b200_msda_f32_trace" if dt == torch.float32 else "b200_msda_f16_trace"
+            st = getattr(lib, name)(value.data_ptr(), shapes.data_ptr(), ref.data_ptr(), off.data_ptr(), w.data_ptr(),
+                                    *dims, out.data_ptr(), rec.data_ptr(), _lib.current_stream_ptr())  # fmt: skip
         else:
             raise _lib.B200OpsError("msda_trace", 1)
     _lib.check(name, st)

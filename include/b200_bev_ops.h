@@ -117,37 +117,25 @@ int b200_msda_sca_shared_f16(const void *value, const int32_t *spatial_shapes, c
                              int spatial_size, int num_heads, int channels, int num_levels, int num_query,
                              int num_point, int points_per_group, float *slots, void *stream);
 
-/* ---- Second-generation MSDA path (csrc/msda_v2.cu): FP16 / INT8, channels == 32, 16 <= num_levels*num_point <= 32 ----
- * Same operator, same semantics and argument meaning as b200_msda_f16 / b200_msda_i8, with two differences in the
- * signature is one addition: the caller lends a WORKSPACE (TensorRT: IPluginV2DynamicExt::getWorkspaceSize / enqueue's
- * `workspace`; the reference's plugin asks for 0 bytes, …Plugin.cpp:64-69). Its size depends on tensor DIMENSIONS only
- * (a bound: 3 * spatial_size entries per camera and head — at base shapes ~1/3 of it is touched); spatial_shapes stays
- * the device tensor the reference plugin receives, the packed-stack plan is evaluated on the device.
+/* ---- Second-generation INT8 MSDA path (csrc/msda_v2.cu): channels == 32, 16 <= num_levels*num_point <= 32 ----
+ * Same operator, same semantics and argument meaning as b200_msda_i8, with one addition to the signature: the caller
+ * lends a WORKSPACE (TensorRT: IPluginV2DynamicExt::getWorkspaceSize / enqueue's `workspace`; the reference's plugin
+ * asks for 0 bytes, …Plugin.cpp:64-69). Its size depends on tensor DIMENSIONS only (a bound: 3 * spatial_size 64-byte
+ * entries per camera and head — at base shapes 97 MB of it are touched); spatial_shapes stays the device tensor the
+ * reference plugin receives, the packed-stack plan is evaluated on the device.
  * Two launches per call: (1) a pack pre-pass re-lays `value` into per-(camera, head) column-pair entries with the two
- * image rows interleaved per channel (value tiles staged through shared memory by TMA bulk copies), (2) the gather:
- * one item per warp, FP16 taps accumulated by mma.sync with the interleaved entry as the A fragment and fp16 hi/lo
- * tap weights in two B columns (fp32 accumulate), INT8 taps by dp2a against 16-bit fixed-point weights.
- * `trace_records` (optional, may be NULL): the gather kernel's own sampling-index records, as in b200_msda_*_trace.
- * Returns B200_ERR_UNSUPPORTED for shapes outside the envelope (callers fall back to b200_msda_f16 / _i8). */
-size_t b200_msda_workspace_size(int dtype /*1 fp16, 2 int8*/, int batch, int spatial_size, int num_heads, int channels,
-                                int num_levels, int num_point, int points_per_group); /* 0 = shape outside the envelope */
-/* L2 budget (bytes) the packed value stack may take; levels get their second (odd-row) copy from the coarsest level
- * down while the stack fits. Default 112 MiB (B200: 126 MB L2). Returns the previous value; bytes <= 0 only queries. */
-long long b200_msda_set_pack_budget(long long bytes);
-int b200_msda_f16_ws(const void *value, const int32_t *spatial_shapes, const void *reference_points,
-                     const void *sampling_offsets, const void *attn_weight, int batch, int spatial_size, int num_heads,
-                     int channels, int num_levels, int num_query, int num_point, int points_per_group, void *out,
-                     void *workspace, size_t workspace_bytes, int32_t *trace_records, void *stream);
+ * image rows interleaved per channel (value tiles staged through shared memory by TMA bulk copies); (2) the gather:
+ * a bilinear sample is one 128-byte run, one LDG.128 per lane, accumulated with dp2a against 16-bit fixed-point tap
+ * weights in int32, one requantisation (T2int8). Index arithmetic is the round-1 kernel's (FP32, bit-exact).
+ * `trace_records` (optional, may be NULL): the gather kernel's own sampling-index records, as in b200_msda_i8_trace.
+ * Returns B200_ERR_UNSUPPORTED for shapes outside the envelope (callers fall back to b200_msda_i8). */
+size_t b200_msda_i8_workspace_size(int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_point,
+                                   int points_per_group); /* 0 = shape outside the envelope */
 int b200_msda_i8_ws(const int8_t *value, float scale_value, const int32_t *spatial_shapes,
                     const void *reference_points, int ref_is_half, const int8_t *sampling_offsets, float scale_offset,
                     const int8_t *attn_weight, float scale_weight, int batch, int spatial_size, int num_heads,
                     int channels, int num_levels, int num_query, int num_point, int points_per_group, int8_t *out,
                     float scale_out, void *workspace, size_t workspace_bytes, int32_t *trace_records, void *stream);
-/* fused SCA sampling (see b200_msda_sca_f16) on the second-generation path */
-int b200_msda_sca_f16_ws(const void *value, const int32_t *spatial_shapes, const void *reference_points,
-                         const void *sampling_offsets, const void *attn_weight, const float *bev_mask, int batch,
-                         int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
-                         int points_per_group, float *accum, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Multi-GPU SCA (not in the reference, which runs spatial_cross_attention.py:270's camera sum on one
  * GPU): reduce-scatter of the fp32 BEV accumulator inside a camera group, over NVLink PEER MEMORY — no NCCL call.
@@ -218,8 +206,8 @@ typedef struct {
 int b200_msda_enqueue(const b200_tensor_desc *input_desc, const b200_tensor_desc *output_desc,
                       const void *const *inputs, void *const *outputs, void *workspace, void *stream, int use_h2);
 
-/* getWorkspaceSize mirror: bytes b200_msda_enqueue wants in `workspace` for the second-generation FP16 / INT8 kernels
- * (0 for FP32 and for shapes outside their envelope). enqueue(workspace == NULL) runs the round-1 kernels. */
+/* getWorkspaceSize mirror: bytes b200_msda_enqueue wants in `workspace` for the second-generation INT8 kernels
+ * (0 for FP32 / FP16 and for shapes outside their envelope). enqueue(workspace == NULL) runs the round-1 kernels. */
 size_t b200_msda_enqueue_workspace_size(const b200_tensor_desc *input_desc);
 
 /* Mirror of supportsFormatCombination (…Plugin.cpp:148-189): 1 if descriptor `pos` of in_out[0..5] is acceptable. */

@@ -29,9 +29,8 @@ def timeit(fn, n=30, warm=5):
 
 def main():
     cfg = CONFIGS["base_sca"]
-    lib = _lib.load()
+    _lib.load()
     out = {}
-    budgets = [int(x) << 20 for x in os.environ.get("AB_BUDGETS_MB", "112,100,1000").split(",")]
     for dist in ("U", "G"):
         host = make_msda_inputs(cfg, dist, 0, torch.float32)
         v, sh, r, o, w = host
@@ -54,13 +53,10 @@ def main():
             m, mn = timeit(fn)
             out[f"{tag}_{dist}_v1"] = {"ms": m, "min_ms": mn}
             bt.set_msda_v2(True)
-            for bud in budgets:
-                prev = lib.b200_msda_set_pack_budget(bud)
+            if tag == "i8":  # FP16 has only the round-1 kernel
                 got = fn().float()
                 m, mn = timeit(fn)
-                lib.b200_msda_set_pack_budget(prev)
-                out[f"{tag}_{dist}_v2_budget{bud >> 20}MB"] = {"ms": m, "min_ms": mn,
-                                                                "max_abs_vs_v1": (got - ref_out).abs().max().item()}
+                out[f"{tag}_{dist}_v2"] = {"ms": m, "min_ms": mn, "max_abs_vs_v1": (got - ref_out).abs().max().item()}
         del f16, i8
         torch.cuda.empty_cache()
     print(json.dumps(out, indent=1))

@@ -203,18 +203,18 @@ int main() {
     in[0].type = I8;
     CHECK(c->getWorkspaceSize(in, 5, &out, 1) ==
           b200_dcn_i8_workspace_size(6, 256, 58, 100, 256, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1));
-    {  // MSDA: room for the packed value stack of the second-generation FP16 / INT8 kernels; 0 where they do not apply
-      PluginTensorDesc base[5] = {desc(H, LIN, {6, 30825, 8, 32}), desc(I32, LIN, {4, 2}), desc(H, LIN, {6, 40000, 1, 8}),
-                                  desc(H, LIN, {6, 40000, 8, 64}), desc(H, LIN, {6, 40000, 8, 32})};
+    {  // MSDA: room for the packed value stack of the second-generation INT8 kernels; 0 where they do not apply
+      PluginTensorDesc base[5] = {desc(I8, LIN, {6, 30825, 8, 32}), desc(I32, LIN, {4, 2}), desc(H, LIN, {6, 40000, 1, 8}),
+                                  desc(I8, LIN, {6, 40000, 8, 64}), desc(I8, LIN, {6, 40000, 8, 32})};
       IPluginV2DynamicExt *m = make(Op::kMSDA, false);
-      CHECK(m->getWorkspaceSize(base, 5, &out, 1) == b200_msda_workspace_size(1, 6, 30825, 8, 32, 4, 8, 4));
-      CHECK(m->getWorkspaceSize(base, 5, &out, 1) == size_t(3) * 30825 * 128 * 6 * 8);
-      base[0].type = I8;
+      CHECK(m->getWorkspaceSize(base, 5, &out, 1) == b200_msda_i8_workspace_size(6, 30825, 8, 32, 4, 8, 4));
       CHECK(m->getWorkspaceSize(base, 5, &out, 1) == size_t(3) * 30825 * 64 * 6 * 8);
+      base[0].type = H;
+      CHECK(m->getWorkspaceSize(base, 5, &out, 1) == 0);  // FP16 / FP32: round-1 kernel, no workspace (…Plugin.cpp:64-69)
       base[0].type = F;
-      CHECK(m->getWorkspaceSize(base, 5, &out, 1) == 0);  // FP32: round-1 kernel, no workspace (…Plugin.cpp:64-69)
-      PluginTensorDesc tsa[5] = {desc(H, LIN, {2, 40000, 8, 32}), desc(I32, LIN, {1, 2}), desc(H, LIN, {2, 40000, 1, 2}),
-                                 desc(H, LIN, {2, 40000, 8, 8}), desc(H, LIN, {2, 40000, 8, 4})};
+      CHECK(m->getWorkspaceSize(base, 5, &out, 1) == 0);
+      PluginTensorDesc tsa[5] = {desc(I8, LIN, {2, 40000, 8, 32}), desc(I32, LIN, {1, 2}), desc(H, LIN, {2, 40000, 1, 2}),
+                                 desc(I8, LIN, {2, 40000, 8, 8}), desc(I8, LIN, {2, 40000, 8, 4})};
       CHECK(m->getWorkspaceSize(tsa, 5, &out, 1) == 0);  // 4 points: outside the v2 envelope
     }
     CHECK(make(Op::kGridSampler2D, false)->getWorkspaceSize(in, 2, &out, 1) == 0);

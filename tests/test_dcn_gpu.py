@@ -73,6 +73,59 @@ def test_fp16_fused_channels_last_input_and_packed_weight_cache():
     assert not torch.equal(upd, want)
 
 
+def test_packed_weight_cache_is_tied_to_the_weight_object():
+    """the packed-weight cache must never serve another tensor's weights. Entries live and die with the
+    nn.Parameter they were packed from; temporaries are packed per call."""
+    import gc
+
+    from bevformer_tensorrt_b200.functions import modulated_deformable_conv2d as mod
+
+    x, off, mask, w, b, kw = make_dcn_inputs("fused_co128", dtype=torch.float16)
+    xs = [t.cuda() for t in (x, off, mask)]
+    call = lambda wt: bt.modulated_deformable_conv2d(*xs, wt, b.cuda(), kw["stride"], kw["padding"], kw["dilation"], 1, 1)  # noqa: E731
+    p1 = torch.nn.Parameter(w.cuda(), requires_grad=False)
+    n0 = len(mod._PACKED)
+    out1 = call(p1)
+    assert len(mod._PACKED) == n0 + 1
+    l0 = _lib.launch_count()
+    assert torch.equal(call(p1), out1)
+    cached_launches = _lib.launch_count() - l0
+    l0 = _lib.launch_count()
+    assert torch.equal(call(w.cuda()), out1)  # a temporary: same values, packed on the spot, never cached
+    assert _lib.launch_count() - l0 == cached_launches + 1 and len(mod._PACKED) == n0 + 1
+    del p1
+    gc.collect()
+    assert len(mod._PACKED) == n0  # the entry died with its weight
+    p2 = torch.nn.Parameter((w * 3).cuda(), requires_grad=False)  # same shape, very likely the same address
+    out2 = call(p2)
+    assert torch.equal(out2, call((w * 3).cuda())) and not torch.equal(out2, out1)
+
+
+def test_dcnv2p_layer_runs_the_plugin_op():
+    """DCNv2P / DCNv2P2 (det2trt/models/modules/cnn/dcn.py:31-164) at the reference op test's structure: groups = 2,
+    deform_groups = 2 (test_modulated_deformable_conv2d.py:6-11,37): conv_offset -> (offset, sigmoid(mask)) -> op."""
+    from bevformer_tensorrt_b200.modules import CONV_LAYERS
+
+    torch.manual_seed(0)
+    for name, dt in (("DCNv2P", torch.float32), ("DCNv2P2", torch.float16)):
+        layer = CONV_LAYERS[name](16, 12, 3, stride=1, padding=1, groups=2, deform_groups=2).cuda()
+        layer.conv_offset.weight.data.normal_(0, 0.05)
+        layer.conv_offset.bias.data.normal_(0, 0.5)
+        layer.bias.data.normal_()
+        layer = layer.to(dt)
+        x = torch.randn(2, 16, 13, 17, device="cuda", dtype=dt)
+        got = layer(x)
+        o = layer.conv_offset(x)
+        o1, o2, m = torch.chunk(o, 3, dim=1)
+        want = odcn.modulated_deformable_conv2d(x.float().cpu().numpy(), torch.cat((o1, o2), 1).float().cpu().numpy(),
+                                                torch.sigmoid(m).float().cpu().numpy(), layer.weight.float().cpu().numpy(),
+                                                layer.bias.float().cpu().numpy(), stride=1, padding=1, dilation=1, groups=2,
+                                                deform_groups=2)  # fmt: skip
+        assert got.shape == (2, 12, 13, 17) and got.dtype == dt
+        tol = 1e-4 if dt == torch.float32 else 5e-3
+        assert np.abs(got.float().cpu().numpy() - want).max() < tol * max(1.0, np.abs(want).max())
+
+
 @pytest.mark.parametrize("case", ["k3_s1_p1_g2_dg2", "backbone_like", "k3_s2_p1_g1_dg1"])
 def test_fp16_matches_oracle(case):
     x, off, mask, w, b, kw = make_dcn_inputs(case, dtype=torch.float16)

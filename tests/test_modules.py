@@ -124,3 +124,28 @@ def test_encoder_prologue_feeds_sca_on_gpu():
     planar = bt.rotate(prev.view(50, 50, 256).permute(2, 0, 1).contiguous(), torch.tensor(3.0, device="cuda"),
                        torch.tensor([25.0, 25.0], device="cuda"))
     assert torch.equal(rot.view(50, 50, 256).permute(2, 0, 1), planar)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DCNv2P / DCNv2P2 conv layers (det2trt/models/modules/cnn/dcn.py:31-164)
+# ---------------------------------------------------------------------------------------------------------------
+def test_dcnv2p_layer_structure_and_checkpoint_keys():
+    from bevformer_tensorrt_b200.modules import CONV_LAYERS, ModulatedDeformConv2dPackPlugin2
+
+    layer = CONV_LAYERS["DCNv2P"](16, 12, 3, stride=1, padding=1, groups=2, deform_groups=2)
+    assert sorted(k for k, _ in layer.named_parameters()) == ["bias", "conv_offset.bias", "conv_offset.weight", "weight"]
+    assert layer.weight.shape == (12, 8, 3, 3) and layer.conv_offset.out_channels == 2 * 3 * 9
+    assert layer.conv_offset.weight.abs().max() == 0 and layer.conv_offset.bias.abs().max() == 0  # dcn.py:62-66
+    assert layer.bias.abs().max() == 0 and 0 < layer.weight.abs().max() <= 1.0 / (16 * 9) ** 0.5 + 1e-6
+    assert CONV_LAYERS["DCNv2P2"] is ModulatedDeformConv2dPackPlugin2 and ModulatedDeformConv2dPackPlugin2._version == 2
+    other = CONV_LAYERS["DCNv2P2"](16, 12, 3, padding=1, groups=2, deform_groups=2, bias=False)
+    assert other.bias is None
+    missing = other.load_state_dict({k: v for k, v in layer.state_dict().items() if k != "bias"})
+    assert not missing.missing_keys and torch.equal(other.weight, layer.weight)
+    # pre-version-2 checkpoints named the offset conv "<layer>_offset" (dcn.py:101-118)
+    sd = {"weight": layer.weight.data, "bias": layer.bias.data, "_offset.weight": torch.ones(54, 16, 3, 3),
+          "_offset.bias": torch.ones(54)}
+    layer._load_from_state_dict(sd, ".", {}, True, [], [], [])
+    assert ".conv_offset.weight" in sd and ".conv_offset.bias" in sd and "_offset.weight" not in sd  # renamed in place
+    with pytest.raises(ValueError):
+        CONV_LAYERS["DCNv2P"](10, 12, 3, groups=4)

@@ -161,7 +161,7 @@ def test_gather_kernel_indices_bit_exact_at_base_shapes(dist):
     bad = (rec != want).any(-1).sum()
     assert bad == 0, f"{bad} of {want[..., 0].size} records differ"
     frac = want[..., 0].mean()
-    assert (frac > 0.99) if dist == "U" else (0.05 < frac < 0.5)
+    assert (frac > 0.9) if dist == "U" else (0.05 < frac < 0.5)
 
 
 @pytest.mark.parametrize("ref_dtype", [torch.float32, torch.float16])
@@ -360,95 +360,72 @@ def test_base_shapes_fp16_vs_fp32_kernel_full_size():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# second-generation path (csrc/msda_v2.cu) against the round-1 kernel and under every packed-stack plan
+# second-generation INT8 path (csrc/msda_v2.cu) against the oracle and the round-1 kernel
 # ---------------------------------------------------------------------------------------------------------------
 V2_CASES = {
     "v2_odd_levels": MSDAConfig("v2_odd_levels", 2, 257, 8, 32, ((13, 21), (7, 11), (4, 6), (1, 3)), 8, 4),  # odd H and W, 1-row level
     "v2_two_levels": MSDAConfig("v2_two_levels", 1, 100, 8, 32, ((9, 70), (5, 129)), 8, 2),  # W > one 64-column pack tile
-    "v2_np16": MSDAConfig("v2_np16", 3, 77, 3, 32, ((6, 6), (3, 3)), 8, 1),  # 16 points: half of the lanes idle
-    "v2_np24": MSDAConfig("v2_np24", 1, 50, 5, 32, ((8, 9), (4, 5), (2, 3)), 8, 8),
+    "v2_np16": MSDAConfig("v2_np16", 3, 77, 3, 32, ((6, 6), (3, 3)), 8, 1),  # 16 points: half of the owner lanes idle
+    "v2_np24": MSDAConfig("v2_np24", 1, 50, 5, 32, ((8, 9), (4, 5), (2, 3)), 8, 4),
 }
 
 
-@pytest.mark.parametrize("budget", [1 << 40, 1])  # every level with / without its odd-row copy
+@pytest.mark.parametrize("ref_dtype", [torch.float32, torch.float16])
 @pytest.mark.parametrize("name,dist,seed", [("small_sca", "U", 111), ("small_sca", "edge", 112), ("v2_odd_levels", "edge", 113),
                                             ("v2_two_levels", "edge", 114), ("v2_np16", "U", 115), ("v2_np24", "edge", 116)])  # fmt: skip
-def test_v2_fp16_and_int8_match_oracle_under_both_pack_plans(name, dist, seed, budget):
+def test_v2_int8_matches_oracle_and_round1_kernel(name, dist, seed, ref_dtype):
     cfg = CONFIGS.get(name) or V2_CASES[name]
     lib = _lib.load()
-    assert lib.b200_msda_workspace_size(1, cfg.batch, cfg.spatial_size, cfg.num_heads, 32, cfg.num_levels, cfg.num_points,
-                                        cfg.points_per_group) > 0  # these shapes are inside the v2 envelope
-    prev = lib.b200_msda_set_pack_budget(budget)
+    assert lib.b200_msda_i8_workspace_size(cfg.batch, cfg.spatial_size, cfg.num_heads, 32, cfg.num_levels, cfg.num_points,
+                                           cfg.points_per_group) > 0  # these shapes are inside the v2 envelope
+    (vq, sv, shapes, ref, oq, so, wq, sw, sout), real = _quantised(cfg, dist, seed, ref_dtype)
+    args = (vq.cuda(), sv, shapes.cuda(), ref.cuda(), oq.cuda(), so, wq.cuda(), sw, sout)
+    n0 = _lib.launch_count()
+    got_t = bt.multi_scale_deformable_attn_int8(*args)
+    assert _lib.launch_count() == n0 + 2  # pack + gather
+    got = got_t.cpu().numpy()
+    assert np.abs(got.astype(np.float32) * sout - real).max() < INT8_TOL
+    want_q = omsda.msda_i8_dequant(vq.numpy(), sv, shapes.numpy(), ref.float().numpy(), oq.numpy(), so, wq.numpy(), sw, sout)
+    diff = np.abs(got.astype(np.int32) - want_q.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.02, (diff.max(), (diff != 0).mean())
+    # the v2 gather kernel's own index records, bit-exact
+    out_t, rec = msda_trace(args[0], args[2], args[3], args[4], args[6], scales=(sv, so, sw, sout))
+    assert torch.equal(out_t, got_t)
+    off_real = oq.numpy().astype(np.float32) * np.float32(so)
+    assert (rec.cpu().numpy() == _want_records(shapes, ref.float().numpy(), off_real, cfg)).all()
+    # round-1 kernel on the same tensors: at most 1 LSB apart on a few elements
+    prev = set_msda_v2(False)
     try:
-        inputs = make_msda_inputs(cfg, dist, seed, torch.float16)
-        want = _oracle_f32(inputs)
         n0 = _lib.launch_count()
-        out = bt.multi_scale_deformable_attn(*_cuda(inputs))
-        assert _lib.launch_count() == n0 + 2  # pack + gather
-        err = np.abs(out.float().cpu().numpy() - want).max()
-        assert err < FP16_TOL, (name, dist, budget, err)
-        # index records of the v2 gather kernel itself
-        out_t, rec = msda_trace(*_cuda(inputs))
-        assert torch.equal(out_t, out)
-        wrec = _want_records(inputs[1], inputs[2].float().numpy(), inputs[3].float().numpy(), cfg)
-        assert (rec.cpu().numpy() == wrec).all()
-        # round-1 kernel on the same inputs: both are within the bar of the oracle, hence within 2x of each other
-        p2 = set_msda_v2(False)
-        try:
-            v1 = bt.multi_scale_deformable_attn(*_cuda(inputs))
-        finally:
-            set_msda_v2(p2)
-        assert (v1.float() - out.float()).abs().max().item() < 2 * FP16_TOL
-        # INT8
-        for ref_dtype in (torch.float32, torch.float16):
-            (vq, sv, shapes, ref, oq, so, wq, sw, sout), real = _quantised(cfg, dist, seed + 1000, ref_dtype)
-            got = bt.multi_scale_deformable_attn_int8(vq.cuda(), sv, shapes, ref.cuda(), oq.cuda(), so, wq.cuda(), sw, sout)
-            got = got.cpu().numpy()
-            assert np.abs(got.astype(np.float32) * sout - real).max() < INT8_TOL
-            want_q = omsda.msda_i8_dequant(vq.numpy(), sv, shapes.numpy(), ref.float().numpy(), oq.numpy(), so, wq.numpy(),
-                                           sw, sout)  # fmt: skip
-            diff = np.abs(got.astype(np.int32) - want_q.astype(np.int32))
-            assert diff.max() <= 1 and (diff != 0).mean() < 0.02, (diff.max(), (diff != 0).mean())
+        v1 = bt.multi_scale_deformable_attn_int8(*args).cpu().numpy()
+        assert _lib.launch_count() == n0 + 1
     finally:
-        lib.b200_msda_set_pack_budget(prev)
+        set_msda_v2(prev)
+    d1 = np.abs(v1.astype(np.int32) - got.astype(np.int32))
+    assert d1.max() <= 1 and (d1 != 0).mean() < 0.03
 
 
 def test_v2_envelope_and_fallback():
     lib = _lib.load()
-    assert lib.b200_msda_workspace_size(1, 2, 40000, 8, 32, 1, 4, 1) == 0  # TSA: 4 points
-    assert lib.b200_msda_workspace_size(1, 1, 100, 8, 20, 4, 8, 4) == 0  # channels != 32
-    assert lib.b200_msda_workspace_size(0, 6, 30825, 8, 32, 4, 8, 4) == 0  # FP32 stays on the round-1 kernel
+    assert lib.b200_msda_i8_workspace_size(2, 40000, 8, 32, 1, 4, 1) == 0  # TSA: 4 points
+    assert lib.b200_msda_i8_workspace_size(1, 100, 8, 20, 4, 8, 4) == 0  # channels != 32
     cfg = EXTRA["many_points"]  # 64 points: outside the envelope, the op silently takes the round-1 kernel
-    inputs = make_msda_inputs(cfg, "U", 7, torch.float16)
+    (vq, sv, shapes, ref, oq, so, wq, sw, sout), real = _quantised(cfg, "U", 7, torch.float16)
     n0 = _lib.launch_count()
-    out = bt.multi_scale_deformable_attn(*_cuda(inputs))
+    out = bt.multi_scale_deformable_attn_int8(vq.cuda(), sv, shapes, ref.cuda(), oq.cuda(), so, wq.cuda(), sw, sout)
     assert _lib.launch_count() == n0 + 1
-    assert np.abs(out.float().cpu().numpy() - _oracle_f32(inputs)).max() < FP16_TOL
+    assert np.abs(out.cpu().numpy().astype(np.float32) * sout - real).max() < INT8_TOL
     # a too-small workspace is an error, not a silent overrun
     cfg = _cfg("small_sca")
-    v, sh, r, o, w = _cuda(make_msda_inputs(cfg, "U", 8, torch.float16))
-    out = torch.empty(cfg.batch, cfg.num_query, cfg.num_heads, 32, dtype=torch.float16, device="cuda")
+    (vq, sv, shapes, ref, oq, so, wq, sw, sout), _ = _quantised(cfg, "U", 8, torch.float16)
+    t = [x.cuda() for x in (vq, shapes, ref, oq, wq)]
+    out = torch.empty(cfg.batch, cfg.num_query, cfg.num_heads, 32, dtype=torch.int8, device="cuda")
     ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
-    st = lib.b200_msda_f16_ws(v.data_ptr(), sh.data_ptr(), r.data_ptr(), o.data_ptr(), w.data_ptr(), cfg.batch,
-                              cfg.spatial_size, cfg.num_heads, 32, cfg.num_levels, cfg.num_query, cfg.num_points,
-                              cfg.points_per_group, out.data_ptr(), ws.data_ptr(), ws.numel(), None, _lib.current_stream_ptr())
+    st = lib.b200_msda_i8_ws(t[0].data_ptr(), sv, t[1].data_ptr(), t[2].data_ptr(), 1, t[3].data_ptr(), so, t[4].data_ptr(), sw,
+                             cfg.batch, cfg.spatial_size, cfg.num_heads, 32, cfg.num_levels, cfg.num_query, cfg.num_points,
+                             cfg.points_per_group, out.data_ptr(), sout, ws.data_ptr(), ws.numel(), None,
+                             _lib.current_stream_ptr())  # fmt: skip
     assert st == 2
-
-
-def test_v2_fused_sca_matches_round1_fused_sca():
-    from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img
-
-    cfg = CONFIGS["base_sca"]
-    ins = _cuda(make_msda_inputs(cfg, "G", 9, torch.float16))
-    _, mask = bev_reference_points_cam(cfg.bev_hw, camera_ring_lidar2img(6))
-    mask = mask.cuda()
-    got = bt.multi_scale_deformable_attn_sca(*ins, mask)
-    prev = set_msda_v2(False)
-    try:
-        want = bt.multi_scale_deformable_attn_sca(*ins, mask)
-    finally:
-        set_msda_v2(prev)
-    assert (got - want).abs().max().item() < 2e-4 and want.abs().max().item() > 0.1
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -477,24 +454,35 @@ def test_plugin_enqueue_entry_matches_function():
     for pos in range(6):
         io = (_lib.TensorDesc * 6)(*in_desc, out_desc[0])
         assert lib.b200_msda_supports_format(pos, io, 5, 1) == 1
-    # workspace == NULL: the round-1 kernels, like the reference's 0-byte workspace (…Plugin.cpp:64-69)
     st = lib.b200_msda_enqueue(in_desc, out_desc, in_ptrs, out_ptrs, None, _lib.current_stream_ptr(), 1)
     assert st == 0
     torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    assert lib.b200_msda_enqueue_workspace_size(in_desc) == 0  # FP16: round-1 kernel, 0 bytes like the reference
+    # INT8: workspace == NULL runs the round-1 kernel (the reference's 0-byte workspace, …Plugin.cpp:64-69), the workspace
+    # getWorkspaceSize asks for selects the second-generation kernels (what the Python op runs)
+    (vq, sv, shq, rq, oq, so, wq, sw, sout), _ = _quantised(cfg, "U", 191, torch.float16)
+    qt = [vq.cuda(), shq.cuda(), rq.cuda(), oq.cuda(), wq.cuda()]
+    want8 = bt.multi_scale_deformable_attn_int8(qt[0], sv, qt[1], qt[2], qt[3], so, qt[4], sw, sout)
+    out8 = torch.empty_like(want8)
+    d8 = (_lib.TensorDesc * 5)(desc(qt[0], 2, sv), desc(qt[1], 3), desc(qt[2], 1), desc(qt[3], 2, so), desc(qt[4], 2, sw))
+    o8 = (_lib.TensorDesc * 1)(desc(out8, 2, sout))
+    p8 = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in qt])
+    q8 = (ctypes.c_void_p * 1)(out8.data_ptr())
+    nbytes = lib.b200_msda_enqueue_workspace_size(d8)
+    assert nbytes == lib.b200_msda_i8_workspace_size(*vq.shape, shq.shape[0], cfg.num_points, cfg.points_per_group) > 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    assert lib.b200_msda_enqueue(d8, o8, p8, q8, ws.data_ptr(), _lib.current_stream_ptr(), 0) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out8, want8)
     prev = set_msda_v2(False)
     try:
-        assert torch.equal(out, bt.multi_scale_deformable_attn(value, shapes, ref, off, logits))
+        want8_r1 = bt.multi_scale_deformable_attn_int8(qt[0], sv, qt[1], qt[2], qt[3], so, qt[4], sw, sout)
     finally:
         set_msda_v2(prev)
-    # with the workspace getWorkspaceSize asks for: the second-generation kernels (what the Python op runs)
-    nbytes = lib.b200_msda_enqueue_workspace_size(in_desc)
-    assert nbytes == lib.b200_msda_workspace_size(1, *value.shape, shapes.shape[0], cfg.num_points, cfg.points_per_group) > 0
-    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-    out.zero_()
-    st = lib.b200_msda_enqueue(in_desc, out_desc, in_ptrs, out_ptrs, ws.data_ptr(), _lib.current_stream_ptr(), 0)
-    assert st == 0
+    assert lib.b200_msda_enqueue(d8, o8, p8, q8, None, _lib.current_stream_ptr(), 0) == 0
     torch.cuda.synchronize()
-    assert torch.equal(out, want)
+    assert torch.equal(out8, want8_r1)
     in_desc[0].type = 3  # int32 value: unsupported dtype -> 1, like the reference's enqueue
     assert lib.b200_msda_enqueue(in_desc, out_desc, in_ptrs, out_ptrs, None, _lib.current_stream_ptr(), 0) == 1
 
