@@ -61,6 +61,12 @@ SIGNATURES = {
                                ctypes.POINTER(_vp), _vp, _vp, _i]),
     "b200_msda_enqueue_workspace_size": (ctypes.c_size_t, [ctypes.POINTER(TensorDesc)]),
     "b200_msda_supports_format": (_i, [_i, ctypes.POINTER(TensorDesc), _i, _i]),
+    "b200_grid_sampler_enqueue": (_i, [ctypes.POINTER(TensorDesc), ctypes.POINTER(TensorDesc), ctypes.POINTER(_vp),
+                                       ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i]),
+    "b200_grid_sampler_supports_format": (_i, [_i, ctypes.POINTER(TensorDesc), _i, _i, _i]),
+    "b200_dcn_enqueue_workspace_size": (ctypes.c_size_t, [ctypes.POINTER(TensorDesc), _ip, _ip, _ip, _i, _i]),
+    "b200_dcn_enqueue": (_i, [ctypes.POINTER(TensorDesc), ctypes.POINTER(TensorDesc), ctypes.POINTER(_vp),
+                              ctypes.POINTER(_vp), _vp, _vp, _i, _ip, _ip, _ip, _i, _i]),
     "b200_dcn_workspace_size": (ctypes.c_size_t, [_i] * 13),
     "b200_dcn_i8_workspace_size": (ctypes.c_size_t, [_i] * 15),
     "b200_dcn_set_fused": (_i, [_i]),
@@ -69,6 +75,8 @@ SIGNATURES = {
     "b200_dcn_i8": (_i, [_vp, _f, _vp, _f, _vp, _i, _vp, _f, _vp, _f, _vp, _f, _vp] + [_i] * 16 + [_vp, _vp]),
     "b200_dcn_f32": (_i, [_vp] * 7 + [_i] * 16 + [_vp, _vp]),
     "b200_dcn_f16": (_i, [_vp] * 7 + [_i] * 16 + [_vp, _vp]),
+    "b200_dcn_f16_chw2": (_i, [_vp] * 7 + [_i] * 16 + [_vp, _vp]),
+    "b200_dcn_f16_chw2_workspace_size": (ctypes.c_size_t, [_i] * 15),
     "b200_grid_sample_f32": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
     "b200_grid_sample_f16": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
     "b200_grid_sample_f16_chw2": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),

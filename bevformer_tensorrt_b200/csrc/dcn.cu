@@ -172,6 +172,36 @@ static int dcn_i8_unfused(const int8_t *input, float scale_i, const int8_t *weig
   return check_launch();
 }
 
+// ---- FP16 kCHW2 (what the …TRT2 plugin negotiates for input, offset and weight, …Conv2dPlugin.cpp:222-250): TensorRT's
+// [N, ceil(C/2), H, W, 2] packets are unpacked into plain NCHW in the workspace, then the normal FP16 path runs.
+__global__ void dcn_chw2_to_nchw_kernel(const __half2 *in, __half *out, int C, long long plane, long long total) {
+  // total = N * ceil(C/2) * plane packets
+  const int C2 = (C + 1) / 2;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = idx % plane, nc2 = idx / plane;
+    const long long n = nc2 / C2, c2 = nc2 % C2;
+    const __half2 v = in[idx];
+    out[(n * C + 2 * c2) * plane + pix] = __low2half(v);
+    if (2 * c2 + 1 < C) out[(n * C + 2 * c2 + 1) * plane + pix] = __high2half(v);
+  }
+}
+
+struct DcnChw2Plan {
+  size_t x, off, w, rest, total;
+};
+static DcnChw2Plan dcn_chw2_plan(int batch, int channels, int height, int width, int channels_out, int kh, int kw, int Ho,
+                                 int Wo, int group, int dg, size_t inner) {
+  DcnChw2Plan p{};
+  size_t o = 0;
+  p.x = o, o += align256(static_cast<size_t>(batch) * channels * height * width * 2);
+  p.off = o, o += align256(static_cast<size_t>(batch) * dg * 2 * kh * kw * Ho * Wo * 2);
+  p.w = o, o += align256(static_cast<size_t>(channels_out) * (channels / group) * kh * kw * 2);
+  p.rest = o, o += inner;
+  p.total = o;
+  return p;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -291,6 +321,60 @@ int b200_dcn_f16(const void *input, const void *weight, const void *bias, const 
                              channels, height, width, channels_out, kernel_w, kernel_h, stride_w, stride_h, pad_w,
                              pad_h, dilation_w, dilation_h, group, deformable_group,
                              static_cast<cudaStream_t>(stream));
+}
+
+size_t b200_dcn_f16_chw2_workspace_size(int batch, int channels, int height, int width, int channels_out, int kernel_w,
+                                        int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                                        int dilation_h, int group, int deformable_group) {
+  if (stride_h <= 0 || stride_w <= 0 || group <= 0 || deformable_group <= 0) return 0;
+  const int Ho = (height + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
+  const int Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
+  if (Ho <= 0 || Wo <= 0 || batch <= 0 || channels <= 0 || channels_out <= 0) return 0;
+  const size_t inner = b200_dcn_workspace_size(1, batch, channels, height, width, kernel_w, kernel_h, stride_w, stride_h,
+                                               pad_w, pad_h, dilation_w, dilation_h);
+  return dcn_chw2_plan(batch, channels, height, width, channels_out, kernel_h, kernel_w, Ho, Wo, group, deformable_group,
+                       inner).total;
+}
+
+int b200_dcn_f16_chw2(const void *input, const void *weight, const void *bias, const void *offset, const void *mask,
+                      void *output, void *workspace, int batch, int channels, int height, int width, int channels_out,
+                      int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                      int dilation_h, int group, int deformable_group, int im2col_step, void *cublas_handle, void *stream) {
+  (void)im2col_step;
+  (void)cublas_handle;
+  if (!input || !weight || !offset || !mask || !output || !workspace) return B200_ERR_BAD_PARAM;
+  if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || channels_out <= 0 || kernel_w <= 0 || kernel_h <= 0 ||
+      stride_w <= 0 || stride_h <= 0 || dilation_w <= 0 || dilation_h <= 0 || group <= 0 || deformable_group <= 0)
+    return B200_ERR_BAD_PARAM;
+  if (channels % group || channels_out % group || channels % deformable_group) return B200_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return B200_ERR_UNSUPPORTED;
+  const int Ho = (height + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
+  const int Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
+  if (Ho <= 0 || Wo <= 0) return B200_ERR_BAD_PARAM;
+  const size_t inner = b200_dcn_workspace_size(1, batch, channels, height, width, kernel_w, kernel_h, stride_w, stride_h,
+                                               pad_w, pad_h, dilation_w, dilation_h);
+  const DcnChw2Plan pl = dcn_chw2_plan(batch, channels, height, width, channels_out, kernel_h, kernel_w, Ho, Wo, group,
+                                       deformable_group, inner);
+  char *ws = static_cast<char *>(workspace);
+  __half *x = reinterpret_cast<__half *>(ws + pl.x), *off = reinterpret_cast<__half *>(ws + pl.off);
+  __half *w = reinterpret_cast<__half *>(ws + pl.w);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long plane = static_cast<long long>(height) * width, kk = static_cast<long long>(kernel_h) * kernel_w;
+  const int coff = deformable_group * 2 * static_cast<int>(kk), cw = channels / group;
+  const long long nx = static_cast<long long>(batch) * ((channels + 1) / 2) * plane;
+  const long long no = static_cast<long long>(batch) * ((coff + 1) / 2) * Ho * Wo;
+  const long long nw = static_cast<long long>(channels_out) * ((cw + 1) / 2) * kk;
+  dcn_chw2_to_nchw_kernel<<<grid_for(nx), 256, 0, s>>>(static_cast<const __half2 *>(input), x, channels, plane, nx);
+  dcn_chw2_to_nchw_kernel<<<grid_for(no), 256, 0, s>>>(static_cast<const __half2 *>(offset), off, coff,
+                                                      static_cast<long long>(Ho) * Wo, no);
+  dcn_chw2_to_nchw_kernel<<<grid_for(nw), 256, 0, s>>>(static_cast<const __half2 *>(weight), w, cw, kk, nw);
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  const int st = check_launch();
+  if (st != B200_OK) return st;
+  return dcn_forward<__half>(x, w, static_cast<const __half *>(bias), off, static_cast<const __half *>(mask),
+                             static_cast<__half *>(output), ws + pl.rest, batch, channels, height, width, channels_out,
+                             kernel_w, kernel_h, stride_w, stride_h, pad_w, pad_h, dilation_w, dilation_h, group,
+                             deformable_group, s);
 }
 
 }  // extern "C"

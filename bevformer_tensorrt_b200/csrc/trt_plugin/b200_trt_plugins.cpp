@@ -77,23 +77,16 @@ class Plugin final : public IPluginV2DynamicExt {
       return d.type == img.type;
     }
     const PluginTensorDesc &d = io[pos], &x = io[0];
-    if (op_ == Op::kGridSampler3D) {  // 5-D: fp32 / fp16 linear only (gridSamplerPlugin.cpp:187-189)
-      if (pos != 0) return d.type == x.type && d.format == x.format;
-      return (d.type == DataType::kFLOAT || d.type == DataType::kHALF) && d.format == TensorFormat::kLINEAR;
-    }
-    if (op_ == Op::kGridSampler2D) {  // gridSamplerPlugin.cpp:168-194: …TRT2 negotiates kCHW2 for FP16; INT8 is kCHW4
-      if (pos != 0) return d.type == x.type && d.format == x.format;
-      if (d.type == DataType::kINT8) return d.format == TensorFormat::kCHW4;
-      if (d.type == DataType::kHALF) return d.format == (v2_ ? TensorFormat::kCHW2 : TensorFormat::kLINEAR);
-      return d.type == DataType::kFLOAT && d.format == TensorFormat::kLINEAR;
-    }
-    // DCN (…Conv2dPlugin.cpp:213-250): fp32 / fp16 linear everywhere; INT8: input and weight kCHW4, offset / mask /
-    // output int8 linear, bias fp32 or fp16 linear. (The reference's kCHW2 FP16 variant is not offered: TensorRT
-    // reformats to linear in front of the plugin.)
+    if (op_ == Op::kGridSampler2D || op_ == Op::kGridSampler3D)  // gridSamplerPlugin.cpp:168-194
+      return b200_grid_sampler_supports_format(pos, reinterpret_cast<const b200_tensor_desc *>(io), nbIn, nbOut, v2_) != 0;
+    // DCN (…Conv2dPlugin.cpp:213-250). …TRT: fp32 / fp16 linear everywhere. …TRT2 (use_h2): FP16 input, offset and weight
+    // as kCHW2 packets, mask / bias / output linear. INT8 (both): input and weight kCHW4, offset / mask / output int8
+    // linear, bias fp32 or fp16 linear.
     const bool int8_ok = x.dims.d[1] % 4 == 0 && (io[nbIn].dims.d[1] / a_.groups) % 4 == 0;
     if (pos == 0) {
       if (d.type == DataType::kINT8) return d.format == TensorFormat::kCHW4 && int8_ok;
-      return (d.type == DataType::kFLOAT || d.type == DataType::kHALF) && d.format == TensorFormat::kLINEAR;
+      if (d.type == DataType::kHALF) return d.format == (v2_ ? TensorFormat::kCHW2 : TensorFormat::kLINEAR);
+      return d.type == DataType::kFLOAT && d.format == TensorFormat::kLINEAR;
     }
     if (x.type == DataType::kINT8) {
       if (nbIn == 5 && pos == 4)
@@ -102,7 +95,8 @@ class Plugin final : public IPluginV2DynamicExt {
       return d.type == DataType::kINT8 && d.format == TensorFormat::kLINEAR;  // offset, mask, output
     }
     (void)nbOut;
-    return d.type == x.type && d.format == TensorFormat::kLINEAR;
+    if ((nbIn == 5 && pos == 4) || pos == nbIn || pos == 2) return d.type == x.type && d.format == TensorFormat::kLINEAR;
+    return d.type == x.type && d.format == x.format;  // offset, weight follow the input's format (…Conv2dPlugin.cpp:246-249)
   }
   void configurePlugin(const DynamicPluginTensorDesc *, int32_t nbIn, const DynamicPluginTensorDesc *, int32_t) noexcept override {
     nb_inputs_ = nbIn;  // DCN: 4 inputs without bias, 5 with (…Conv2dPlugin.cpp:297-299)
@@ -111,12 +105,8 @@ class Plugin final : public IPluginV2DynamicExt {
     if (op_ == Op::kMSDA)  // the reference asks for 0 (…Plugin.cpp:64-69); the v2 kernels want room for the packed value stack
       return b200_msda_enqueue_workspace_size(reinterpret_cast<const b200_tensor_desc *>(in));
     if (op_ != Op::kDCN) return 0;  // grid sampler / rotate need none
-    const Dims &x = in[0].dims, &w = in[3].dims;
-    if (in[0].type == DataType::kINT8)
-      return b200_dcn_i8_workspace_size(x.d[0], x.d[1], x.d[2], x.d[3], w.d[0], w.d[3], w.d[2], a_.stride[1], a_.stride[0],
-                                        a_.pad[1], a_.pad[0], a_.dil[1], a_.dil[0], a_.groups, a_.deform_groups);
-    return b200_dcn_workspace_size(in[0].type == DataType::kHALF, x.d[0], x.d[1], x.d[2], x.d[3], w.d[3], w.d[2],
-                                   a_.stride[1], a_.stride[0], a_.pad[1], a_.pad[0], a_.dil[1], a_.dil[0]);
+    return b200_dcn_enqueue_workspace_size(reinterpret_cast<const b200_tensor_desc *>(in), a_.stride, a_.pad, a_.dil,
+                                           a_.groups, a_.deform_groups);
   }
   int32_t enqueue(const PluginTensorDesc *in, const PluginTensorDesc *out, const void *const *inputs, void *const *outputs,
                   void *workspace, cudaStream_t stream) noexcept override {
@@ -137,50 +127,14 @@ class Plugin final : public IPluginV2DynamicExt {
                               in[0].scale, inputs[1], inputs[2], in[1].type == DataType::kHALF, dims, a_.interp, stream);
       return 1;
     }
-    if (op_ == Op::kGridSampler3D) {
-      int id[5], gd[5], od[5];
-      for (int i = 0; i < 5; ++i) id[i] = in[0].dims.d[i], gd[i] = in[1].dims.d[i], od[i] = out[0].dims.d[i];
-      if (in[0].type == DataType::kFLOAT)
-        return b200_grid_sample_f32(static_cast<float *>(outputs[0]), static_cast<const float *>(inputs[0]),
-                                    static_cast<const float *>(inputs[1]), od, id, gd, 5, a_.interp, a_.padding, a_.align,
-                                    stream);
-      return b200_grid_sample_f16(outputs[0], inputs[0], inputs[1], od, id, gd, 5, a_.interp, a_.padding, a_.align, stream);
-    }
-    if (op_ == Op::kGridSampler2D) {
-      int id[4], gd[4], od[4];
-      for (int i = 0; i < 4; ++i) id[i] = in[0].dims.d[i], gd[i] = in[1].dims.d[i], od[i] = out[0].dims.d[i];
-      if (in[0].type == DataType::kFLOAT)
-        return b200_grid_sample_f32(static_cast<float *>(outputs[0]), static_cast<const float *>(inputs[0]),
-                                    static_cast<const float *>(inputs[1]), od, id, gd, 4, a_.interp, a_.padding, a_.align,
-                                    stream);
-      if (in[0].type == DataType::kINT8)  // kCHW4, scales from the tensor descriptors (gridSamplerPlugin.cpp:114-116)
-        return b200_grid_sample_i8_chw4(static_cast<int8_t *>(outputs[0]), out[0].scale,
-                                        static_cast<const int8_t *>(inputs[0]), in[0].scale,
-                                        static_cast<const int8_t *>(inputs[1]), in[1].scale, od, id, gd, 4, a_.interp,
-                                        a_.padding, a_.align, stream);
-      if (in[0].format == TensorFormat::kCHW2)
-        return b200_grid_sample_f16_chw2(outputs[0], inputs[0], inputs[1], od, id, gd, 4, a_.interp, a_.padding, a_.align,
-                                         stream);
-      return b200_grid_sample_f16(outputs[0], inputs[0], inputs[1], od, id, gd, 4, a_.interp, a_.padding, a_.align, stream);
-    }
-    const Dims &x = in[0].dims, &w = in[3].dims;  // inputs: x, offset, mask, weight[, bias] (…Conv2dPlugin.cpp:117-160)
-    const void *bias = nb_inputs_ == 5 ? inputs[4] : nullptr;
-    if (in[0].type == DataType::kINT8)  // scales: input, weight, offset, mask, output (…Conv2dPlugin.cpp:161-199)
-      return b200_dcn_i8(static_cast<const int8_t *>(inputs[0]), in[0].scale, static_cast<const int8_t *>(inputs[3]),
-                         in[3].scale, bias, nb_inputs_ == 5 && in[4].type == DataType::kHALF,
-                         static_cast<const int8_t *>(inputs[1]), in[1].scale, static_cast<const int8_t *>(inputs[2]),
-                         in[2].scale, static_cast<int8_t *>(outputs[0]), out[0].scale, workspace, x.d[0], x.d[1], x.d[2],
-                         x.d[3], w.d[0], w.d[3], w.d[2], a_.stride[1], a_.stride[0], a_.pad[1], a_.pad[0], a_.dil[1],
-                         a_.dil[0], a_.groups, a_.deform_groups, x.d[0], nullptr, stream);
-    if (in[0].type == DataType::kFLOAT)
-      return b200_dcn_f32(static_cast<const float *>(inputs[0]), static_cast<const float *>(inputs[3]),
-                          static_cast<const float *>(bias), static_cast<const float *>(inputs[1]),
-                          static_cast<const float *>(inputs[2]), static_cast<float *>(outputs[0]), workspace, x.d[0],
-                          x.d[1], x.d[2], x.d[3], w.d[0], w.d[3], w.d[2], a_.stride[1], a_.stride[0], a_.pad[1], a_.pad[0],
-                          a_.dil[1], a_.dil[0], a_.groups, a_.deform_groups, x.d[0], nullptr, stream);
-    return b200_dcn_f16(inputs[0], inputs[3], bias, inputs[1], inputs[2], outputs[0], workspace, x.d[0], x.d[1], x.d[2],
-                        x.d[3], w.d[0], w.d[3], w.d[2], a_.stride[1], a_.stride[0], a_.pad[1], a_.pad[0], a_.dil[1],
-                        a_.dil[0], a_.groups, a_.deform_groups, x.d[0], nullptr, stream);
+    if (op_ == Op::kGridSampler2D || op_ == Op::kGridSampler3D)
+      return b200_grid_sampler_enqueue(reinterpret_cast<const b200_tensor_desc *>(in),
+                                       reinterpret_cast<const b200_tensor_desc *>(out), inputs, outputs, workspace, stream,
+                                       a_.interp, a_.padding, a_.align);
+    // DCN: inputs x, offset, mask, weight[, bias]; attribute element [0] -> *_w slot, [1] -> *_h, as the reference's call
+    return b200_dcn_enqueue(reinterpret_cast<const b200_tensor_desc *>(in), reinterpret_cast<const b200_tensor_desc *>(out),
+                            inputs, outputs, workspace, stream, nb_inputs_, a_.stride, a_.pad, a_.dil, a_.groups,
+                            a_.deform_groups);
   }
   // ---- IPluginV2Ext / IPluginV2
   DataType getOutputDataType(int32_t, const DataType *types, int32_t) const noexcept override { return types[0]; }

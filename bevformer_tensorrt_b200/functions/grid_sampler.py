@@ -4,8 +4,9 @@
 [-10, 10] range (Appendix B of SURVEY.md).
 
 forward() calls the sm_100a kernels through the C ABI (the reference's forward is ``aten.grid_sampler`` on
-``grid.permute(...)/10``, :28-32). The reference binding also defines a backward (:39-55) for QAT; this port is the
-inference path only, so gradients are not provided.
+``grid.permute(...)/10``, :28-32). backward() is the reference's, statement for statement (:39-55 / :93-109): ATen's
+``grid_sampler_{2,3}d_backward`` on the saved ``(input, grid/10)``, the grid gradient permuted back and scaled by 10 — it
+exists for quantisation-aware training only and is not on the inference path.
 
 TensorRT-format entries: ``grid_sampler_chw2`` (FP16 kCHW2, what the …TRT2 plugin negotiates, gridSamplerPlugin.cpp:
 171-186) and ``grid_sampler_int8`` (INT8 kCHW4 with per-tensor scales) take tensors already in those packed layouts;
@@ -69,7 +70,20 @@ def _make(op_name):
 
         @staticmethod
         def forward(ctx, input, grid, interpolation_mode, padding_mode, align_corners):
+            if input.requires_grad or grid.requires_grad:
+                perm = (0, 2, 3, 1) if grid.dim() == 4 else (0, 2, 3, 4, 1)
+                ctx.save_for_backward(input, grid.permute(*perm) / 10)
+                ctx.interpolation_mode, ctx.padding_mode, ctx.align_corners = interpolation_mode, padding_mode, align_corners
             return _forward(input, grid, interpolation_mode, padding_mode, align_corners)
+
+        @staticmethod
+        def backward(ctx, grad_outputs):
+            input, grid = ctx.saved_tensors
+            bwd = torch.ops.aten.grid_sampler_2d_backward if grid.dim() == 4 else torch.ops.aten.grid_sampler_3d_backward
+            input_grad, grid_grad = bwd(grad_outputs.contiguous(), input, grid.to(input.dtype), ctx.interpolation_mode,
+                                        ctx.padding_mode, ctx.align_corners, [True, True])
+            back = (0, 3, 1, 2) if grid.dim() == 4 else (0, 4, 1, 2, 3)
+            return input_grad, grid_grad.permute(*back) * 10, None, None, None
 
     _GridSampler.__name__ = "_" + op_name
     return _GridSampler

@@ -147,6 +147,32 @@ def modulated_deformable_conv2d2(input, offset, mask, weight, bias=None, stride=
                                                      groups, deform_groups)  # fmt: skip
 
 
+def modulated_deformable_conv2d_chw2(input_chw2, offset_chw2, mask, weight_chw2, bias, channels, stride=1, padding=0,
+                                     dilation=1, groups=1, deform_groups=1):
+    """FP16 in TensorRT's kCHW2 packets, the format table of the …TRT2 plugin (…Conv2dPlugin.cpp:222-250): ``input_chw2``
+    [N, ceil(C/2), H, W, 2], ``offset_chw2`` [N, ceil(dg*2*kh*kw/2), Ho, Wo, 2], ``weight_chw2`` [Co, ceil(C/g/2), kh, kw, 2]
+    (``functions.grid_sampler.pack_chw(x, 2)``); ``mask`` / ``bias`` plain FP16. Returns plain NCHW FP16."""
+    assert input_chw2.is_cuda and input_chw2.dtype == torch.float16 and input_chw2.shape[-1] == 2
+    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
+    n, _, h, w, _ = input_chw2.shape
+    co, _, kh, kw, _ = weight_chw2.shape
+    ho = (h + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    wo = (w + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    lib = _lib.load()
+    ws_bytes = lib.b200_dcn_f16_chw2_workspace_size(n, channels, h, w, co, kw, kh, sw, sh, pw, ph, dw, dh, groups, deform_groups)
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=input_chw2.device)
+    out = torch.empty(n, co, ho, wo, dtype=torch.float16, device=input_chw2.device)
+    x, off, msk, wt = (t.contiguous() for t in (input_chw2, offset_chw2, mask.half(), weight_chw2))
+    bias_t = bias.half().contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        st = lib.b200_dcn_f16_chw2(x.data_ptr(), wt.data_ptr(), bias_t.data_ptr() if bias_t is not None else None,
+                                   off.data_ptr(), msk.data_ptr(), out.data_ptr(), workspace.data_ptr(), n, channels, h, w,
+                                   co, kw, kh, sw, sh, pw, ph, dw, dh, groups, deform_groups, min(n, 32), None,
+                                   _lib.current_stream_ptr())  # fmt: skip
+    _lib.check("b200_dcn_f16_chw2", st)
+    return out
+
+
 def modulated_deformable_conv2d_int8(input_chw4, scale_i, offset_q, scale_off, mask_q, scale_mask, weight_chw4, scale_w,
                                      bias, scale_o, channels, stride=1, padding=0, dilation=1, groups=1, deform_groups=1):
     """INT8 flavour of the plugin (…Conv2dPlugin.cpp:117-199 / launcher …Conv2dKernel.h:21-29): ``input_chw4`` int8

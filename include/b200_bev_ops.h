@@ -322,7 +322,8 @@ int b200_bev_point_sampling(const void *reference_points, const double *pc_range
  *   output [batch, channels_out, Ho, Wo],  Ho = (height + 2*pad_h - (dilation_h*(kernel_h-1)+1))/stride_h + 1
  *   workspace: device scratch of b200_dcn_workspace_size(...) bytes (the plugin's getWorkspaceSize,
  *              …Conv2dPlugin.cpp:73-115, should return this instead of its single-image column size).
- *   cublas_handle: a cublasHandle_t (as TensorRT passes through attachToContext, …Conv2dPlugin.cpp:286-290) or NULL
+ *   cublas_handle: the reference's slot (…Conv2dPlugin.cpp:286-290), kept for signature compatibility and IGNORED — no
+ *   library GEMM runs on this path (dcn_fused.cu: tcgen05 implicit GEMM; dcn_generic.cu: fused FP32-pipe implicit GEMM)
  *              to use the library's own handle.
  * Argument order = the reference launcher ModulatedDeformConvForwardCUDAKernel<T> (…Conv2dKernel.h:11-19).
  * FP16 accumulates the GEMM in FP32 (the reference accumulates in FP16, common/cuda_helper.cu:101-110).
@@ -332,7 +333,8 @@ size_t b200_dcn_workspace_size(int dtype /* 0 f32, 1 f16 */, int batch, int chan
                                int dilation_w, int dilation_h);
 
 /* FP16 runs as one fused implicit GEMM on tcgen05 tensor cores (csrc/dcn_fused.cu) when groups == deformable_groups == 1,
- * channels % 64 == 0 and channels_out in {128, 256, 512}; otherwise (and for FP32) as gather + cuBLAS GEMM.
+ * channels % 64 == 0 and channels_out in {128, 256, 512}; otherwise (and for FP32) as the generic fused implicit GEMM on
+ * the FP32 pipe (csrc/dcn_generic.cu: any groups / deformable groups / kernel size). No library GEMM on either path.
  * b200_dcn_set_fused(0) forces the second path (A/B measurements), a negative argument only queries; returns the
  * previous setting. */
 int b200_dcn_set_fused(int enabled);
@@ -379,6 +381,39 @@ int b200_dcn_f16(const void *input, const void *weight, const void *bias, const 
                  void *output, void *workspace, int batch, int channels, int height, int width, int channels_out,
                  int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
                  int dilation_h, int group, int deformable_group, int im2col_step, void *cublas_handle, void *stream);
+
+/* FP16 in TensorRT's kCHW2 packets — what the …TRT2 plugin negotiates (…Conv2dPlugin.cpp:222-250: input, offset and
+ * weight as __half2 packets [N, ceil(C/2), H, W, 2]; mask, bias and output linear). Replaces
+ * ModulatedDeformConvForwardCUDAKernel<__half2> (…Conv2dKernel.cu:828-895). The packets are unpacked into the workspace
+ * (sized by b200_dcn_f16_chw2_workspace_size) and the FP16 path above runs. */
+size_t b200_dcn_f16_chw2_workspace_size(int batch, int channels, int height, int width, int channels_out, int kernel_w,
+                                        int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                                        int dilation_h, int group, int deformable_group);
+int b200_dcn_f16_chw2(const void *input, const void *weight, const void *bias, const void *offset, const void *mask,
+                      void *output, void *workspace, int batch, int channels, int height, int width, int channels_out,
+                      int kernel_w, int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,
+                      int dilation_h, int group, int deformable_group, int im2col_step, void *cublas_handle, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Plugin-shaped entries for the other two plugins (the argument list of IPluginV2DynamicExt::enqueue plus the plugin's
+ * attributes), so that a TensorRT shell — or a test — forwards verbatim, as b200_msda_enqueue does for MSDA.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* GridSampler{2D,3D}TRT[2] (gridSamplerPlugin.cpp:110-155): inputs = input, grid; dispatch on the input descriptor's
+ * type / format (fp32, fp16 linear, fp16 kCHW2, int8 kCHW4 with the descriptors' scales). Needs no workspace. */
+int b200_grid_sampler_enqueue(const b200_tensor_desc *input_desc, const b200_tensor_desc *output_desc,
+                              const void *const *inputs, void *const *outputs, void *workspace, void *stream,
+                              int interpolation_mode, int padding_mode, int align_corners);
+/* supportsFormatCombination mirror (gridSamplerPlugin.cpp:168-194): in_out = {input, grid, output}. */
+int b200_grid_sampler_supports_format(int pos, const b200_tensor_desc *in_out, int nb_inputs, int nb_outputs, int use_h2);
+
+/* ModulatedDeformableConv2dTRT[2] (…Conv2dPlugin.cpp:117-199): inputs = x, offset, mask, weight[, bias] (nb_inputs 4 or
+ * 5). stride / padding / dilation = the plugin attributes' int[2]; element [0] is handed to the launcher's *_w slot and
+ * [1] to *_h exactly as the reference's enqueue does (:152-160). Dispatch: fp32, fp16 linear, fp16 kCHW2, int8 kCHW4. */
+size_t b200_dcn_enqueue_workspace_size(const b200_tensor_desc *input_desc, const int32_t *stride, const int32_t *padding,
+                                       const int32_t *dilation, int groups, int deform_groups);
+int b200_dcn_enqueue(const b200_tensor_desc *input_desc, const b200_tensor_desc *output_desc, const void *const *inputs,
+                     void *const *outputs, void *workspace, void *stream, int nb_inputs, const int32_t *stride,
+                     const int32_t *padding, const int32_t *dilation, int groups, int deform_groups);
 
 #ifdef __cplusplus
 } /* extern "C" */

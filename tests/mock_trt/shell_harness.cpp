@@ -180,6 +180,18 @@ int main() {
     for (int pos = 0; pos < 6; ++pos) CHECK(c->supportsFormatCombination(pos, cf, 5, 1));
     cf[1].type = F;
     CHECK(!c->supportsFormatCombination(1, cf, 5, 1));
+    // …TRT2 (use_h2, :222-250): FP16 input, offset and weight as kCHW2 packets; mask, bias and output stay linear
+    IPluginV2DynamicExt *c2 = make(Op::kDCN, true);
+    PluginTensorDesc ch[6] = {desc(H, CHW2, {2, 64, 8, 8}), desc(H, CHW2, {2, 18, 8, 8}), desc(H, LIN, {2, 9, 8, 8}),
+                              desc(H, CHW2, {128, 64, 3, 3}), desc(H, LIN, {128}), desc(H, LIN, {2, 128, 8, 8})};
+    for (int pos = 0; pos < 6; ++pos) CHECK(c2->supportsFormatCombination(pos, ch, 5, 1));
+    ch[0].format = LIN;
+    CHECK(!c2->supportsFormatCombination(0, ch, 5, 1));  // …TRT2 does not take linear FP16 input
+    ch[0].format = CHW2, ch[2].format = CHW2;
+    CHECK(!c2->supportsFormatCombination(2, ch, 5, 1));  // mask is linear
+    ch[2].format = LIN, ch[5].format = CHW2;
+    CHECK(!c2->supportsFormatCombination(5, ch, 5, 1));  // output is linear
+    CHECK(!c->supportsFormatCombination(0, ch, 5, 1));    // …TRT (not 2) does not take kCHW2
 
     // MSDA goes through b200_msda_supports_format (…Plugin.cpp:148-189): shapes are int32, everything linear
     IPluginV2DynamicExt *m = make(Op::kMSDA, false);
@@ -200,6 +212,10 @@ int main() {
                                                      {"padding", one, PluginFieldType::kINT32, 2},
                                                      {"dilation", one, PluginFieldType::kINT32, 2}});
     CHECK(c->getWorkspaceSize(in, 5, &out, 1) == b200_dcn_workspace_size(1, 6, 256, 58, 100, 3, 3, 1, 1, 1, 1, 1, 1));
+    in[0].format = CHW2;
+    CHECK(c->getWorkspaceSize(in, 5, &out, 1) ==
+          b200_dcn_f16_chw2_workspace_size(6, 256, 58, 100, 256, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1));
+    in[0].format = LIN;
     in[0].type = I8;
     CHECK(c->getWorkspaceSize(in, 5, &out, 1) ==
           b200_dcn_i8_workspace_size(6, 256, 58, 100, 256, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1));

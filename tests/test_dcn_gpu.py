@@ -78,7 +78,9 @@ def test_packed_weight_cache_is_tied_to_the_weight_object():
     nn.Parameter they were packed from; temporaries are packed per call."""
     import gc
 
-    from bevformer_tensorrt_b200.functions import modulated_deformable_conv2d as mod
+    import importlib
+
+    mod = importlib.import_module("bevformer_tensorrt_b200.functions.modulated_deformable_conv2d")
 
     x, off, mask, w, b, kw = make_dcn_inputs("fused_co128", dtype=torch.float16)
     xs = [t.cuda() for t in (x, off, mask)]
@@ -101,6 +103,20 @@ def test_packed_weight_cache_is_tied_to_the_weight_object():
     assert torch.equal(out2, call((w * 3).cuda())) and not torch.equal(out2, out1)
 
 
+@pytest.mark.parametrize("case", ["k3_s1_p1_g2_dg2", "fused_co128", "k3x5_s1_p1_g1_dg1"])
+def test_fp16_chw2_entry_equals_linear_entry(case):
+    """kCHW2 packets (…TRT2 format table, …Conv2dPlugin.cpp:222-250) in, the same bits out as the linear FP16 entry."""
+    from bevformer_tensorrt_b200.functions.grid_sampler import pack_chw
+    from bevformer_tensorrt_b200.functions.modulated_deformable_conv2d import modulated_deformable_conv2d_chw2
+
+    x, off, mask, w, b, kw = make_dcn_inputs(case, dtype=torch.float16)
+    want = _call(bt.modulated_deformable_conv2d, x, off, mask, w, b, kw)
+    got = modulated_deformable_conv2d_chw2(pack_chw(x, 2).cuda(), pack_chw(off, 2).cuda(), mask.cuda(), pack_chw(w, 2).cuda(),
+                                           b.cuda(), x.shape[1], kw["stride"], kw["padding"], kw["dilation"], kw["groups"],
+                                           kw["deform_groups"])  # fmt: skip
+    assert torch.equal(got, want)
+
+
 def test_dcnv2p_layer_runs_the_plugin_op():
     """DCNv2P / DCNv2P2 (det2trt/models/modules/cnn/dcn.py:31-164) at the reference op test's structure: groups = 2,
     deform_groups = 2 (test_modulated_deformable_conv2d.py:6-11,37): conv_offset -> (offset, sigmoid(mask)) -> op."""
@@ -117,13 +133,13 @@ def test_dcnv2p_layer_runs_the_plugin_op():
         got = layer(x)
         o = layer.conv_offset(x)
         o1, o2, m = torch.chunk(o, 3, dim=1)
-        want = odcn.modulated_deformable_conv2d(x.float().cpu().numpy(), torch.cat((o1, o2), 1).float().cpu().numpy(),
-                                                torch.sigmoid(m).float().cpu().numpy(), layer.weight.float().cpu().numpy(),
-                                                layer.bias.float().cpu().numpy(), stride=1, padding=1, dilation=1, groups=2,
-                                                deform_groups=2)  # fmt: skip
+        npf = lambda t_: t_.detach().float().cpu().numpy()  # noqa: E731
+        want = odcn.modulated_deformable_conv2d(npf(x), npf(torch.cat((o1, o2), 1)), npf(torch.sigmoid(m)),
+                                                npf(layer.weight), npf(layer.bias), stride=1, padding=1, dilation=1,
+                                                groups=2, deform_groups=2)  # fmt: skip
         assert got.shape == (2, 12, 13, 17) and got.dtype == dt
         tol = 1e-4 if dt == torch.float32 else 5e-3
-        assert np.abs(got.float().cpu().numpy() - want).max() < tol * max(1.0, np.abs(want).max())
+        assert np.abs(npf(got) - want).max() < tol * max(1.0, np.abs(want).max())
 
 
 @pytest.mark.parametrize("case", ["k3_s1_p1_g2_dg2", "backbone_like", "k3_s2_p1_g1_dg1"])
