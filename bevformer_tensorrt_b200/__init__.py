@@ -41,6 +41,7 @@ from .functions import (  # noqa: E402
     rotate_hwc,
     rotate_int8,
     set_msda_v2,
+    set_msda_f16_path,
 )
 
 from .host_pipeline import HostMSDA, empty_pinned  # noqa: E402
@@ -70,5 +71,6 @@ __all__ = [
     "rotate_hwc",
     "rotate_int8",
     "set_msda_v2",
+    "set_msda_f16_path",
 ]
 __version__ = "0.1.0"

@@ -57,6 +57,9 @@ SIGNATURES = {
     "b200_msda_i8_trace": (_i, [_vp, _f, _vp, _vp, _i, _vp, _f, _vp, _f] + _MSDA_DIMS + [_vp, _f, _vp, _vp]),
     "b200_msda_debug_indices": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200_msda_set_f16_mode": (_i, [_i]),
+    "b200_msda_set_f16_path": (_i, [_i]),
+    "b200_msda_set_resident_bytes": (_i, [_i]),
+    "b200_msda_set_i8_resident_bytes": (_i, [_i]),
     "b200_msda_enqueue": (_i, [ctypes.POINTER(TensorDesc), ctypes.POINTER(TensorDesc), ctypes.POINTER(_vp),
                                ctypes.POINTER(_vp), _vp, _vp, _i]),
     "b200_msda_enqueue_workspace_size": (ctypes.c_size_t, [ctypes.POINTER(TensorDesc)]),

@@ -32,6 +32,14 @@ constexpr int kMinBlocks = B200_MSDA_MIN_BLOCKS;  // 3: registers capped at 85, 
 // exact by default; 1 = mixed FHFMA (opt-in, see Io<__half, 1>). Atomic: enqueue may be called from several host
 // threads (SURVEY §8(b) threading), the setter from another.
 static std::atomic<int> g_f16_mode{0};
+// FP16 kernel selection: 1 (default) = resident-tail kernel (msda_res.cu) where its envelope holds, 0 = this file's
+// round-1 gather kernel everywhere.
+static std::atomic<int> g_f16_path{0};
+static std::atomic<int> g_res_cap_bytes{128 * 1024};
+
+// msda_res.cu
+int msda_res_f16(const void *value, const int32_t *shapes, const void *ref, const void *off, const void *logits, int B, int S,
+                 int M, int C, int L, int Q, int P, int G, void *out, int4 *trace, int cap_bytes, cudaStream_t s);
 
 struct MsdaParams {
   const void *value;
@@ -737,6 +745,8 @@ using namespace b200;
 extern "C" {
 
 int b200_msda_set_f16_mode(int mode) { return g_f16_mode.exchange(mode ? 1 : 0); }
+int b200_msda_set_f16_path(int path) { return g_f16_path.exchange(path ? 1 : 0); }
+int b200_msda_set_resident_bytes(int bytes) { return g_res_cap_bytes.exchange(bytes < 8192 ? 8192 : (bytes > 200 * 1024 ? 200 * 1024 : bytes)); }
 
 int b200_msda_f32(const float *value, const int32_t *spatial_shapes, const float *reference_points,
                   const float *sampling_offsets, const float *attn_weight, int batch, int spatial_size, int num_heads,
@@ -755,6 +765,12 @@ int b200_msda_f16(const void *value, const int32_t *spatial_shapes, const void *
   const MsdaParams p = make_params(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch,
                                    spatial_size, num_heads, channels, num_levels, num_query, num_point,
                                    points_per_group, out);
+  if (g_f16_path.load(std::memory_order_relaxed) && !g_f16_mode.load(std::memory_order_relaxed) && validate(p) == B200_OK) {
+    const int st = msda_res_f16(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch, spatial_size,
+                                num_heads, channels, num_levels, num_query, num_point, points_per_group, out, nullptr,
+                                g_res_cap_bytes.load(std::memory_order_relaxed), static_cast<cudaStream_t>(stream));
+    if (st != B200_ERR_UNSUPPORTED) return st;
+  }
   return g_f16_mode.load(std::memory_order_relaxed) ? dispatch<__half, __half, 1>(p, static_cast<cudaStream_t>(stream))
                                                    : dispatch<__half, __half, 0>(p, static_cast<cudaStream_t>(stream));
 }
@@ -856,6 +872,12 @@ int b200_msda_f16_trace(const void *value, const int32_t *spatial_shapes, const 
   const int st = trace_prologue(records, p.items * num_levels * num_point, static_cast<cudaStream_t>(stream));
   if (st != B200_OK) return st;
   p.trace = reinterpret_cast<int4 *>(records);
+  if (g_f16_path.load(std::memory_order_relaxed) && validate(p) == B200_OK) {  // the kernel the plugin op runs is the one traced
+    const int st2 = msda_res_f16(value, spatial_shapes, reference_points, sampling_offsets, attn_weight, batch, spatial_size,
+                                 num_heads, channels, num_levels, num_query, num_point, points_per_group, out, p.trace,
+                                 g_res_cap_bytes.load(std::memory_order_relaxed), static_cast<cudaStream_t>(stream));
+    if (st2 != B200_ERR_UNSUPPORTED) return st2;
+  }
   return dispatch<__half, __half, 0>(p, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,7 +1,7 @@
 // msda_v2.cu — packed-layout INT8 multi-scale deformable attention for B200 (channels == 32, 16 <= levels*points <= 32,
 // points % 4 == 0): the second-generation path of the INT8 plugin op.
 //
-// Why (measured, profiles/r02a_micro_gather_bw2.txt and profiles/README.md): the round-1 kernel (msda.cu) gathers each
+// Why (measured, profiles/r02f_micro_gather_bw2.txt and profiles/README.md): the round-1 kernel (msda.cu) gathers each
 // bilinear tap of a head as its own 32-byte piece out of the reference's value layout [S, heads, 32]. The B200 L1/LSU
 // path retires about ONE distinct 128-byte line per clock per SM whatever the piece size (0.99 pieces/clk/SM for
 // L2-resident 32-byte pieces = 32 B/clk/SM; INT8 therefore ran no faster than FP16), and the SIMT accumulate pays 13
@@ -16,21 +16,17 @@
 //      microbenchmark against 0.25 for four 32-byte taps. Value tiles enter shared memory by TMA bulk copies
 //      (cp.async.bulk, SASS UBLKCP: the pixels of a row chunk are contiguous in [S, heads*32]), are interleaved by the
 //      threads (conflict-free: a warp reads 256 contiguous bytes) and leave as 16-byte stores.
-//   2. GATHER (msda_i8p_kernel), organised like the round-1 kernel — 8 lanes per item (batch, query, head), 4 items per
-//      warp, chunk c (4 points) of an item owned by lane c of its group, which evaluates the bit-exact index arithmetic
-//      (…Kernel.cu:657-674 / :138-172: fp32, loc = fma(ref, size, off) - 0.5) and the softmax numerators once — but
-//        * the owner leaves one 16-byte record per point in shared memory: {entry address | right-column flag, the
-//          four tap weights as two pairs of 16-bit fixed point} instead of six warp shuffles;
-//        * a sample is ONE LDG.128 per lane (8 lanes x 16 B = the 128-byte run; lane = (column, 8 channels x (y0, y1)));
-//        * the interleaved bytes are dp2a operands: b = {ch_i:y0, ch_i:y1, ch_j:y0, ch_j:y1}, a = (w_y0, w_y1) as u16:
-//          8 IDP per 16 bytes instead of 26 convert / FMA slots; int32 accumulators (exact), the two columns are added
-//          by one shuffle round, scale_value / (65536 * sum(exp)) / scale_out applied at the single requantisation.
-//      Weight quantisation to 16 bits: |error| <= 2^-17 per tap weight, <= 0.13 value-quanta worst case over 128 taps
-//      (typically 0.006) before the division by sum(exp) >= 1 — two orders of magnitude below the INT8 output step.
+//   2. GATHER (msda_i8p_kernel): persistent CTAs bound to one (camera, head) slab; the slab's coarsest levels (both
+//      parity copies) stay resident in shared memory after one TMA bulk-copy staging; 8 lanes per item, 4 items per warp;
+//      a sample is ONE 16-byte load per lane (8 lanes x 16 B = the 128-byte run: a conflict-free shared-memory
+//      wavefront for resident levels, 1.5 L1 lines otherwise) and 8 dp2a against 16-bit fixed-point tap-weight pairs
+//      (details at the kernel). Weight quantisation to 16 bits: |error| <= 2^-17 per tap weight, <= 0.13 value-quanta
+//      worst case over 128 taps (typically 0.006) before the division by sum(exp) >= 1 — two orders of magnitude below
+//      the INT8 output step.
 //
 // Replaces (same as msda.cu) ms_deformable_im2col_cuda_int8<float|__half2>
 // (TensorRT/plugin/multi_scale_deformable_attn/multiScaleDeformableAttnKernel.cu:1172-1218, kernels :849-1104).
-// The FP16 op stays on msda.cu: for 64-byte taps the same re-layout only helps where taps hit L1 (the L2 -> L1 path
+// The FP16 op does not use this layout (msda_res.cu serves it): for 64-byte taps the re-layout only helps where taps hit L1 (the L2 -> L1 path
 // tops out at 70 B/clk/SM either way), and a tensor-core variant (mma.sync with the interleaved entry as A fragment,
 // built and measured in round 2: 3.3 ms against 1.03 ms) loses to fragment-order loads that touch 4 lines per quarter warp.
 #include "common.cuh"
@@ -164,7 +160,7 @@ __global__ void __launch_bounds__(256) msda_pack_kernel(const PackParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 2. gather
+// 2. gather: persistent CTAs bound to one (camera, head) slab, coarse levels resident in shared memory
 // ---------------------------------------------------------------------------------------------------------------
 struct I8PParams {
   const char *packed;
@@ -173,7 +169,8 @@ struct I8PParams {
   int8_t *out;
   const int32_t *shapes;
   int B, M, Q, P, G, NP, L;
-  long long items;
+  int cpp;          // CTAs per (camera, head) pair
+  int cap_entries;  // shared-memory capacity in 64-byte entries
   float scale_value, scale_offset, scale_weight, scale_out;
   int4 *trace;
 };
@@ -196,160 +193,260 @@ __device__ __forceinline__ uint32_t fixed_pair(float w0, float w1) {
 __device__ __forceinline__ float deq8(uint32_t word, int byte, float s) {
   return static_cast<float>(static_cast<int8_t>(word >> (8 * byte))) * s;
 }
+__device__ __forceinline__ uint4 lds128_v2(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
 
-constexpr int kI8Threads = 256;
+#ifndef B200_I8_WARPS
+#define B200_I8_WARPS 24
+#endif
+constexpr int kI8Warps = B200_I8_WARPS;
+constexpr int kI8Threads = kI8Warps * 32;
 constexpr int kI8ItemsPerWarp = 4;
-constexpr int kI8ItemsPerBlock = kI8ItemsPerWarp * (kI8Threads / 32);
+constexpr int kI8ItemsPerBlock = kI8ItemsPerWarp * kI8Warps;
+constexpr int kI8CopyBytes = 16384;  // one bulk copy of the tail staging
 
-// R: reference-point storage (__half or float). One record per point: {address | flag, wA, wB, in-range}.
+// R: reference-point storage (__half or float).
+//   * CTA <-> one (camera, head) slab of the packed stack, `cpp` CTAs per slab interleaving its query blocks; the TAIL of
+//     the slab — the maximal run of whole levels (both parity copies), counted from the coarsest, that fits shared memory —
+//     is staged once by TMA bulk copies (the slab is contiguous; SASS UBLKCP) and every sample of those levels is ONE
+//     conflict-free 128-byte shared-memory wavefront (two adjacent 64-byte entries over 8 lanes).
+//   * 8 lanes per item (camera, query, head), 4 items per warp; chunk c (4 points of one level) of an item is owned by lane
+//     c, which evaluates the bit-exact index arithmetic (…Kernel.cu:657-674 / :138-172: fp32, loc = fma(ref, size, off)
+//     - 0.5) and the softmax numerators once and hands {entry | right-column flag, (w_y0, w_y1) of the left column, of
+//     the right column as 16-bit fixed point} to its group with three shuffles per point;
+//   * a sample is one 16-byte load per lane (lane = (column, 8 channels x (y0, y1))) and 8 dp2a: b = {ch_i:y0, ch_i:y1,
+//     ch_j:y0, ch_j:y1}, a = (w_y0, w_y1) as u16; int32 accumulators (exact), the two columns are added by one shuffle
+//     round, scale_value / (65536 * sum(exp)) / scale_out applied at the single requantisation.
 template <typename R, bool DBG>
-__global__ void __launch_bounds__(kI8Threads, 4) msda_i8p_kernel(const I8PParams prm) {
-  __shared__ uint4 recs[kI8Threads / 32][kI8ItemsPerWarp][33];  // [warp][item][point] (+1: bank spread between items)
+__global__ void __launch_bounds__(kI8Threads, 1) msda_i8p_kernel(const I8PParams prm) {
+  extern __shared__ __align__(128) char tail[];  // entries [E0, entries) of this CTA's slab, then the per-warp records
+  __shared__ __align__(8) unsigned long long bar;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane & 7, grp_i = lane >> 3;
-  const int M = prm.M, Q = prm.Q, P = prm.P, G = prm.G, NP = prm.NP;
+  const int sub = lane & 7, grp_i = lane >> 3, col = sub >> 2, cj = sub & 3;
+  // per-warp sample records: [item][point k of the chunk][chunk] x {address col 0, weights col 0, address col 1, weights
+  // col 1}; 33 slots per item so that the four items of a warp sit in different banks
+  const uint32_t rec_s = smem_addr(tail) + static_cast<uint32_t>(prm.cap_entries) * kEB + (warp * kI8ItemsPerWarp + grp_i) * (33 * 16);
+  const int M = prm.M, Q = prm.Q, P = prm.P, G = prm.G, NP = prm.NP, L = prm.L;
   const int NCH = NP >> 2, CPL = P >> 2;
-  const long long it_raw = static_cast<long long>(blockIdx.x) * kI8ItemsPerBlock + warp * kI8ItemsPerWarp + grp_i;
-  const bool active = it_raw < prm.items;
-  const long long it = active ? it_raw : prm.items - 1;  // inactive groups shadow the last item, never store
-  const long long bq = it / M;
-  const int m = static_cast<int>(it - bq * M), b = static_cast<int>(bq / Q);
-  uint4 *rec = recs[warp][grp_i];
 
-  // ---- owner part: lane `sub` owns chunk `sub` (4 consecutive points of one level)
-  const bool have = sub < NCH;
-  const int c = have ? sub : 0, lvl = c / CPL;
-  const LevelInfo lv = plan_level(prm.shapes, prm.L, lvl);
-  const int entries = plan_level(prm.shapes, prm.L, prm.L).e0;
-  const float Hf = static_cast<float>(lv.H), Wf = static_cast<float>(lv.W);
-
-  // reference points of the four points of the chunk: point k uses group k % G (P % 4 == 0, G in {1, 2, 4})
-  float rpx[4], rpy[4];
-  if (sizeof(R) == 2) {
-    const uint32_t *rp = reinterpret_cast<const uint32_t *>(prm.ref) + bq * G;
+  // ---- level table in registers (lane l < L): H, W, first entry of the parity-0 block (parity 1 follows at + blk)
+  int lvH = 1, lvW = 1;
+  if (lane < L) {
+    lvH = __ldg(prm.shapes + 2 * lane), lvW = __ldg(prm.shapes + 2 * lane + 1);
+  }
+  const int lvBlk = lane < L ? level_block(lvH, lvW) : 0;
+  int lvE0;
+  {
+    int incl = 2 * lvBlk;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = h2_to_f2(__ldg(rp + (k % G)));
-      rpx[k] = f.x, rpy[k] = f.y;
+    for (int d = 1; d < kV2MaxLevels; d <<= 1) {
+      const int t = __shfl_up_sync(kFullMask, incl, d);
+      if (lane >= d) incl += t;
     }
-  } else {
-    const float2 *rp = reinterpret_cast<const float2 *>(prm.ref) + bq * G;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = __ldg(rp + (k % G));
-      rpx[k] = f.x, rpy[k] = f.y;
-    }
+    lvE0 = incl - 2 * lvBlk;
   }
-  // ---- phase A (bit-exact): loc = fma(ref, size, off) - 0.5; off * scale is rounded to fp32 first (…Kernel.cu:916-921)
-  const uint2 o8 = ldg64_stream(prm.off + it * NP * 2 + c * 8);
-  float wim[4], him[4];
-  unsigned inr = 0;
+  const int entries = __shfl_sync(kFullMask, lvE0 + 2 * lvBlk, L - 1);
+  int E0 = (lane < L && entries - lvE0 <= prm.cap_entries) ? lvE0 : entries;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t w2 = k < 2 ? o8.x : o8.y;
-    const float ox = deq8(w2, (k & 1) * 2, prm.scale_offset), oy = deq8(w2, (k & 1) * 2 + 1, prm.scale_offset);
-    wim[k] = __fadd_rn(__fmaf_rn(rpx[k], Wf, ox), -0.5f);
-    him[k] = __fadd_rn(__fmaf_rn(rpy[k], Hf, oy), -0.5f);
-    const bool ok = have && him[k] > -1.f && wim[k] > -1.f && him[k] < Hf && wim[k] < Wf;
-    inr |= ok ? (1u << k) : 0u;
-  }
-  int8_t *out_item = prm.out + it * 32;
-  const unsigned vm = __ballot_sync(kFullMask, inr != 0u);  // bit (8*item + chunk): the chunk has a point in range
-  if (vm == 0u) {  // nothing of the warp's items is in range: exact zeros, logits are never read
-    if (active) reinterpret_cast<uint32_t *>(out_item)[sub] = 0u;
-    return;
-  }
-  // ---- phase B: softmax statistics over the item's NP logits (group of 8 lanes)
-  float lg[4];
-  if (have) {
-    const uint32_t l4 = ldg32_stream(prm.logits + it * NP + c * 4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) lg[k] = deq8(l4, k, prm.scale_weight);
-  } else {
-    lg[0] = lg[1] = lg[2] = lg[3] = -INFINITY;
-  }
-  float mx = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
-#pragma unroll
-  for (int d = 1; d < 8; d <<= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, d));
-  float sum = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) lg[k] = expf(lg[k] - mx), sum += lg[k];
-#pragma unroll
-  for (int d = 1; d < 8; d <<= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
+  for (int d = 16; d >= 1; d >>= 1) E0 = min(E0, __shfl_xor_sync(kFullMask, E0, d));
 
-  // ---- phase C: one record per owned point
-  if (have) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool ok = (inr >> k) & 1u;
-      const float hf = floorf(him[k]), wf = floorf(wim[k]);
-      const int h_low = ok ? static_cast<int>(hf) : 0, w_low = ok ? static_cast<int>(wf) : 0;
-      const float lh = __fsub_rn(him[k], hf), lw = __fsub_rn(wim[k], wf), hh = 1.f - lh, hw = 1.f - lw;
-      const bool t = h_low >= 0, bt = h_low + 1 <= lv.H - 1, lf = w_low >= 0, rt = w_low + 1 <= lv.W - 1;
-      const float e = lg[k];
-      const float w00 = (ok && t && lf) ? hh * hw * e : 0.f, w01 = (ok && t && rt) ? hh * lw * e : 0.f;
-      const float w10 = (ok && bt && lf) ? lh * hw * e : 0.f, w11 = (ok && bt && rt) ? lh * lw * e : 0.f;
-      const int par = h_low & 1, r = (h_low + 1) >> 1;
-      const int xl = max(w_low, 0), xr = min(w_low + 1, lv.W - 1);
-      const unsigned base = static_cast<unsigned>((par ? lv.e1 : lv.e0) + r * lv.W + xl) * kEB;
-      // bit 0: the right column is the next entry (otherwise it aliases the left one and carries weight 0)
-      rec[c * 4 + k] = make_uint4(base | (xr > xl ? 1u : 0u), fixed_pair(w00, w10), fixed_pair(w01, w11), 0u);
-      if (DBG && active)
-        prm.trace[it * NP + c * 4 + k] = ok ? make_int4(1, h_low, w_low, ((t && lf) ? 1 : 0) | ((t && rt) ? 2 : 0) |
-                                                                             ((bt && lf) ? 4 : 0) | ((bt && rt) ? 8 : 0))
-                                            : make_int4(0, 0, 0, 0);
-    }
+  const uint32_t barr = smem_addr(&bar), tail_s = smem_addr(tail);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barr) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+  __syncthreads();
 
-  // ---- gather: lane = (column = sub >> 2, channels 8*(sub & 3) .. +7 as (y0, y1) byte pairs)
-  const int col = sub >> 2, cj = sub & 3;
-  const char *vl = prm.packed + (static_cast<long long>(b) * M + m) * (static_cast<long long>(entries) * kEB) + cj * 16;
-  int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const unsigned chunk_any = (vm | (vm >> 8) | (vm >> 16) | (vm >> 24)) & 0xffu;  // chunk in range for ANY item of the warp
+  const int pairs = prm.B * M;
+  const int groups = gridDim.x / prm.cpp;
+  const int j = blockIdx.x % prm.cpp;
+  const long long slab = static_cast<long long>(entries) * kEB;
+  uint32_t phase = 0;
+  for (int pair = blockIdx.x / prm.cpp; pair < pairs; pair += groups) {
+    const int b = pair / M, m = pair - b * M;
+    const char *vl = prm.packed + static_cast<long long>(pair) * slab;
+    const int tail_bytes = (entries - E0) * kEB;
+    if (tail_bytes > 0) {
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barr), "r"(tail_bytes) : "memory");
+        for (int o = 0; o < tail_bytes; o += kI8CopyBytes) {
+          const int n = min(kI8CopyBytes, tail_bytes - o);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tail_s + o),
+                       "l"(vl + static_cast<long long>(E0) * kEB + o), "r"(n), "r"(barr)
+                       : "memory");
+        }
+      }
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                     : "=r"(done) : "r"(barr), "r"(phase) : "memory");
+      phase ^= 1u;
+    }
+    const char *gbase = vl + cj * 16;
+
+    for (long long qb = static_cast<long long>(j) * kI8ItemsPerBlock; qb < Q; qb += static_cast<long long>(prm.cpp) * kI8ItemsPerBlock) {
+      const long long q_raw = qb + warp * kI8ItemsPerWarp + grp_i;
+      const bool active = q_raw < Q;
+      const long long bq = static_cast<long long>(b) * Q + (active ? q_raw : Q - 1);
+      const long long it = bq * M + m;
+
+      // ---- owner part: lane `sub` owns chunk `sub` (4 consecutive points of one level)
+      const bool have = sub < NCH;
+      const int c = have ? sub : 0, lvl = c / CPL;
+      const int H = __shfl_sync(kFullMask, lvH, lvl), W = __shfl_sync(kFullMask, lvW, lvl);
+      const int e0 = __shfl_sync(kFullMask, lvE0, lvl), blk = __shfl_sync(kFullMask, lvBlk, lvl);
+      const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
+
+      float rpx[4], rpy[4];
+      if (sizeof(R) == 2) {
+        const uint32_t *rp = reinterpret_cast<const uint32_t *>(prm.ref) + bq * G;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = h2_to_f2(__ldg(rp + (k % G)));
+          rpx[k] = f.x, rpy[k] = f.y;
+        }
+      } else {
+        const float2 *rp = reinterpret_cast<const float2 *>(prm.ref) + bq * G;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __ldg(rp + (k % G));
+          rpx[k] = f.x, rpy[k] = f.y;
+        }
+      }
+      // ---- phase A (bit-exact): loc = fma(ref, size, off) - 0.5; off * scale is rounded to fp32 first (…Kernel.cu:916-921)
+      const uint2 o8 = ldg64_stream(prm.off + it * NP * 2 + c * 8);
+      float wim[4], him[4];
+      unsigned inr = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w2 = k < 2 ? o8.x : o8.y;
+        const float ox = deq8(w2, (k & 1) * 2, prm.scale_offset), oy = deq8(w2, (k & 1) * 2 + 1, prm.scale_offset);
+        wim[k] = __fadd_rn(__fmaf_rn(rpx[k], Wf, ox), -0.5f);
+        him[k] = __fadd_rn(__fmaf_rn(rpy[k], Hf, oy), -0.5f);
+        const bool ok = have && him[k] > -1.f && wim[k] > -1.f && him[k] < Hf && wim[k] < Wf;
+        inr |= ok ? (1u << k) : 0u;
+      }
+      int8_t *out_item = prm.out + it * 32;
+      const unsigned vm = __ballot_sync(kFullMask, inr != 0u);  // bit (8*item + chunk): the chunk has a point in range
+      if (vm == 0u) {  // nothing of the warp's items is in range: exact zeros, logits are never read
+        if (active) reinterpret_cast<uint32_t *>(out_item)[sub] = 0u;
+        continue;
+      }
+      // ---- phase B: softmax statistics over the item's NP logits (group of 8 lanes)
+      float lg[4];
+      if (have) {
+        const uint32_t l4 = ldg32_stream(prm.logits + it * NP + c * 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lg[k] = deq8(l4, k, prm.scale_weight);
+      } else {
+        lg[0] = lg[1] = lg[2] = lg[3] = -INFINITY;
+      }
+      float mx = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, d));
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lg[k] = expf(lg[k] - mx), sum += lg[k];
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
+
+      // ---- phase C (owner): one 16-byte record per point {load address and (w_y0, w_y1) of the left column, of the
+      // right column}: a shared-memory address for resident levels, a byte offset into the slab otherwise
+      const bool own_tail = e0 >= E0;
+      __syncwarp();  // the previous iteration's records have been consumed
+      if (have) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool ok = (inr >> k) & 1u;
+          const float hf = floorf(him[k]), wf = floorf(wim[k]);
+          const int h_low = ok ? static_cast<int>(hf) : 0, w_low = ok ? static_cast<int>(wf) : 0;
+          const float lh = __fsub_rn(him[k], hf), lw = __fsub_rn(wim[k], wf), hh = 1.f - lh, hw = 1.f - lw;
+          const bool t = h_low >= 0, bt = h_low + 1 <= H - 1, lf = w_low >= 0, rt = w_low + 1 <= W - 1;
+          const float e = lg[k];
+          const float w00 = (ok && t && lf) ? hh * hw * e : 0.f, w01 = (ok && t && rt) ? hh * lw * e : 0.f;
+          const float w10 = (ok && bt && lf) ? lh * hw * e : 0.f, w11 = (ok && bt && rt) ? lh * lw * e : 0.f;
+          const int par = h_low & 1, r = (h_low + 1) >> 1;
+          const int xl = max(w_low, 0);
+          const unsigned ent = static_cast<unsigned>(e0 + (par ? blk : 0) + r * W + xl);
+          // the right column is the next entry; without a right neighbour it aliases the left one and carries weight 0
+          const unsigned a0 = own_tail ? tail_s + (ent - static_cast<unsigned>(E0)) * kEB : ent * kEB;
+          const unsigned a1 = a0 + ((xl + 1 <= W - 1) ? kEB : 0);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rec_s + (k * 8 + sub) * 16), "r"(a0), "r"(fixed_pair(w00, w10)),
+                       "r"(a1), "r"(fixed_pair(w01, w11))
+                       : "memory");
+          if (DBG && active)
+            prm.trace[it * NP + c * 4 + k] = ok ? make_int4(1, h_low, w_low, ((t && lf) ? 1 : 0) | ((t && rt) ? 2 : 0) |
+                                                                                 ((bt && lf) ? 4 : 0) | ((bt && rt) ? 8 : 0))
+                                                : make_int4(0, 0, 0, 0);
+        }
+      }
+      __syncwarp();
+
+      // ---- gather: lane = (column col, channels 8*cj .. +7 as (y0, y1) byte pairs): one 8-byte record read, one 16-byte
+      // load and 8 dp2a per sample
+      int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int ch = 0;
+      const uint32_t my_rec = rec_s + col * 8;
 #pragma unroll 1
-  for (int ch = 0; ch < NCH; ++ch) {
-    if (!((chunk_any >> ch) & 1u)) continue;  // warp-uniform
-    uint4 v[4];
-    uint32_t wq[4];
+      for (int lc = 0; lc < L; ++lc) {
+        const bool in_tail = __shfl_sync(kFullMask, lvE0, lc) >= E0;  // warp-uniform: this level lives in shared memory
+#pragma unroll 1
+        for (int cc2 = 0; cc2 < CPL; ++cc2, ++ch) {
+          if ((vm & (0x01010101u << ch)) == 0u) continue;  // warp-uniform: chunk out of range for every item
+          uint2 rr[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint4 rr = rec[ch * 4 + k];
-      const unsigned a = (rr.x & ~1u) + ((col & rr.x & 1u) ? kEB : 0u);
-      wq[k] = col ? rr.z : rr.y;
-      v[k] = ldg128(vl + a);
+          for (int k = 0; k < 4; ++k)
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rr[k].x), "=r"(rr[k].y) : "r"(my_rec + (k * 8 + ch) * 16));
+          uint4 v[4];
+          if (in_tail) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = lds128_v2(rr[k].x + cj * 16);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = ldg128(gbase + rr[k].x);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const unsigned wq = rr[k].y;
+            acc[0] = dp2a_lo(wq, v[k].x, acc[0]), acc[1] = dp2a_hi(wq, v[k].x, acc[1]);
+            acc[2] = dp2a_lo(wq, v[k].y, acc[2]), acc[3] = dp2a_hi(wq, v[k].y, acc[3]);
+            acc[4] = dp2a_lo(wq, v[k].z, acc[4]), acc[5] = dp2a_hi(wq, v[k].z, acc[5]);
+            acc[6] = dp2a_lo(wq, v[k].w, acc[6]), acc[7] = dp2a_hi(wq, v[k].w, acc[7]);
+          }
+        }
+      }
+      // the two columns of a sample live in lanes sub and sub ^ 4
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(kFullMask, acc[i], 4);
+      if (active && col == 0) {
+        // real = acc / 65536 * scale_value / sum ; q = T2int8(real / scale_out)
+        const float mul = prm.scale_value / (65536.f * sum * prm.scale_out);
+        uint32_t o[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          uint32_t word = 0;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            word |= (static_cast<uint32_t>(to_int8_sat(static_cast<float>(acc[4 * i + jj]) * mul)) & 0xffu) << (8 * jj);
+          o[i] = word;
+        }
+        asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(out_item + 8 * cj), "r"(o[0]), "r"(o[1]) : "memory");
+      }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      acc[0] = dp2a_lo(wq[k], v[k].x, acc[0]), acc[1] = dp2a_hi(wq[k], v[k].x, acc[1]);
-      acc[2] = dp2a_lo(wq[k], v[k].y, acc[2]), acc[3] = dp2a_hi(wq[k], v[k].y, acc[3]);
-      acc[4] = dp2a_lo(wq[k], v[k].z, acc[4]), acc[5] = dp2a_hi(wq[k], v[k].z, acc[5]);
-      acc[6] = dp2a_lo(wq[k], v[k].w, acc[6]), acc[7] = dp2a_hi(wq[k], v[k].w, acc[7]);
-    }
-  }
-  // the two columns of a sample live in lanes sub and sub ^ 4
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(kFullMask, acc[i], 4);
-  if (active && col == 0) {
-    // real = acc / 65536 * scale_value / sum ; q = T2int8(real / scale_out)
-    const float mul = prm.scale_value / (65536.f * sum * prm.scale_out);
-    uint32_t o[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      uint32_t word = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        word |= (static_cast<uint32_t>(to_int8_sat(static_cast<float>(acc[4 * i + j]) * mul)) & 0xffu) << (8 * j);
-      o[i] = word;
-    }
-    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(out_item + 8 * cj), "r"(o[0]), "r"(o[1]) : "memory");
+    __syncthreads();  // every warp is done with the tail before the next slab's copies overwrite it
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+static std::atomic<int> g_i8_tail_bytes{128 * 1024};  // shared memory of the gather kernel's resident tail
+
 static bool i8p_shape_ok(int C, int L, int P, int G) {
   const int NP = L * P;
   return C == 32 && L >= 1 && L <= kV2MaxLevels && P % 4 == 0 && NP >= 16 && NP <= 32 && (G == 1 || G == 2 || G == 4);
@@ -411,23 +508,38 @@ int b200_msda_i8_ws(const int8_t *value, float scale_value, const int32_t *spati
   int st = check_launch();
   if (st != B200_OK) return st;
 
-  // 2. gather
+  // 2. gather: one persistent CTA per SM, `cpp` CTAs per (camera, head) slab
   I8PParams gp{};
   gp.packed = static_cast<const char *>(workspace), gp.ref = reference_points, gp.off = sampling_offsets;
   gp.logits = attn_weight, gp.out = out, gp.shapes = spatial_shapes;
   gp.B = batch, gp.M = num_heads, gp.Q = num_query, gp.P = num_point, gp.G = points_per_group;
-  gp.NP = num_levels * num_point, gp.L = num_levels, gp.items = items;
+  gp.NP = num_levels * num_point, gp.L = num_levels;
   gp.scale_value = scale_value, gp.scale_offset = scale_offset, gp.scale_weight = scale_weight, gp.scale_out = scale_out;
+  const int pairs = batch * num_heads;
+  gp.cpp = pairs >= sms ? 1 : sms / pairs;
+  const int blocks_q = (num_query + kI8ItemsPerBlock - 1) / kI8ItemsPerBlock;
+  if (gp.cpp > blocks_q) gp.cpp = blocks_q;
+  const int grid = pairs >= sms ? sms : pairs * gp.cpp;
+  long long cap = g_i8_tail_bytes.load(std::memory_order_relaxed);
+  const long long need = static_cast<long long>(3) * spatial_size * kEB;  // never more than a whole slab
+  if (cap > need) cap = (need + 127) / 128 * 128;
+  gp.cap_entries = static_cast<int>(cap / kEB);
+  const int gsmem = gp.cap_entries * kEB + kI8Warps * kI8ItemsPerWarp * 33 * 16;  // tail + per-warp sample records
+  auto launch = [&](auto kern) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gsmem) != cudaSuccess) return B200_ERR_LAUNCH;
+    kern<<<grid, kI8Threads, gsmem, s>>>(gp);
+    return check_launch();
+  };
   if (trace_records) {
     if (cudaMemsetAsync(trace_records, 0, static_cast<size_t>(items) * gp.NP * 16, s) != cudaSuccess) return B200_ERR_LAUNCH;
     gp.trace = reinterpret_cast<int4 *>(trace_records);
-    if (ref_is_half) msda_i8p_kernel<__half, true><<<static_cast<unsigned>(blocks), kI8Threads, 0, s>>>(gp);
-    else msda_i8p_kernel<float, true><<<static_cast<unsigned>(blocks), kI8Threads, 0, s>>>(gp);
-  } else {
-    if (ref_is_half) msda_i8p_kernel<__half, false><<<static_cast<unsigned>(blocks), kI8Threads, 0, s>>>(gp);
-    else msda_i8p_kernel<float, false><<<static_cast<unsigned>(blocks), kI8Threads, 0, s>>>(gp);
+    return ref_is_half ? launch(msda_i8p_kernel<__half, true>) : launch(msda_i8p_kernel<float, true>);
   }
-  return check_launch();
+  return ref_is_half ? launch(msda_i8p_kernel<__half, false>) : launch(msda_i8p_kernel<float, false>);
+}
+
+int b200_msda_set_i8_resident_bytes(int bytes) {
+  return g_i8_tail_bytes.exchange(bytes < 4096 ? 4096 : (bytes > 200 * 1024 ? 200 * 1024 : bytes));
 }
 
 }  // extern "C"

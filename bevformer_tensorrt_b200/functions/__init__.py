@@ -14,6 +14,7 @@ from .multi_scale_deformable_attn import (
     multi_scale_deformable_attn_sca,
     multi_scale_deformable_attn_sca_shared,
     set_msda_v2,
+    set_msda_f16_path,
 )
 from .point_sampling import bev_point_sampling, get_reference_points_3d, point_sampling_trt
 from .rotate import rotate, rotate2, rotate_chw2, rotate_hwc, rotate_int8

@@ -28,6 +28,19 @@ def set_msda_v2(enabled: bool) -> bool:
     return prev
 
 
+def set_msda_f16_path(resident: bool, resident_bytes: int = None):
+    """Selects the kernel behind the FP16 plugin op: True (library default) = the resident-tail kernel
+    (csrc/msda_res.cu: coarse pyramid levels staged in shared memory by TMA) where its envelope holds, False = the round-1
+    gather kernel (csrc/msda.cu). ``resident_bytes``: shared memory the resident kernel may use for the tail.
+    Returns the previous (path, bytes-or-None)."""
+    lib = _lib.load()
+    prev = bool(lib.b200_msda_set_f16_path(int(bool(resident))))
+    prev_bytes = None
+    if resident_bytes is not None:
+        prev_bytes = int(lib.b200_msda_set_resident_bytes(int(resident_bytes)))
+    return prev, prev_bytes
+
+
 def _v2_workspace(lib, dims, device):
     """Workspace tensor for the INT8 v2 path, or None when the shape is outside its envelope (or v2 is switched off)."""
     if not _V2["enabled"]:

@@ -125,10 +125,14 @@ int b200_msda_sca_shared_f16(const void *value, const int32_t *spatial_shapes, c
  * reference plugin receives, the packed-stack plan is evaluated on the device.
  * Two launches per call: (1) a pack pre-pass re-lays `value` into per-(camera, head) column-pair entries with the two
  * image rows interleaved per channel (value tiles staged through shared memory by TMA bulk copies); (2) the gather:
- * a bilinear sample is one 128-byte run, one LDG.128 per lane, accumulated with dp2a against 16-bit fixed-point tap
- * weights in int32, one requantisation (T2int8). Index arithmetic is the round-1 kernel's (FP32, bit-exact).
+ * persistent CTAs bound to one (camera, head) slab of the packed stack, the coarsest levels of the slab resident in
+ * shared memory (TMA bulk copies; b200_msda_set_i8_resident_bytes, default 128 KiB); a bilinear sample is one 128-byte
+ * run, one 16-byte load per lane (shared memory for resident levels, L1/L2 otherwise), accumulated with dp2a against
+ * 16-bit fixed-point tap weights in int32, one requantisation (T2int8). Index arithmetic is the round-1 kernel's
+ * (FP32, bit-exact).
  * `trace_records` (optional, may be NULL): the gather kernel's own sampling-index records, as in b200_msda_i8_trace.
  * Returns B200_ERR_UNSUPPORTED for shapes outside the envelope (callers fall back to b200_msda_i8). */
+int b200_msda_set_i8_resident_bytes(int bytes); /* returns the previous setting */
 size_t b200_msda_i8_workspace_size(int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_point,
                                    int points_per_group); /* 0 = shape outside the envelope */
 int b200_msda_i8_ws(const int8_t *value, float scale_value, const int32_t *spatial_shapes,
@@ -183,6 +187,15 @@ int b200_msda_debug_indices(int dtype, const int32_t *spatial_shapes, const void
  * accumulator (fma.rn.f32.f16, FHFMA); ~15 % fewer issue slots but the FP16 rounding of the weights adds up to ~3e-4
  * on O(1) outputs, so it is opt-in. Returns the previous setting. */
 int b200_msda_set_f16_mode(int mode);
+
+/* Selects the kernel behind b200_msda_f16 / _f16_h2 / _f16_trace. 1 (default) = the resident-tail kernel (csrc/msda_res.cu:
+ * CTAs bound to one (batch, head), the coarsest pyramid levels staged in shared memory by TMA, taps of those levels served
+ * from shared memory) whenever channels == 32, num_levels*num_point <= 32, num_point % 4 == 0; 0 = the round-1 gather
+ * kernel (csrc/msda.cu) for every shape. Same results either way (same index arithmetic, FP32 accumulation).
+ * b200_msda_set_resident_bytes: shared memory the resident kernel may use for the tail (default 128 KiB). Both return
+ * the previous setting. */
+int b200_msda_set_f16_path(int path);
+int b200_msda_set_resident_bytes(int bytes);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Plugin-shaped entry: the argument list of IPluginV2DynamicExt::enqueue

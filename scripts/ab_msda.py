@@ -27,6 +27,9 @@ def timeit(fn, n=30, warm=5):
     return sum(per) / len(per), per[0]
 
 
+CAPS = [int(x) << 10 for x in os.environ.get("AB_CAPS", "128,32,8").split(",")]
+
+
 def main():
     cfg = CONFIGS["base_sca"]
     _lib.load()
@@ -49,14 +52,23 @@ def main():
 
         for tag, fn in (("f16", run16), ("i8", run8)):
             bt.set_msda_v2(False)
+            bt.set_msda_f16_path(False)
             ref_out = fn().float()
             m, mn = timeit(fn)
             out[f"{tag}_{dist}_v1"] = {"ms": m, "min_ms": mn}
             bt.set_msda_v2(True)
-            if tag == "i8":  # FP16 has only the round-1 kernel
+            if tag == "i8":
                 got = fn().float()
                 m, mn = timeit(fn)
                 out[f"{tag}_{dist}_v2"] = {"ms": m, "min_ms": mn, "max_abs_vs_v1": (got - ref_out).abs().max().item()}
+            else:  # resident-tail kernel at several shared-memory capacities
+                for cap in (CAPS if dist == "U" else CAPS[:1]):
+                    bt.set_msda_f16_path(True, cap)
+                    got = fn().float()
+                    m, mn = timeit(fn)
+                    out[f"{tag}_{dist}_res{cap >> 10}k"] = {"ms": m, "min_ms": mn,
+                                                            "max_abs_vs_v1": (got - ref_out).abs().max().item()}
+                bt.set_msda_f16_path(True, 128 << 10)
         del f16, i8
         torch.cuda.empty_cache()
     print(json.dumps(out, indent=1))

@@ -218,8 +218,10 @@ def test_base_shape_int8_config4_vs_dequant_oracle_and_reference_kernel():
 
 @pytest.mark.parametrize("interp,pad,align", [("bilinear", "zeros", False), ("bilinear", "border", True), ("bicubic", "zeros", False)])
 def test_backward_matches_the_reference_binding(interp, pad, align):
-    """functions/grid_sampler.py:39-55: gradients w.r.t. input and the [-10, 10] grid equal those of the reference
-    binding's forward differentiated by autograd (its torch restatement in oracle/grid_sampler.py)."""
+    """functions/grid_sampler.py:39-55: the input gradient equals autograd's of the reference binding's forward (its
+    torch restatement in oracle/grid_sampler.py); the grid gradient is the REFERENCE's: its backward() returns ATen's
+    gradient w.r.t. grid/10 multiplied by 10 (:55) where the chain rule gives a division — i.e. 100 x autograd's. The
+    drop-in reproduces the reference's statement, so that is what is asserted."""
     inp, grid = make_grid_sampler_inputs(2, 5, 9, 11, 13, 12, seed=31, span=9.0)
     a, g = inp.cuda().requires_grad_(True), grid.cuda().requires_grad_(True)
     out = bt.grid_sampler(a, g, interp, pad, align)
@@ -229,13 +231,13 @@ def test_backward_matches_the_reference_binding(interp, pad, align):
     ref = ogs.grid_sampler_torch_port(a2, g2, IM[interp], PM[pad], align)
     (ref * w).sum().backward()
     assert (out - ref).abs().max().item() < 1e-5
-    assert (a.grad - a2.grad).abs().max().item() < 1e-5 and (g.grad - g2.grad).abs().max().item() < 1e-4
+    assert (a.grad - a2.grad).abs().max().item() < 1e-5 and (g.grad - 100 * g2.grad).abs().max().item() < 1e-2
     inp3, grid3 = make_grid_sampler_inputs(1, 3, 5, 6, 7, 8, seed=32, depth=(4, 5), span=9.0)
     a, g = inp3.cuda().requires_grad_(True), grid3.cuda().requires_grad_(True)
     (bt.grid_sampler(a, g, "bilinear", "zeros", False) ** 2).sum().backward()
     a2, g2 = inp3.cuda().requires_grad_(True), grid3.cuda().requires_grad_(True)
     (ogs.grid_sampler_torch_port(a2, g2, 0, 0, False) ** 2).sum().backward()
-    assert (a.grad - a2.grad).abs().max().item() < 1e-4 and (g.grad - g2.grad).abs().max().item() < 1e-3
+    assert (a.grad - a2.grad).abs().max().item() < 1e-4 and (g.grad - 100 * g2.grad).abs().max().item() < 1e-1
 
 
 def test_error_behaviour():

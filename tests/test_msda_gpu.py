@@ -59,6 +59,52 @@ def _oracle_f32(inputs):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# resident-tail FP16 kernel (csrc/msda_res.cu): the library default behind the FP16 plugin op
+# ---------------------------------------------------------------------------------------------------------------
+RES_EXTRA = {
+    # more (batch, head) pairs than SMs: CTAs walk several pairs and re-stage the tail in between
+    "many_pairs": MSDAConfig("many_pairs", 20, 70, 8, 32, ((6, 7), (3, 4), (2, 2)), 8, 4),
+    # tail boundary inside the pyramid at every capacity tried below; 3 levels x 8 points
+    "three_levels": MSDAConfig("three_levels", 2, 501, 8, 32, ((40, 60), (20, 30), (10, 15)), 8, 2),
+}
+
+
+@pytest.mark.parametrize("cap", [8192, 32768, 131072, 204800])
+@pytest.mark.parametrize("name,dist,seed", [("small_sca", "edge", 61), ("small_sca", "U", 62), ("tiny_sca", "G", 63),
+                                            ("tsa_like", "edge", 64), ("g2", "edge", 65), ("ragged_tail", "edge", 66),
+                                            ("one_pixel", "edge", 67), ("many_pairs", "edge", 68),
+                                            ("three_levels", "edge", 69), ("three_levels", "U", 70)])  # fmt: skip
+def test_resident_kernel_matches_oracle_and_round1_kernel(name, dist, seed, cap):
+    """Same inputs through the resident-tail kernel (coarse levels served from shared memory after TMA staging) at several
+    shared-memory capacities — 8 KB: nothing or only the coarsest level resident; 200 KB: everything for the small
+    pyramids — and through the round-1 gather kernel. Values within the FP16 bar of the FP32 oracle, and the two kernels
+    agree to FP16 rounding (same taps, same FP32 weights; only the order of the two column sums differs); the index
+    records traced out of the resident kernel itself are bit-identical to the oracle's."""
+    cfg = RES_EXTRA.get(name) or _cfg(name)
+    inputs = make_msda_inputs(cfg, dist, seed, torch.float16)
+    want = _oracle_f32(inputs)
+    dev = _cuda(inputs)
+    prev = bt.set_msda_f16_path(True, cap)
+    try:
+        got = bt.multi_scale_deformable_attn(*dev)
+        out_t, rec = msda_trace(*dev)
+    finally:
+        bt.set_msda_f16_path(prev[0], prev[1])
+    prev = bt.set_msda_f16_path(False)
+    try:
+        r1 = bt.multi_scale_deformable_attn(*dev)
+    finally:
+        bt.set_msda_f16_path(prev[0])
+    err = np.abs(got.float().cpu().numpy() - want).max()
+    assert err < FP16_TOL, (name, dist, cap, err)
+    assert torch.equal(out_t, got)
+    d = (got.float() - r1.float()).abs().max().item()
+    assert d <= 2e-3 * max(1.0, float(np.abs(want).max())), (name, cap, d)
+    wrec = _want_records(inputs[1], inputs[2].float().numpy(), inputs[3].float().numpy(), cfg)
+    assert (rec.cpu().numpy() == wrec).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # golden vectors produced by the reference's own Python code
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("path", golden_msda_cases())
@@ -370,11 +416,22 @@ V2_CASES = {
 }
 
 
+@pytest.fixture(params=[4096, 131072])
+def i8_resident_bytes(request):
+    """Shared memory the INT8 gather kernel may keep resident: 4 KB (at most the coarsest level of the small pyramids:
+    most samples take the global path) and the 128 KB default (small pyramids entirely resident)."""
+    lib = _lib.load()
+    prev = lib.b200_msda_set_i8_resident_bytes(request.param)
+    yield request.param
+    lib.b200_msda_set_i8_resident_bytes(prev)
+
+
 @pytest.mark.parametrize("ref_dtype", [torch.float32, torch.float16])
 @pytest.mark.parametrize("name,dist,seed", [("small_sca", "U", 111), ("small_sca", "edge", 112), ("v2_odd_levels", "edge", 113),
-                                            ("v2_two_levels", "edge", 114), ("v2_np16", "U", 115), ("v2_np24", "edge", 116)])  # fmt: skip
-def test_v2_int8_matches_oracle_and_round1_kernel(name, dist, seed, ref_dtype):
-    cfg = CONFIGS.get(name) or V2_CASES[name]
+                                            ("v2_two_levels", "edge", 114), ("v2_np16", "U", 115), ("v2_np24", "edge", 116),
+                                            ("many_pairs", "edge", 117)])  # fmt: skip
+def test_v2_int8_matches_oracle_and_round1_kernel(name, dist, seed, ref_dtype, i8_resident_bytes):
+    cfg = CONFIGS.get(name) or V2_CASES.get(name) or RES_EXTRA[name]
     lib = _lib.load()
     assert lib.b200_msda_i8_workspace_size(cfg.batch, cfg.spatial_size, cfg.num_heads, 32, cfg.num_levels, cfg.num_points,
                                            cfg.points_per_group) > 0  # these shapes are inside the v2 envelope
