@@ -34,6 +34,7 @@ from .functions import (  # noqa: E402
     multi_scale_deformable_attn_int8,
     multi_scale_deformable_attn_sca,
     multi_scale_deformable_attn_sca_shared,
+    multi_scale_deformable_attn_queue_mean,
     point_sampling_trt,
     rotate,
     rotate2,
@@ -64,6 +65,7 @@ __all__ = [
     "multi_scale_deformable_attn_int8",
     "multi_scale_deformable_attn_sca",
     "multi_scale_deformable_attn_sca_shared",
+    "multi_scale_deformable_attn_queue_mean",
     "point_sampling_trt",
     "rotate",
     "rotate2",

@@ -187,8 +187,12 @@ __device__ __forceinline__ int dp2a_hi(uint32_t a, uint32_t b, int c) {
 }
 // two tap weights in [0, 1] as 16-bit fixed point, (w_y0 | w_y1 << 16)
 __device__ __forceinline__ uint32_t fixed_pair(float w0, float w1) {
-  const uint32_t q0 = min(__float2uint_rn(w0 * 65536.f), 65535u), q1 = min(__float2uint_rn(w1 * 65536.f), 65535u);
-  return q0 | (q1 << 16);
+  uint32_t r;  // round to nearest, saturate at 65535 (w = 1.0), pack
+  asm("{ .reg .u16 a, b; .reg .f32 x, y;\n\t"
+      "mul.f32 x, %1, 0f47800000; mul.f32 y, %2, 0f47800000;\n\t"
+      "cvt.rni.sat.u16.f32 a, x; cvt.rni.sat.u16.f32 b, y; mov.b32 %0, {a, b}; }"
+      : "=r"(r) : "f"(w0), "f"(w1));
+  return r;
 }
 __device__ __forceinline__ float deq8(uint32_t word, int byte, float s) {
   return static_cast<float>(static_cast<int8_t>(word >> (8 * byte))) * s;
@@ -261,6 +265,17 @@ __global__ void __launch_bounds__(kI8Threads, 1) msda_i8p_kernel(const I8PParams
   }
   __syncthreads();
 
+  // lane `sub` owns chunk `sub` (4 consecutive points of one level) of its item: the level's constants, once
+  const bool have = sub < NCH;
+  const int c = have ? sub : 0, lvl = c / CPL;
+  const int H = __shfl_sync(kFullMask, lvH, lvl), W = __shfl_sync(kFullMask, lvW, lvl);
+  const int e0 = __shfl_sync(kFullMask, lvE0, lvl), blk = __shfl_sync(kFullMask, lvBlk, lvl);
+  const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
+  const bool own_tail = e0 >= E0;
+  const int gmask = G - 1;  // G in {1, 2, 4}: point k of a chunk uses reference group k & (G - 1)
+  unsigned tailmask = 0;    // bit ch: chunk ch belongs to a level that lives in shared memory (warp-uniform)
+  for (int ch = 0; ch < NCH; ++ch) tailmask |= (__shfl_sync(kFullMask, lvE0, ch / CPL) >= E0) ? (1u << ch) : 0u;
+
   const int pairs = prm.B * M;
   const int groups = gridDim.x / prm.cpp;
   const int j = blockIdx.x % prm.cpp;
@@ -295,26 +310,19 @@ __global__ void __launch_bounds__(kI8Threads, 1) msda_i8p_kernel(const I8PParams
       const long long bq = static_cast<long long>(b) * Q + (active ? q_raw : Q - 1);
       const long long it = bq * M + m;
 
-      // ---- owner part: lane `sub` owns chunk `sub` (4 consecutive points of one level)
-      const bool have = sub < NCH;
-      const int c = have ? sub : 0, lvl = c / CPL;
-      const int H = __shfl_sync(kFullMask, lvH, lvl), W = __shfl_sync(kFullMask, lvW, lvl);
-      const int e0 = __shfl_sync(kFullMask, lvE0, lvl), blk = __shfl_sync(kFullMask, lvBlk, lvl);
-      const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
-
       float rpx[4], rpy[4];
       if (sizeof(R) == 2) {
         const uint32_t *rp = reinterpret_cast<const uint32_t *>(prm.ref) + bq * G;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 f = h2_to_f2(__ldg(rp + (k % G)));
+          const float2 f = h2_to_f2(__ldg(rp + (k & gmask)));
           rpx[k] = f.x, rpy[k] = f.y;
         }
       } else {
         const float2 *rp = reinterpret_cast<const float2 *>(prm.ref) + bq * G;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 f = __ldg(rp + (k % G));
+          const float2 f = __ldg(rp + (k & gmask));
           rpx[k] = f.x, rpy[k] = f.y;
         }
       }
@@ -357,7 +365,6 @@ __global__ void __launch_bounds__(kI8Threads, 1) msda_i8p_kernel(const I8PParams
 
       // ---- phase C (owner): one 16-byte record per point {load address and (w_y0, w_y1) of the left column, of the
       // right column}: a shared-memory address for resident levels, a byte offset into the slab otherwise
-      const bool own_tail = e0 >= E0;
       __syncwarp();  // the previous iteration's records have been consumed
       if (have) {
 #pragma unroll
@@ -371,11 +378,11 @@ __global__ void __launch_bounds__(kI8Threads, 1) msda_i8p_kernel(const I8PParams
           const float w00 = (ok && t && lf) ? hh * hw * e : 0.f, w01 = (ok && t && rt) ? hh * lw * e : 0.f;
           const float w10 = (ok && bt && lf) ? lh * hw * e : 0.f, w11 = (ok && bt && rt) ? lh * lw * e : 0.f;
           const int par = h_low & 1, r = (h_low + 1) >> 1;
-          const int xl = max(w_low, 0);
+          const int xl = max(w_low, 0), xr = min(w_low + 1, W - 1);
           const unsigned ent = static_cast<unsigned>(e0 + (par ? blk : 0) + r * W + xl);
           // the right column is the next entry; without a right neighbour it aliases the left one and carries weight 0
           const unsigned a0 = own_tail ? tail_s + (ent - static_cast<unsigned>(E0)) * kEB : ent * kEB;
-          const unsigned a1 = a0 + ((xl + 1 <= W - 1) ? kEB : 0);
+          const unsigned a1 = a0 + (xr > xl ? kEB : 0);
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rec_s + (k * 8 + sub) * 16), "r"(a0), "r"(fixed_pair(w00, w10)),
                        "r"(a1), "r"(fixed_pair(w01, w11))
                        : "memory");
@@ -390,34 +397,29 @@ __global__ void __launch_bounds__(kI8Threads, 1) msda_i8p_kernel(const I8PParams
       // ---- gather: lane = (column col, channels 8*cj .. +7 as (y0, y1) byte pairs): one 8-byte record read, one 16-byte
       // load and 8 dp2a per sample
       int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      int ch = 0;
       const uint32_t my_rec = rec_s + col * 8;
 #pragma unroll 1
-      for (int lc = 0; lc < L; ++lc) {
-        const bool in_tail = __shfl_sync(kFullMask, lvE0, lc) >= E0;  // warp-uniform: this level lives in shared memory
-#pragma unroll 1
-        for (int cc2 = 0; cc2 < CPL; ++cc2, ++ch) {
-          if ((vm & (0x01010101u << ch)) == 0u) continue;  // warp-uniform: chunk out of range for every item
-          uint2 rr[4];
+      for (int ch = 0; ch < NCH; ++ch) {
+        if ((vm & (0x01010101u << ch)) == 0u) continue;  // warp-uniform: chunk out of range for every item
+        uint2 rr[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rr[k].x), "=r"(rr[k].y) : "r"(my_rec + (k * 8 + ch) * 16));
-          uint4 v[4];
-          if (in_tail) {
+        for (int k = 0; k < 4; ++k)
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rr[k].x), "=r"(rr[k].y) : "r"(my_rec + (k * 8 + ch) * 16));
+        uint4 v[4];
+        if ((tailmask >> ch) & 1u) {  // warp-uniform
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = lds128_v2(rr[k].x + cj * 16);
-          } else {
+          for (int k = 0; k < 4; ++k) v[k] = lds128_v2(rr[k].x + cj * 16);
+        } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = ldg128(gbase + rr[k].x);
-          }
+          for (int k = 0; k < 4; ++k) v[k] = ldg128(gbase + rr[k].x);
+        }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const unsigned wq = rr[k].y;
-            acc[0] = dp2a_lo(wq, v[k].x, acc[0]), acc[1] = dp2a_hi(wq, v[k].x, acc[1]);
-            acc[2] = dp2a_lo(wq, v[k].y, acc[2]), acc[3] = dp2a_hi(wq, v[k].y, acc[3]);
-            acc[4] = dp2a_lo(wq, v[k].z, acc[4]), acc[5] = dp2a_hi(wq, v[k].z, acc[5]);
-            acc[6] = dp2a_lo(wq, v[k].w, acc[6]), acc[7] = dp2a_hi(wq, v[k].w, acc[7]);
-          }
+        for (int k = 0; k < 4; ++k) {
+          const unsigned wq = rr[k].y;
+          acc[0] = dp2a_lo(wq, v[k].x, acc[0]), acc[1] = dp2a_hi(wq, v[k].x, acc[1]);
+          acc[2] = dp2a_lo(wq, v[k].y, acc[2]), acc[3] = dp2a_hi(wq, v[k].y, acc[3]);
+          acc[4] = dp2a_lo(wq, v[k].z, acc[4]), acc[5] = dp2a_hi(wq, v[k].z, acc[5]);
+          acc[6] = dp2a_lo(wq, v[k].w, acc[6]), acc[7] = dp2a_hi(wq, v[k].w, acc[7]);
         }
       }
       // the two columns of a sample live in lanes sub and sub ^ 4
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) msda_i8p_kernel(const I8PParams
       for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(kFullMask, acc[i], 4);
       if (active && col == 0) {
         // real = acc / 65536 * scale_value / sum ; q = T2int8(real / scale_out)
-        const float mul = prm.scale_value / (65536.f * sum * prm.scale_out);
+        const float mul = __fdividef(prm.scale_value, 65536.f * sum * prm.scale_out);
         uint32_t o[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {

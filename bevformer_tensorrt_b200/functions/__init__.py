@@ -13,6 +13,7 @@ from .multi_scale_deformable_attn import (
     multi_scale_deformable_attn_int8,
     multi_scale_deformable_attn_sca,
     multi_scale_deformable_attn_sca_shared,
+    multi_scale_deformable_attn_queue_mean,
     set_msda_v2,
     set_msda_f16_path,
 )
@@ -33,6 +34,7 @@ TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn2)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_int8)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_sca)
 TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_sca_shared)
+TRT_FUNCTIONS.register_module(module=multi_scale_deformable_attn_queue_mean)
 
 TRT_FUNCTIONS.register_module(module=rotate)
 TRT_FUNCTIONS.register_module(module=rotate2)

@@ -230,6 +230,20 @@ def multi_scale_deformable_attn_sca(value, value_spatial_shapes, reference_point
     return accum
 
 
+def multi_scale_deformable_attn_queue_mean(value, value_spatial_shapes, reference_points, sampling_offsets,
+                                           attention_weights):
+    """TemporalSelfAttention's sampling with its BEV-queue mean folded in: the reference calls the plugin
+    on ``bs*num_bev_queue`` value stacks and then takes ``torch.mean(output, dim=0, keepdim=True)``
+    (temporal_self_attention.py:447-453). Here the per-queue outputs are never written: the fused epilogue adds
+    ``out[b] / num_bev_queue`` into one fp32 accumulator (two commutative adds per slot: deterministic). Same arguments
+    as the plugin op; returns ``[1, num_query, heads*channels]`` in ``value.dtype``."""
+    bs, num_query = value.shape[0], sampling_offsets.shape[1]
+    mask = torch.full((bs, num_query), 1.0 / bs, dtype=torch.float32, device=value.device)
+    acc = multi_scale_deformable_attn_sca(value, value_spatial_shapes, reference_points, sampling_offsets,
+                                          attention_weights, mask)
+    return acc.to(value.dtype).unsqueeze(0)
+
+
 def multi_scale_deformable_attn_sca_shared(value, value_spatial_shapes, reference_points, sampling_offsets,
                                            attention_weights, bev_mask):
     """Camera-shared fused SCA sampling. SpatialCrossAttention repeats the BEV query per camera before its

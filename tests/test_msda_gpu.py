@@ -665,6 +665,17 @@ def test_shared_sca_base_shapes_and_errors():
         bt.multi_scale_deformable_attn_sca_shared(*shared, mask)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float16, FP16_TOL)])
+def test_tsa_queue_mean_matches_mean_of_oracle(dtype, tol):
+    """temporal_self_attention.py:447-453: plugin op on the 2-entry BEV queue, then mean over the queue."""
+    cfg = _cfg("tsa_like")
+    inputs = make_msda_inputs(cfg, "edge", 91, dtype)
+    want = _oracle_f32(inputs).reshape(cfg.batch, cfg.num_query, -1).mean(0, keepdims=True)
+    got = bt.multi_scale_deformable_attn_queue_mean(*_cuda(inputs))
+    assert got.shape == (1, cfg.num_query, cfg.num_heads * cfg.channels) and got.dtype == dtype
+    assert np.abs(got.float().cpu().numpy() - want).max() < tol
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # host-buffer entry (bench.py's e2e leg): per-camera H2D / kernel / D2H pipeline
 # ---------------------------------------------------------------------------------------------------------------
