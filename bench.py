@@ -7,8 +7,13 @@
 
 A step = one pass of the hot path over one 6-camera frame of synthetic NuScenes-shaped input:
   N = 1 : one MultiScaleDeformableAttn call at BASELINE configs[2] (200x200 BEV, 6 cams, 4 levels, 8 heads, 4x8 points)
-  N > 1 : the same frame sharded per camera (and per query tile when 6 does not divide N): local MSDA kernels,
-          bev_mask-weighted camera sum, ONE NCCL all-reduce of the BEV accumulator [40000, 256] ("scaling": "strong").
+  N > 1 : the same frame on a (camera group x query tile) grid of ranks: one fused sampling launch per rank (bev_mask
+          camera sum folded in) and one reduce-scatter of the BEV accumulator inside the camera group — our kernel over
+          NVLink peer memory, or NCCL ("scaling": "strong"). Every line also carries `scaling_anchor`: the same fused
+          step on ONE GPU (same work as N > 1), because the N = 1 headline is the plain plugin op.
+Input distribution: G (camera-ring geometry, the NuScenes-shaped case north_star names) is the headline; the reference unit
+test's uniform distribution U (every point of every camera in range: worst case) is measured in the same run and printed
+as `worst_case_U` with its own roofline.
 `value` is timed with inputs resident in HBM (CUDA events on the launching stream, barrier + synchronize on both sides,
 max over ranks); `e2e` is the same call through the public Python operator with pinned HOST buffers (H2D of the step's
 inputs and D2H of its result inside the timed region). `roofline` divides the ALGORITHMIC bytes of one launch
@@ -66,7 +71,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dist", default="U", choices=["U", "G"], help="input distribution (SURVEY §8(d) config 3)")
+    ap.add_argument("--dist", default="G", choices=["U", "G"],
+                    help="input distribution (SURVEY §8(d) config 3). G = the NuScenes-shaped camera-ring geometry that "
+                         "north_star names (headline); U = the reference unit test's uniform worst case (always reported "
+                         "next to it, `worst_case_U`)")
     ap.add_argument("--dtype", default="f16", choices=["f16", "f32", "i8"])
     ap.add_argument("--f16-mode", type=int, default=None, help="0 exact fp32 FMA, 1 mixed FHFMA (library default)")
     ap.add_argument("--round1-kernel", action="store_true", help="run csrc/msda.cu instead of the second-generation path")
@@ -78,6 +86,7 @@ def parse():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the same-box GPU baseline of the reference's kernels")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: reduce-scatter inside the camera group by our NVLink peer-memory kernel, or by NCCL")
+    ap.add_argument("--no-graph", action="store_true", help="N>1: eager launches instead of the CUDA graph of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other distribution / INT8) legs")
     return ap.parse_args()
@@ -350,8 +359,8 @@ def run_single(args, cfg, peak, peak_src):
                      "traffic": ncu_traffic(f"{args.dtype}_{args.dist}"),
                      "traffic_source": "static: dram__bytes_read+write per launch from the committed ncu --set full "
                                        "capture of this kernel/config (profiles/ncu_traffic.json), not re-measured in this run",
-                     "kernel": ("msda_pack_kernel + msda_v2_kernel: the op's two launches, timed together (pack pre-pass "
-                                "included in the denominator)") if args.dtype in ("f16", "i8") and v2_on else "msda_gather_kernel",
+                     "kernel": ("msda_pack_kernel + msda_i8p_kernel: the op's two launches, timed together (pack pre-pass "
+                                "included in the denominator)") if args.dtype == "i8" and v2_on else "msda_gather_kernel",
                      "kernel_ms": k_ms, "kernel_ms_min": per[0],
                      "algorithmic_bytes": alg, "peak_source": peak_src},
         "wall_s": wall,
@@ -535,6 +544,10 @@ def run_multi(args, cfg, peak, peak_src):
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    if os.environ.get("B200_BENCH_HANG_DUMP"):  # debugging aid: stack of every thread if the run is still going after N s
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["B200_BENCH_HANG_DUMP"]), exit=True)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
@@ -567,6 +580,19 @@ def run_multi(args, cfg, peak, peak_src):
     for _ in range(max(3, args.warmup)):
         smp.step()
     torch.cuda.synchronize()
+    # CUDA graph of the step (two consecutive steps per graph: the partial buffers alternate) — only with our own exchange
+    # kernel: the step then contains no library collective, and its launch parameters never change
+    graphed = False
+    if smp.exchange == "peer" and not args.no_graph:
+        flag = torch.ones(1, device=dev)
+        try:
+            smp.capture_pair()
+            smp.step_pair()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] rank {rank}: CUDA-graph capture of the step failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+            flag.zero_()
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        graphed = flag.item() == 1
     # ---- correctness of the sharded result on hardware: owned slices gathered on rank 0 vs the single-GPU fused op
     got = smp.step().float().clone()
     rows_max = max(x.own1 - x.own0 for x in plan)
@@ -574,15 +600,24 @@ def run_multi(args, cfg, peak, peak_src):
     pad[: got.shape[0]] = got
     gathered = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
     dist.gather(pad, gathered, dst=0)
-    max_abs_vs_1gpu = None
+    max_abs_vs_1gpu = anchor_ms = None
     if rank == 0:
         full = [t.to(dev) for t in (value, shapes, ref, off, logits)]
         want = bt.multi_scale_deformable_attn_sca(*full, bev_mask.to(dev))
         err = 0.0
         for x, g in zip(plan, gathered):
-            err = max(err, (g[: x.own1 - x.own0] - want[x.own0 : x.own1]).abs().max().item())
+            err = max(err, (g[: x.own1 - x.own0] - want[x.own_queries().to(dev)]).abs().max().item())
         max_abs_vs_1gpu = err
-        del full, want
+        # the same fused step on ONE GPU (same work as the sharded step), timed like the kernel legs of the N=1 run
+        bm_d = bev_mask.to(dev)
+
+        def one_gpu_step():
+            want.zero_()
+            bt.multi_scale_deformable_attn_sca(*full, bm_d, want)
+
+        _, per1 = time_kernel(one_gpu_step, 20, 3)
+        anchor_ms = sum(per1) / len(per1)
+        del full, want, bm_d
     del value, ref, off, logits
     torch.cuda.empty_cache()
 
@@ -593,13 +628,17 @@ def run_multi(args, cfg, peak, peak_src):
     with ClockSampler(local) as clk:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(args.steps):
-            smp.step()
+        if graphed:
+            for _ in range((args.steps + 1) // 2):
+                smp.step_pair()
+        else:
+            for _ in range(args.steps):
+                smp.step()
         b.record()
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / args.steps
+        ms = a.elapsed_time(b) / (2 * ((args.steps + 1) // 2) if graphed else args.steps)
         launches = _lib.launch_count() - n0
         t0 = time.perf_counter()
         while time.perf_counter() - t0 < 0.7:
@@ -664,6 +703,8 @@ def run_multi(args, cfg, peak, peak_src):
             "dtype": "f16 storage, f32 index math + accumulate" if eb == 2 else "f32", "data": "synthetic",
             "config": workload_config(args.dist, world, False),
             "sharding": {"camera_groups": shard.groups, "query_tiles": shard.tiles,
+                         "tile_layout": (f"interleaved blocks of {shard.block} BEV queries (balances the visible (camera, query) "
+                                         "pairs between the ranks of a camera group)") if shard.block else "contiguous query ranges",
                          "per_rank": f"{shard.cam1 - shard.cam0} cameras x {shard.q1 - shard.q0} queries, one fused "
                                      "sampling launch (bev_mask camera-sum folded in) into an fp32 partial accumulator",
                          "exchange": {"peer": "b200_sca_peer_reduce: reduce-scatter inside the camera group by our kernel over "
@@ -672,6 +713,11 @@ def run_multi(args, cfg, peak, peak_src):
                                       "none": "no exchange (one camera group)"}[smp.exchange],
                          "result": f"every rank owns the final fp32 rows of {shard.own1 - shard.own0} BEV queries"},
             "max_abs_vs_1gpu": max_abs_vs_1gpu,
+            "launch_mode": ("CUDA graph replay, two steps per graph (sampling launch + exchange launch each)" if graphed
+                            else "eager launches (two per step)"),
+            "scaling_anchor": {"what": "the same fused step (all cameras, all queries, no exchange) on rank 0's GPU alone, "
+                                       "measured in this run before the sharded loop: same work as this N-GPU step",
+                               "ms_per_step": anchor_ms, "value": cfg.num_query / (anchor_ms * 1e-3), "unit": "BEV queries/s"},
             "gpu_launches": int(launches), "clocks": clk.summary(),
             "breakdown_ms": {"step": ms, "local_sampling_launch": ms_compute, "exchange_only": ms_exchange},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -718,8 +764,10 @@ def main():
 
         # (dtype, distribution, second-generation path on?) — the *_round1_kernel legs run csrc/msda.cu on the same
         # tensors (A/B of the rework); f32 has only the round-1 kernel
-        for dtype, dist_name, v2 in (("f16", "G", True), ("i8", "U", True), ("i8", "G", True), ("f16", "U", False),
-                                     ("f16", "G", False), ("i8", "U", False), ("i8", "G", False), ("f32", "U", True)):  # fmt: skip
+        # (dtype, distribution, second-generation INT8 path on?) — the i8_*_round1_kernel legs run csrc/msda.cu's gather
+        # kernel on the same INT8 tensors (A/B of the rework); FP16 / FP32 have one kernel
+        for dtype, dist_name, v2 in (("f16", "U", True), ("f16", "G", True), ("i8", "U", True), ("i8", "G", True),
+                                     ("i8", "U", False), ("i8", "G", False), ("f32", "U", True)):  # fmt: skip
             if dtype == args.dtype and dist_name == args.dist and v2:
                 continue
             from bevformer_tensorrt_b200.workloads import make_msda_inputs
@@ -736,6 +784,15 @@ def main():
                         "roofline_frac": alg / (k * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg}
             del f2, _d, h
             torch.cuda.empty_cache()
+        other = "U" if args.dist == "G" else "G"
+        o = sec.get(f"{args.dtype}_{other}")
+        if o is not None:
+            out["worst_case_U" if other == "U" else "geometry_G"] = {
+                "what": f"same op, same shapes, distribution {DIST_TEXT[other]}; per-launch CUDA events, mean of 30",
+                "value": o["bev_queries_per_s"], "unit": "BEV queries/s", "ms_per_step": o["kernel_ms"],
+                "roofline": {"bound": "hbm", "achieved": o["algorithmic_bytes"] / (o["kernel_ms"] * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": o["roofline_frac"], "traffic": ncu_traffic(f"{args.dtype}_{other}"),
+                             "algorithmic_bytes": o["algorithmic_bytes"]}}
         # fused SCA sampling (MSDA + bev_mask camera-sum into the fp32 BEV accumulator): what the
         # sharded N>1 path runs per rank, timed here on one GPU (includes zeroing the accumulator). Each distribution
         # gets ITS OWN visibility weights: U -> every camera sees every query (1/6 everywhere: the same sampling work as
@@ -772,6 +829,12 @@ def main():
                                                   "note": "offsets/logits once for all cameras; single kernel, no memset"}
             del h, hs
         torch.cuda.empty_cache()
+        anchor = sec.get(f"f16_{args.dist}_fused_sca_{'uniform' if args.dist == 'U' else 'ring'}_mask")
+        if anchor is not None and args.dtype == "f16":
+            out["scaling_anchor"] = {
+                "what": "the step bench.py --gpus N>1 runs (fused sampling + bev_mask camera sum into the fp32 BEV accumulator, "
+                        "zeroing included) on ONE GPU: same work at every N; the N=1 headline above is the plain plugin op",
+                "ms_per_step": anchor["kernel_ms"], "value": anchor["bev_queries_per_s"], "unit": "BEV queries/s"}
         sec.update(other_ops_legs(peak))
         out["secondary"] = sec
     if not args.no_ref_gpu:

@@ -480,13 +480,10 @@ static int make_weight_tmap(CUtensorMap *tm, const __half *w_r, int Co, int K) {
 template <int MH, bool I8>
 static int launch_fused(const DcnFusedParams &p, cudaStream_t stream) {
   using Cfg = FusedCfg<MH>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(dcn_fused_kernel<MH, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
-        cudaSuccess)
-      return B200_ERR_LAUNCH;
-    configured = true;
-  }
+  // per launch: the attribute is per device (and this may run on several devices / host threads); the call is cheap
+  if (cudaFuncSetAttribute(dcn_fused_kernel<MH, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
+      cudaSuccess)
+    return B200_ERR_LAUNCH;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

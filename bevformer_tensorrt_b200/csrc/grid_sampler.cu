@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256, INTERP == 2 ? 2 : 4) grid_sample_2d_kerne
       const int o_nw = cy0 * p.Wi + cx0, o_ne = cy0 * p.Wi + cx1, o_sw = cy1 * p.Wi + cx0, o_se = cy1 * p.Wi + cx1;
       const T *ip = in_n;
       T *op = out_p;
-#pragma unroll 4
+#pragma unroll 8
       for (int cp = cp0; cp < cp1; ++cp, ip += plane_i, op += plane_o) {
         float a[W], b[W], c[W], d[W], o[W];
         P::load(ip + o_nw, a, p.scale_i), P::load(ip + o_ne, b, p.scale_i);
@@ -277,10 +277,12 @@ static int launch_gs(void *out, const void *in, const void *grid, const int *od,
   const long long plane_i = static_cast<long long>(p.Di) * p.Hi * p.Wi;
   const long long plane_o = static_cast<long long>(p.Do) * p.Ho * p.Wo;
   if (plane_i >= (1ll << 31) || plane_o >= (1ll << 31)) return B200_ERR_BAD_PARAM;
-  // enough (pixel, slice) threads to fill 148 SMs a few times over, at most 16 packets per thread
+  // (pixel, slice) threads: about two resident waves of the 148 SMs (4 CTAs x 256 threads each) so that the index
+  // arithmetic of a pixel (~150 instructions) is amortised over as many channel packets as possible, at most 64 per
+  // thread; measured at the prev-BEV warp [1,256,200,200]: 8 slices x 32 channels beat 32 x 8 by 2x
   const long long pixels = static_cast<long long>(p.N) * plane_o;
   int slices = 1;
-  while (slices < p.CP && (pixels * slices < 148ll * 2048 * 4 || (p.CP + slices - 1) / slices > 16)) slices <<= 1;
+  while (slices < p.CP && (pixels * slices < 148ll * 1024 * 2 || (p.CP + slices - 1) / slices > 64)) slices <<= 1;
   p.cps = (p.CP + slices - 1) / slices;
   p.slices = (p.CP + p.cps - 1) / p.cps;
   const long long total = pixels * p.slices;

@@ -19,14 +19,14 @@ namespace b200 {
 constexpr int kMaxPeers = 8;
 
 struct PeerReduceParams {
-  const float *part[kMaxPeers];  // peer r's partial buffer of this step (index `me` = the local one)
-  uint32_t *flags[kMaxPeers];    // peer r's flag row: uint32[kMaxPeers], slot j is written by peer j
+  const float *part[2][kMaxPeers];  // [step parity][peer r]: r's partial buffer of that step (index `me` = the local one)
+  uint32_t *flags[kMaxPeers];       // peer r's flag row: uint32[kMaxPeers + 2], slot j is written by peer j
   int n, me;
-  uint32_t epoch;
+  uint32_t epoch;  // host-supplied step number, or 0: read it from the device (flags[me][kMaxPeers] + 1)
   long long elem0, elems;  // owned slice, in floats (multiples of 4)
   void *out;
   int out_half;
-  float *zero;  // local buffer of the next step (may be null)
+  float *zero[2];  // [step parity]: local buffer of the NEXT step to zero-fill (may be null)
   long long zero_elems;
 };
 
@@ -47,65 +47,133 @@ __device__ __forceinline__ float4 ld_peer(const float *p) {
 
 __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerReduceParams p) {
   const int t = threadIdx.x;
+  // Step number: from the host, or (CUDA-graph replays: identical launch parameters every step) from this rank's own
+  // counter in device memory, which the last block of the previous launch advanced.
+  uint32_t *ctr = p.flags[p.me] + kMaxPeers;  // [0] completed steps, [1] blocks done in this launch
+  const uint32_t epoch = p.epoch ? p.epoch : *reinterpret_cast<volatile uint32_t *>(ctr) + 1u;
+  const int par = static_cast<int>((epoch - 1u) & 1u);
   if (t < p.n && t != p.me) {
     if (blockIdx.x == 0) {
       __threadfence_system();
-      st_release_sys(p.flags[t] + p.me, p.epoch);
+      st_release_sys(p.flags[t] + p.me, epoch);
     }
     const uint32_t *mine = p.flags[p.me] + t;
-    while (static_cast<int32_t>(ld_acquire_sys(mine) - p.epoch) < 0) __nanosleep(64);
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) __nanosleep(32);
   }
   __syncthreads();
 
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + t;
-  for (long long i = first; i < p.elems / 4; i += stride) {
-    const long long e = p.elem0 + i * 4;
-    float4 acc = *reinterpret_cast<const float4 *>(p.part[p.me] + e);
+  const long long n4 = p.elems / 4;
+  // NVLink round trips are ~3 us: keep kUnroll x (n - 1) independent 16-byte peer loads in flight per thread
+  constexpr int kUnroll = 4;
+  for (long long i0 = first; i0 < n4; i0 += stride * kUnroll) {
+    float4 acc[kUnroll];
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r) {
-      if (r < p.n && r != p.me) {
-        const float4 v = ld_peer(p.part[r] + e);
-        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      acc[u] = i < n4 ? *reinterpret_cast<const float4 *>(p.part[par][p.me] + p.elem0 + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll 1
+    for (int r = 0; r < p.n; ++r) {
+      if (r == p.me) continue;
+      const float *src = p.part[par][r] + p.elem0;
+      float4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long i = i0 + u * stride;
+        v[u] = i < n4 ? ld_peer(src + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) acc[u].x += v[u].x, acc[u].y += v[u].y, acc[u].z += v[u].z, acc[u].w += v[u].w;
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n4) break;
+      const float4 a = acc[u];
+      if (p.out_half) {
+        const uint2 h = make_uint2(f2_to_h2(a.x, a.y), f2_to_h2(a.z, a.w));
+        *reinterpret_cast<uint2 *>(static_cast<__half *>(p.out) + i * 4) = h;
+      } else {
+        *reinterpret_cast<float4 *>(static_cast<float *>(p.out) + i * 4) = a;
       }
     }
-    if (p.out_half) {
-      uint2 h = make_uint2(f2_to_h2(acc.x, acc.y), f2_to_h2(acc.z, acc.w));
-      *reinterpret_cast<uint2 *>(static_cast<__half *>(p.out) + i * 4) = h;
-    } else {
-      *reinterpret_cast<float4 *>(static_cast<float *>(p.out) + i * 4) = acc;
+  }
+  float *zero = p.zero[par];
+  if (zero != nullptr)
+    for (long long i = first; i < p.zero_elems / 4; i += stride)
+      *reinterpret_cast<float4 *>(zero + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.epoch == 0u) {  // device-side step counter: the last block to finish advances it (every block has read it by then)
+    __syncthreads();
+    if (t == 0) {
+      __threadfence();
+      if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+        ctr[1] = 0u;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t *>(ctr) = epoch;
+      }
     }
   }
-  if (p.zero != nullptr)
-    for (long long i = first; i < p.zero_elems / 4; i += stride)
-      *reinterpret_cast<float4 *>(p.zero + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 }  // namespace b200
 
 using namespace b200;
 
+static int launch_peer_reduce(PeerReduceParams &p, cudaStream_t stream) {
+  const long long work = (p.elems > p.zero_elems ? p.elems : p.zero_elems) / 4;
+  long long blocks = (work + 255) / 256 / 4;  // 4 x 16 bytes per thread and peer in flight
+  // every block spins in the handshake: keep the grid within one wave so that no block waits behind a spinning one
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  peer_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+  return check_launch();
+}
+
 extern "C" int b200_sca_peer_reduce(const void *const *partials, void *const *flags, int group_size, int my_index,
                                     unsigned int epoch, long long first_elem, long long num_elems, void *out,
                                     int out_is_half, float *zero_next, long long zero_elems, void *stream) {
   if (!partials || !flags || !out || group_size < 1 || group_size > kMaxPeers || my_index < 0 || my_index >= group_size)
     return B200_ERR_BAD_PARAM;
+  if (epoch == 0u) return B200_ERR_BAD_PARAM;  // steps are numbered from 1
   if (first_elem < 0 || num_elems < 0 || (first_elem % 4) || (num_elems % 4) || (zero_elems % 4) || zero_elems < 0)
     return B200_ERR_BAD_PARAM;
   PeerReduceParams p{};
   for (int r = 0; r < group_size; ++r) {
     if (!partials[r] || !flags[r] || reinterpret_cast<uintptr_t>(partials[r]) % 16) return B200_ERR_BAD_PARAM;
-    p.part[r] = static_cast<const float *>(partials[r]);
+    p.part[0][r] = p.part[1][r] = static_cast<const float *>(partials[r]);
     p.flags[r] = static_cast<uint32_t *>(flags[r]);
   }
   if (reinterpret_cast<uintptr_t>(out) % 16 || reinterpret_cast<uintptr_t>(zero_next) % 16) return B200_ERR_BAD_PARAM;
   p.n = group_size, p.me = my_index, p.epoch = epoch, p.elem0 = first_elem, p.elems = num_elems;
-  p.out = out, p.out_half = out_is_half, p.zero = zero_next, p.zero_elems = zero_next ? zero_elems : 0;
-  const long long work = (num_elems > p.zero_elems ? num_elems : p.zero_elems) / 4;
-  long long blocks = (work + 255) / 256;
-  // every block spins in the handshake: keep the grid within one wave so that no block waits behind a spinning one
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  if (blocks < 1) blocks = 1;
-  peer_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  return check_launch();
+  p.out = out, p.out_half = out_is_half, p.zero[0] = p.zero[1] = zero_next, p.zero_elems = zero_next ? zero_elems : 0;
+  return launch_peer_reduce(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_sca_peer_reduce_auto(const void *const *partials_even, const void *const *partials_odd,
+                                         void *const *flags, int group_size, int my_index, long long first_elem,
+                                         long long num_elems, void *out, int out_is_half, long long zero_elems,
+                                         void *stream) {
+  if (!partials_even || !partials_odd || !flags || !out || group_size < 1 || group_size > kMaxPeers || my_index < 0 ||
+      my_index >= group_size)
+    return B200_ERR_BAD_PARAM;
+  if (first_elem < 0 || num_elems < 0 || (first_elem % 4) || (num_elems % 4) || (zero_elems % 4) || zero_elems < 0)
+    return B200_ERR_BAD_PARAM;
+  PeerReduceParams p{};
+  for (int r = 0; r < group_size; ++r) {
+    if (!partials_even[r] || !partials_odd[r] || !flags[r] || reinterpret_cast<uintptr_t>(partials_even[r]) % 16 ||
+        reinterpret_cast<uintptr_t>(partials_odd[r]) % 16)
+      return B200_ERR_BAD_PARAM;
+    p.part[0][r] = static_cast<const float *>(partials_even[r]);  // steps 1, 3, 5, ... ((step - 1) & 1 == 0)
+    p.part[1][r] = static_cast<const float *>(partials_odd[r]);
+    p.flags[r] = static_cast<uint32_t *>(flags[r]);
+  }
+  if (reinterpret_cast<uintptr_t>(out) % 16) return B200_ERR_BAD_PARAM;
+  p.n = group_size, p.me = my_index, p.epoch = 0u, p.elem0 = first_elem, p.elems = num_elems;
+  p.out = out, p.out_half = out_is_half, p.zero_elems = zero_elems;
+  // after reducing the buffer of parity k, zero the OTHER buffer: it is the next step's accumulator
+  p.zero[0] = zero_elems ? const_cast<float *>(p.part[1][my_index]) : nullptr;
+  p.zero[1] = zero_elems ? const_cast<float *>(p.part[0][my_index]) : nullptr;
+  return launch_peer_reduce(p, static_cast<cudaStream_t>(stream));
 }

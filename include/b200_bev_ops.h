@@ -150,11 +150,20 @@ int b200_msda_i8_ws(const int8_t *value, float scale_value, const int32_t *spati
  * the kernel starts; (2) out[i] = sum_r partials[r][first_elem + i], peers read directly over NVLink; (3) zero-fills
  * `zero_next` (the local partial buffer of the NEXT step; partials are double-buffered by step parity).
  *   partials / flags: HOST arrays of `group_size` DEVICE pointers (peer-mapped: torch symmetric memory / cudaIpc);
- *   flags[r] is uint32[8], zero-initialised; epoch starts at 1 and increases by 1 per step on every rank;
+ *   flags[r] is uint32[10], zero-initialised; epoch starts at 1 and increases by 1 per step on every rank;
  *   out: float (out_is_half == 0) or __half [num_elems]; element counts are multiples of 4. */
 int b200_sca_peer_reduce(const void *const *partials, void *const *flags, int group_size, int my_index,
                          unsigned int epoch, long long first_elem, long long num_elems, void *out, int out_is_half,
                          float *zero_next, long long zero_elems, void *stream);
+/* The same kernel with the step number kept ON THE DEVICE (flags[my_index][8] counts completed steps; the last block of
+ * a launch advances it), so that every step's launch has identical parameters and the whole step — sampling launch +
+ * this launch — can be captured once into a CUDA graph and replayed. Step s (1, 2, ...) reduces partials_even when
+ * s is odd and partials_odd when s is even (the buffers alternate), and zero-fills the OTHER local buffer (zero_elems
+ * floats; 0 = do not zero). flags[r] is uint32[10], zero-initialised. */
+int b200_sca_peer_reduce_auto(const void *const *partials_even, const void *const *partials_odd, void *const *flags,
+                              int group_size, int my_index, long long first_elem, long long num_elems, void *out,
+                              int out_is_half, long long zero_elems, void *stream);
+
 
 /* Trace entries: b200_msda_f32 / _f16 / _i8 with the production kernel's trace switch on (the same kernel template,
  * compiled with one extra store): besides `out` they write, for every (batch, query, head, level*point), the

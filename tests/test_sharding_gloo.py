@@ -125,8 +125,8 @@ def test_grid_plan_covers_and_owns_every_query_once(world):
     cover = np.zeros((6, 40000), np.int32)
     owned = np.zeros(40000, np.int32)
     for s in plan:
-        cover[s.cam0 : s.cam1, s.q0 : s.q1] += 1
-        owned[s.own0 : s.own1] += 1
+        cover[s.cam0 : s.cam1, s.tile_queries().numpy()] += 1
+        owned[s.own_queries().numpy()] += 1
         assert s.q0 <= s.own0 <= s.own1 <= s.q1 and s.rank in s.peers and len(s.peers) == A
         assert (s.own0 - s.q0) % 4 == 0  # float4 granularity of the exchange kernel at width 256
         for r in s.peers:  # the ranks of a camera group share the query tile
@@ -134,6 +134,21 @@ def test_grid_plan_covers_and_owns_every_query_once(world):
     assert (cover == 1).all() and (owned == 1).all()
     loads = [(s.cam1 - s.cam0) * (s.q1 - s.q0) for s in plan]
     assert max(loads) - min(loads) <= 8 * 6
+
+
+def test_interleaved_tiles_balance_the_camera_ring():
+    """Visible (camera, query) pairs per rank on the synthetic camera ring: contiguous query ranges are badly skewed
+    (a camera sees a compact wedge of the BEV), interleaved 8-query blocks are balanced."""
+    from bevformer_tensorrt_b200.workloads import bev_reference_points_cam, camera_ring_lidar2img
+
+    _, mask = bev_reference_points_cam((200, 200), camera_ring_lidar2img(6))
+    vis = mask[..., 0] > 0
+    for world in (4, 8):
+        for block, bound in ((0, 1.5), (8, 1.01)):
+            plan = plan_grid(6, 40000, world, block=block)
+            loads = [int(vis[s.cam0 : s.cam1][:, s.tile_queries()].sum()) for s in plan]
+            ratio = max(loads) / (sum(loads) / world)
+            assert (ratio > bound) if block == 0 else (ratio < bound), (world, block, ratio)
 
 
 def test_grid_plan_traffic_is_minimal_for_even_worlds():
@@ -146,7 +161,7 @@ def test_grid_plan_traffic_is_minimal_for_even_worlds():
 
 def _oracle_fused(value, shapes, ref, off, logits, mask, accum):
     out = _oracle_op(value, shapes, ref, off, logits)
-    accum += (out.reshape(value.shape[0], accum.shape[0], -1) * mask).sum(0)
+    accum += (out.reshape(value.shape[0], accum.shape[0], -1) * mask.reshape(value.shape[0], accum.shape[0], 1)).sum(0)
     return accum
 
 
@@ -162,8 +177,8 @@ def _grid_worker(rank, world, port, q):
     errs = []
     for _ in range(3):  # repeated steps: the partial is re-zeroed, the result does not drift
         got = smp.step()
-        errs.append(float((got - want[s.own0 : s.own1]).abs().max()))
-    q.put((rank, max(errs), float(want[s.own0 : s.own1].abs().max()), got.shape[0]))
+        errs.append(float((got - want[s.own_queries()]).abs().max()))
+    q.put((rank, max(errs), float(want[s.own_queries()].abs().max()), got.shape[0]))
     dist.destroy_process_group()
 
 
