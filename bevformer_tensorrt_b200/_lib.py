@@ -82,6 +82,7 @@ SIGNATURES = {
     "b200_dcn_f16": (_i, [_vp] * 7 + [_i] * 16 + [_vp, _vp]),
     "b200_dcn_f16_chw2": (_i, [_vp] * 7 + [_i] * 16 + [_vp, _vp]),
     "b200_dcn_f16_chw2_workspace_size": (ctypes.c_size_t, [_i] * 15),
+    "b200_grid_sample_set_tile_path": (_i, [_i]),
     "b200_grid_sample_f32": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
     "b200_grid_sample_f16": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),
     "b200_grid_sample_f16_chw2": (_i, [_vp, _vp, _vp, _ip, _ip, _ip, _i, _i, _i, _i, _vp]),

@@ -555,27 +555,36 @@ int dcn_pack_weights_f16(const __half *weight, __half *packed, int channels_out,
 }
 
 // ---- INT8 flavour: pre-passes + launch ---------------------------------------------------------------------------------
-// input kCHW4 int8 [B, C/4, H, W, 4] -> NHWC fp16 (the int8 values as exact fp16 integers)
+// input kCHW4 int8 [B, C/4, H, W, 4] -> NHWC fp16 (the int8 values as exact fp16 integers): 64 pixels x 64 channels per
+// block through shared memory, so that both sides are coalesced (reads: 64 consecutive pixels of a channel quad = 256
+// contiguous bytes; writes: the 64 channels of a pixel = one 128-byte row)
 __global__ void __launch_bounds__(256) dcn_chw4_to_nhwc_f16_kernel(const int8_t *__restrict__ in, __half *__restrict__ out,
                                                                    int C, int HW) {
-  // thread = (pixel, group of 8 channels = two CHW4 packs): two 4-byte loads, one 16-byte store
-  const long long total = static_cast<long long>(gridDim.z) * HW * (C / 8);
-  (void)total;
-  const int b = blockIdx.z;
-  const int c8 = blockIdx.y;  // group of 8 channels
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
-  const uint32_t *src = reinterpret_cast<const uint32_t *>(in) + (static_cast<long long>(b) * (C / 4) + 2 * c8) * HW + p;
-  const uint32_t u0 = __ldg(src), u1 = __ldg(src + HW);
-  uint32_t o[4];
+  __shared__ uint32_t tile[16][65];  // [channel quad][pixel], 65: the transposed reads below are conflict-free
+  const int b = blockIdx.z, p0 = blockIdx.x * 64, q0 = blockIdx.y * 16;
+  const int t = threadIdx.x;
+  {
+    const int quad = t >> 4, pj = (t & 15) * 4;  // 16 quads x 16 groups of 4 pixels
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(in) + (static_cast<long long>(b) * (C / 4) + q0 + quad) * HW + p0 + pj;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    o[i] = f2_to_h2(static_cast<float>(static_cast<int8_t>(u0 >> (16 * i))),
-                    static_cast<float>(static_cast<int8_t>(u0 >> (16 * i + 8))));
-    o[2 + i] = f2_to_h2(static_cast<float>(static_cast<int8_t>(u1 >> (16 * i))),
-                        static_cast<float>(static_cast<int8_t>(u1 >> (16 * i + 8))));
+    for (int i = 0; i < 4; ++i) tile[quad][pj + i] = (p0 + pj + i < HW) ? __ldg(src + i) : 0u;
   }
-  *reinterpret_cast<uint4 *>(out + (static_cast<long long>(b) * HW + p) * C + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  __syncthreads();
+  {
+    const int pp = t >> 2, cj = t & 3;  // 64 pixels x 4 chunks of 16 channels
+    if (p0 + pp < HW) {
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t u = tile[cj * 4 + i][pp];
+        o[2 * i] = f2_to_h2(static_cast<float>(static_cast<int8_t>(u)), static_cast<float>(static_cast<int8_t>(u >> 8)));
+        o[2 * i + 1] = f2_to_h2(static_cast<float>(static_cast<int8_t>(u >> 16)), static_cast<float>(static_cast<int8_t>(u >> 24)));
+      }
+      uint4 *dst = reinterpret_cast<uint4 *>(out + (static_cast<long long>(b) * HW + p0 + pp) * C + q0 * 4 + cj * 16);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
 }
 
 // weight kCHW4 int8 [Co, C/4, kh, kw, 4] -> Wr fp16 [Co][C/64][t][64]
@@ -611,7 +620,7 @@ int dcn_fused_i8(const int8_t *input, float scale_i, const int8_t *weight, float
   ws += (static_cast<size_t>(channels_out) * channels * kk * 2 + 255) / 256 * 256;
   float *bias_f = reinterpret_cast<float *>(ws);  // 512 floats fit the 2 KB tail reserved by dcn_fused_workspace_bytes
 
-  dcn_chw4_to_nhwc_f16_kernel<<<dim3((HW + 255) / 256, channels / 8, batch), 256, 0, stream>>>(input, x_nhwc, channels, HW);
+  dcn_chw4_to_nhwc_f16_kernel<<<dim3((HW + 63) / 64, channels / 64, batch), 256, 0, stream>>>(input, x_nhwc, channels, HW);
   int st = check_launch();
   if (st != B200_OK) return st;
   const long long wn = static_cast<long long>(channels_out) * channels * kk;

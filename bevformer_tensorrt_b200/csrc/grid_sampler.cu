@@ -14,6 +14,8 @@
 // INT8 kernel leaves out-of-image taps uninitialised (:1140-1176); neither is reproduced.
 #include <climits>
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 #include "packets.cuh"
 
@@ -188,6 +190,175 @@ __global__ void __launch_bounds__(256, INTERP == 2 ? 2 : 4) grid_sample_2d_kerne
   }
 }
 
+// ---- 2-D bilinear fast path: source window staged in shared memory by TMA bulk copies ---------------------------------
+// The generic kernel above pays ~30 instructions per output element, two thirds of them 64-bit address arithmetic for
+// four scattered 2/4-byte loads that each wait a full L2 round trip. For a smooth sampling grid (the prev-BEV warp is a
+// small rotation, onnx_ops.py:226-232) the source pixels of an 8 x 32 output tile form a compact window. One CTA = one
+// output tile x one block of channel packets:
+//   1. every thread evaluates the index arithmetic of its pixel (the same device functions as the generic kernel: the
+//      sampled pixel is bit-identical), and the CTA reduces the bounding box of the clamped tap coordinates;
+//   2. if the box fits kBH rows x kRowBytes, warp 0 issues one bulk copy (cp.async.bulk, SASS UBLKCP: 16-byte aligned row
+//      segments of the planar layout) per (channel packet, row) into shared memory, completion counted on one mbarrier;
+//      otherwise the CTA runs the generic per-tap global loads;
+//   3. each packet is then 4 shared-memory loads at compile-time channel offsets + 4 FMAs + one coalesced store.
+// (A cp.async.bulk.tensor variant — 3-D box, then one 2-D box per packet — assembled to UTMALDG but raised "illegal
+// instruction" on the B200 boxes for window origins that are not 16-byte aligned; the 1-D bulk copies below align the
+// segment start themselves. gpurun r02q-r02s.)
+constexpr int kTW = 32, kTH = 8;  // output tile (a warp = 32 consecutive x)
+constexpr int kBH = 16;           // source window rows held in shared memory
+
+template <int K>
+struct TileCfg {
+  using T = typename Pk<K>::T;
+  static constexpr int kEB = static_cast<int>(sizeof(T));
+  static constexpr int kCB = kEB == 2 ? 32 : 16;                   // packets per CTA
+  static constexpr int kRowBytes = kEB == 2 ? 96 : 176;            // 48 halves / 44 words per window row (incl. alignment slack)
+  static constexpr int kRowElems = kRowBytes / kEB;
+  static constexpr int kSmem = kCB * kBH * kRowBytes;              // 48 KB / 44 KB
+};
+
+template <int K, bool TENSOR>
+__global__ void __launch_bounds__(256, 4) grid_sample_2d_tile_kernel(const GsParams p, const __grid_constant__ CUtensorMap tmap,
+                                                                     int tiles_x) {
+  using P = Pk<K>;
+  using T = typename P::T;
+  using Cfg = TileCfg<K>;
+  constexpr int W = P::W;
+  constexpr int CB = Cfg::kCB, EB = Cfg::kEB, RE = Cfg::kRowElems;
+  extern __shared__ __align__(128) unsigned char gs_smem[];
+  __shared__ int red[8][4];
+  __shared__ int fin[4];
+  __shared__ __align__(8) unsigned long long bar;
+  const T *win = reinterpret_cast<const T *>(gs_smem);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int ox = tx * kTW + lane, oy = ty * kTH + warp;
+  const int n = blockIdx.z, cp0 = blockIdx.y * CB, cp1 = min(p.CP, cp0 + CB);
+  const bool valid = ox < p.Wo && oy < p.Ho;
+  const long long plane_o = static_cast<long long>(p.Ho) * p.Wo, plane_i = static_cast<long long>(p.Hi) * p.Wi;
+  const long long pix = static_cast<long long>(oy) * p.Wo + ox;
+  const bool align = p.align != 0;
+  const float so = K == kI8x4 ? 1.f / p.scale_o : 1.f;
+
+  float w_nw = 0.f, w_ne = 0.f, w_sw = 0.f, w_se = 0.f;
+  int cx0 = INT_MAX, cx1 = INT_MIN, cy0 = INT_MAX, cy1 = INT_MIN;
+  if (valid) {
+    float gx, gy, gz;
+    P::grid_xy(p.grid, plane_o, pix, n, p.scale_g, gx, gy, gz, false);
+    const float ix = gs_source_index(gx, p.Wi, p.padding, align);
+    const float iy = gs_source_index(gy, p.Hi, p.padding, align);
+    const int ix_nw = static_cast<int>(floorf(ix)), iy_nw = static_cast<int>(floorf(iy));
+    const int ix_se = ix_nw + 1, iy_se = iy_nw + 1;
+    const float fx1 = __fsub_rn(static_cast<float>(ix_se), ix), fx0 = __fsub_rn(ix, static_cast<float>(ix_nw));
+    const float fy1 = __fsub_rn(static_cast<float>(iy_se), iy), fy0 = __fsub_rn(iy, static_cast<float>(iy_nw));
+    const bool x0 = ix_nw >= 0 && ix_nw < p.Wi, x1 = ix_se >= 0 && ix_se < p.Wi;
+    const bool y0 = iy_nw >= 0 && iy_nw < p.Hi, y1 = iy_se >= 0 && iy_se < p.Hi;
+    w_nw = (x0 && y0) ? fx1 * fy1 : 0.f, w_ne = (x1 && y0) ? fx0 * fy1 : 0.f;
+    w_sw = (x0 && y1) ? fx1 * fy0 : 0.f, w_se = (x1 && y1) ? fx0 * fy0 : 0.f;
+    // out-of-image taps carry weight 0 and alias an in-image pixel (clamped), so loads are unconditional
+    cx0 = min(max(ix_nw, 0), p.Wi - 1), cx1 = min(max(ix_se, 0), p.Wi - 1);
+    cy0 = min(max(iy_nw, 0), p.Hi - 1), cy1 = min(max(iy_se, 0), p.Hi - 1);
+  }
+  // ---- bounding box of the tile's taps
+  int bx0 = min(cx0, cx1), bx1 = max(cx0, cx1), by0 = min(cy0, cy1), by1 = max(cy0, cy1);
+  if (!valid) bx0 = by0 = INT_MAX, bx1 = by1 = INT_MIN;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    bx0 = min(bx0, __shfl_xor_sync(kFullMask, bx0, d)), bx1 = max(bx1, __shfl_xor_sync(kFullMask, bx1, d));
+    by0 = min(by0, __shfl_xor_sync(kFullMask, by0, d)), by1 = max(by1, __shfl_xor_sync(kFullMask, by1, d));
+  }
+  if (lane == 0) red[warp][0] = bx0, red[warp][1] = bx1, red[warp][2] = by0, red[warp][3] = by1;
+  const uint32_t barr = static_cast<uint32_t>(__cvta_generic_to_shared(&bar));
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barr) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // warp 0 finishes the reduction and, if the window fits, issues the row copies (segment start rounded down to 16 bytes)
+  if (warp == 0) {
+    const int w8 = lane & 7;
+    bx0 = __reduce_min_sync(kFullMask, red[w8][0]), bx1 = __reduce_max_sync(kFullMask, red[w8][1]);
+    by0 = __reduce_min_sync(kFullMask, red[w8][2]), by1 = __reduce_max_sync(kFullMask, red[w8][3]);
+    const int xs = bx0 & ~(16 / EB - 1);
+    const int len = ((bx1 - xs + 1) * EB + 15) & ~15, nrows = by1 - by0 + 1, ncp = cp1 - cp0;
+    const bool fits0 = bx1 >= bx0 && len <= Cfg::kRowBytes && nrows <= kBH;
+    if (lane == 0) fin[0] = xs, fin[1] = by0, fin[2] = fits0 ? 1 : 0;
+    if (fits0 && TENSOR) {
+      // one 2-D tensor copy per channel packet: box = kRowElems columns x kBH rows of the [N*CP*Hi, Wi] view, origin
+      // (xs, plane row + by0) with xs * EB a multiple of 16 bytes; columns past the image are zero-filled, rows past the
+      // plane belong to the next plane (never read: the window is inside the image)
+      if (lane == 0) {
+        const uint32_t dst0 = static_cast<uint32_t>(__cvta_generic_to_shared(gs_smem));
+        const int row0 = (n * p.CP + cp0) * p.Hi + by0;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barr), "r"(ncp * kBH * Cfg::kRowBytes) : "memory");
+#pragma unroll 1
+        for (int c = 0; c < ncp; ++c)
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                  dst0 + c * (kBH * Cfg::kRowBytes)),
+              "l"(&tmap), "r"(xs), "r"(row0 + c * p.Hi), "r"(barr)
+              : "memory");
+      }
+    } else if (fits0) {
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barr), "r"(ncp * nrows * len) : "memory");
+      __syncwarp();
+      const unsigned char *src0 = static_cast<const unsigned char *>(p.in) +
+                                  ((static_cast<long long>(n) * p.CP + cp0) * plane_i + static_cast<long long>(by0) * p.Wi + xs) * EB;
+      const uint32_t dst0 = static_cast<uint32_t>(__cvta_generic_to_shared(gs_smem));
+      for (int i = lane; i < ncp * nrows; i += 32) {
+        const int c = i / nrows, r = i - c * nrows;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         dst0 + (c * kBH + r) * Cfg::kRowBytes),
+                     "l"(src0 + (c * plane_i + static_cast<long long>(r) * p.Wi) * EB), "r"(len), "r"(barr)
+                     : "memory");
+      }
+    }
+  }
+  __syncthreads();
+  const int xs = fin[0];
+  by0 = fin[1];
+  const bool fits = fin[2] != 0;  // CTA-uniform
+  T *out_p = static_cast<T *>(p.out) + (static_cast<long long>(n) * p.CP + cp0) * plane_o + pix;
+
+  if (fits) {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                   : "=r"(done) : "r"(barr), "r"(0u) : "memory");
+    if (valid) {
+      const int o_nw = (cy0 - by0) * RE + (cx0 - xs), o_ne = (cy0 - by0) * RE + (cx1 - xs);
+      const int o_sw = (cy1 - by0) * RE + (cx0 - xs), o_se = (cy1 - by0) * RE + (cx1 - xs);
+      const int ncp = cp1 - cp0;
+#pragma unroll 8
+      for (int c = 0; c < CB; ++c) {
+        if (c >= ncp) break;
+        const T *wc = win + c * (kBH * RE);
+        float a[W], b[W], cc[W], d[W], o[W];
+        P::unpack(wc[o_nw], a, p.scale_i), P::unpack(wc[o_ne], b, p.scale_i);
+        P::unpack(wc[o_sw], cc, p.scale_i), P::unpack(wc[o_se], d, p.scale_i);
+#pragma unroll
+        for (int i = 0; i < W; ++i) o[i] = fmaf(d[i], w_se, fmaf(cc[i], w_sw, fmaf(b[i], w_ne, a[i] * w_nw)));
+        P::store(out_p + c * plane_o, o, so);
+      }
+    }
+  } else if (valid) {  // window too large for shared memory (a strongly distorted grid): per-tap global loads
+    const T *ip = static_cast<const T *>(p.in) + (static_cast<long long>(n) * p.CP + cp0) * plane_i;
+    const int o_nw = cy0 * p.Wi + cx0, o_ne = cy0 * p.Wi + cx1, o_sw = cy1 * p.Wi + cx0, o_se = cy1 * p.Wi + cx1;
+    T *op = out_p;
+#pragma unroll 4
+    for (int cp = cp0; cp < cp1; ++cp, ip += plane_i, op += plane_o) {
+      float a[W], b[W], cc[W], d[W], o[W];
+      P::load(ip + o_nw, a, p.scale_i), P::load(ip + o_ne, b, p.scale_i);
+      P::load(ip + o_sw, cc, p.scale_i), P::load(ip + o_se, d, p.scale_i);
+#pragma unroll
+      for (int i = 0; i < W; ++i) o[i] = fmaf(d[i], w_se, fmaf(cc[i], w_sw, fmaf(b[i], w_ne, a[i] * w_nw)));
+      P::store(op, o, so);
+    }
+  }
+}
+
 // ---- 3-D kernel (GridSampler3DTRT, :1271-1923): trilinear / nearest, fp32 / fp16 kLINEAR ----------------------------
 template <int K>
 __global__ void __launch_bounds__(256) grid_sample_3d_kernel(const GsParams p) {
@@ -253,6 +424,52 @@ __global__ void __launch_bounds__(256) grid_sample_3d_kernel(const GsParams p) {
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------------
+static std::atomic<int> g_gs_tile{0};  // 1: shared-memory tile path for 2-D bilinear where it applies (b200_grid_sample_set_tile_path)
+
+typedef CUresult (*GsEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// B200_ERR_UNSUPPORTED = the layout does not meet the copies' 16-byte rules (the caller takes the generic kernel).
+// mode 1: one bulk copy per (packet, row); mode 2: one 2-D tensor copy per packet.
+template <int K>
+static int launch_gs_tile(const GsParams &p, int mode, cudaStream_t s) {
+  using Cfg = TileCfg<K>;
+  if (reinterpret_cast<uintptr_t>(p.in) % 16 || (static_cast<long long>(p.Wi) * Cfg::kEB) % 16) return B200_ERR_UNSUPPORTED;
+  if (p.N > 65535 || static_cast<long long>(p.N) * p.CP * p.Hi >= (1ll << 31)) return B200_ERR_UNSUPPORTED;
+  const int tiles_x = (p.Wo + kTW - 1) / kTW, tiles_y = (p.Ho + kTH - 1) / kTH;
+  const long long tiles = static_cast<long long>(tiles_x) * tiles_y;
+  const int cblocks = (p.CP + Cfg::kCB - 1) / Cfg::kCB;
+  if (tiles > 0x7fffffffll || cblocks > 65535) return B200_ERR_UNSUPPORTED;
+  CUtensorMap tm{};
+  if (mode == 2) {
+    static std::atomic<GsEncodeTiledFn> cached{nullptr};
+    GsEncodeTiledFn encode = cached.load(std::memory_order_acquire);
+    if (!encode) {
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+        return B200_ERR_UNSUPPORTED;
+      encode = reinterpret_cast<GsEncodeTiledFn>(fn);
+      cached.store(encode, std::memory_order_release);
+    }
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.Wi), static_cast<cuuint64_t>(p.N) * p.CP * p.Hi};
+    const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(p.Wi) * Cfg::kEB};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(Cfg::kRowElems), kBH};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = Cfg::kEB == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (encode(&tm, dt, 2, const_cast<void *>(p.in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return B200_ERR_UNSUPPORTED;
+  }
+  auto launch = [&](auto kern) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess) return B200_ERR_LAUNCH;
+    kern<<<dim3(static_cast<unsigned>(tiles), cblocks, p.N), 256, Cfg::kSmem, s>>>(p, tm, tiles_x);
+    return check_launch();
+  };
+  return mode == 2 ? launch(grid_sample_2d_tile_kernel<K, true>) : launch(grid_sample_2d_tile_kernel<K, false>);
+}
+
 template <int K>
 static int launch_gs(void *out, const void *in, const void *grid, const int *od, const int *id, const int *gd, int nb,
                      int interp, int padding, int align, float si, float sg, float so, cudaStream_t s) {
@@ -277,6 +494,10 @@ static int launch_gs(void *out, const void *in, const void *grid, const int *od,
   const long long plane_i = static_cast<long long>(p.Di) * p.Hi * p.Wi;
   const long long plane_o = static_cast<long long>(p.Do) * p.Ho * p.Wo;
   if (plane_i >= (1ll << 31) || plane_o >= (1ll << 31)) return B200_ERR_BAD_PARAM;
+  if (nb == 4 && interp == 0 && g_gs_tile.load(std::memory_order_relaxed)) {
+    const int st = launch_gs_tile<K>(p, g_gs_tile.load(std::memory_order_relaxed), s);
+    if (st != B200_ERR_UNSUPPORTED) return st;
+  }
   // (pixel, slice) threads: about two resident waves of the 148 SMs (4 CTAs x 256 threads each) so that the index
   // arithmetic of a pixel (~150 instructions) is amortised over as many channel packets as possible, at most 64 per
   // thread; measured at the prev-BEV warp [1,256,200,200]: 8 slices x 32 channels beat 32 x 8 by 2x
@@ -304,6 +525,8 @@ static int launch_gs(void *out, const void *in, const void *grid, const int *od,
 using namespace b200;
 
 extern "C" {
+
+int b200_grid_sample_set_tile_path(int mode) { return g_gs_tile.exchange(mode < 0 || mode > 2 ? 0 : mode); }
 
 int b200_grid_sample_f32(float *output, const float *input, const float *grid, const int *output_dims,
                          const int *input_dims, const int *grid_dims, int nb_dims, int interp, int padding,

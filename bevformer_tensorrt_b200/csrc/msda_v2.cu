@@ -204,7 +204,7 @@ __device__ __forceinline__ uint4 lds128_v2(uint32_t addr) {
 }
 
 #ifndef B200_I8_WARPS
-#define B200_I8_WARPS 24
+#define B200_I8_WARPS 32
 #endif
 constexpr int kI8Warps = B200_I8_WARPS;
 constexpr int kI8Threads = kI8Warps * 32;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) msda_i8p_kernel(const I8PParams
       for (int d = 1; d < 8; d <<= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, d));
       float sum = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) lg[k] = expf(lg[k] - mx), sum += lg[k];
+      for (int k = 0; k < 4; ++k) lg[k] = __expf(lg[k] - mx), sum += lg[k];  // ex2.approx: 2 ulp, far below the INT8 steps
 #pragma unroll
       for (int d = 1; d < 8; d <<= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
 

@@ -16,6 +16,7 @@ template <>
 struct Pk<kF32> {
   using T = float;
   static constexpr int W = 1;
+  __device__ static void unpack(T raw, float (&v)[1], float) { v[0] = raw; }
   __device__ static void load(const T *p, float (&v)[1], float) { v[0] = __ldg(p); }
   __device__ static void store(T *p, const float (&v)[1], float) { *p = v[0]; }
   __device__ static void grid_xy(const void *g, long long plane, long long pix, long long n, float, float &x, float &y,
@@ -28,6 +29,7 @@ template <>
 struct Pk<kF16> {
   using T = __half;
   static constexpr int W = 1;
+  __device__ static void unpack(T raw, float (&v)[1], float) { v[0] = __half2float(raw); }
   __device__ static void load(const T *p, float (&v)[1], float) { v[0] = __half2float(__ldg(p)); }
   __device__ static void store(T *p, const float (&v)[1], float) { *p = __float2half_rn(v[0]); }
   __device__ static void grid_xy(const void *g, long long plane, long long pix, long long n, float, float &x, float &y,
@@ -41,6 +43,10 @@ template <>
 struct Pk<kF16x2> {  // kCHW2: [N, ceil(C/2), H, W, 2]; the 2-channel grid is one (x, y) pair per pixel (:946-961)
   using T = uint32_t;
   static constexpr int W = 2;
+  __device__ static void unpack(T raw, float (&v)[2], float) {
+    const float2 f = h2_to_f2(raw);
+    v[0] = f.x, v[1] = f.y;
+  }
   __device__ static void load(const T *p, float (&v)[2], float) {
     const float2 f = h2_to_f2(__ldg(p));
     v[0] = f.x, v[1] = f.y;
@@ -56,6 +62,10 @@ template <>
 struct Pk<kI8x4> {  // kCHW4: [N, ceil(C/4), H, W, 4]; grid = (x, y, pad, pad) int8 per pixel (:1088-1103)
   using T = uint32_t;
   static constexpr int W = 4;
+  __device__ static void unpack(T raw, float (&v)[4], float s) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = static_cast<float>(static_cast<int8_t>(raw >> (8 * i))) * s;
+  }
   __device__ static void load(const T *p, float (&v)[4], float s) {
     const uint32_t u = __ldg(p);
 #pragma unroll

@@ -250,6 +250,11 @@ int b200_msda_supports_format(int pos, const b200_tensor_desc *in_out, int nb_in
  * ---------------------------------------------------------------------------------------------------------- */
 
 /* replaces grid_sample<float>   — gridSamplerKernel.h:14-18, .cu:1933-1964 */
+/* 2-D bilinear sampling runs a tile kernel by default (source window of an 8 x 32 output tile staged in shared memory by
+ * TMA bulk copies, one per channel packet and row; falls back per tile to scattered loads when the window does not fit,
+ * and per call when the layout does not meet the copies' 16-byte rules: input pointer and row pitch). 0 = always the
+ * generic kernel. Same results bit for bit. Returns the previous setting. */
+int b200_grid_sample_set_tile_path(int on);
 int b200_grid_sample_f32(float *output, const float *input, const float *grid, const int *output_dims,
                          const int *input_dims, const int *grid_dims, int nb_dims, int interp, int padding,
                          int align_corners, void *stream);

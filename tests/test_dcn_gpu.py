@@ -1,7 +1,9 @@
 """GPU parity tests for DCNv2 (pytest -m gpu). Checkers: oracle/dcn (reference im2col restated + fp64-accumulated GEMM),
 torchvision.ops.deform_conv2d on the GPU at larger sizes, and the reference's own CUDA launcher in oracle/_ref.
-Tolerances: FP32 1e-4 relative to max|out| (GEMM summation order); FP16 5e-3 absolute on O(1) outputs (the reference's
-own FP16 bar is mean-abs 0.05, test_modulated_deformable_conv2d.py:100-103)."""
+Tolerances: FP32 1e-4 relative to max|out| (GEMM summation order). FP16, against the FP32 formulas evaluated on the
+FP16-rounded inputs: half an FP16 spacing of the largest |out| (the output rounding no FP16-out kernel can avoid; 1.95e-3
+for |out| in [4, 8)) + north_star's 1e-3 for everything before it (`fp16_tol`; measured 1e-4..2e-4 of the 1e-3 are used).
+The reference's own FP16 bar is mean-abs 0.05 (test_modulated_deformable_conv2d.py:100-103)."""
 import ctypes
 import os
 
@@ -10,6 +12,11 @@ import pytest
 import torch
 
 import bevformer_tensorrt_b200 as bt
+
+
+def fp16_tol(want):
+    """FP16-output error budget: 0.5 * spacing_fp16(max|want|) + 1e-3 (see the module docstring)."""
+    return 0.5 * float(np.spacing(np.float16(np.abs(want).max()))) + 1e-3
 from bevformer_tensorrt_b200 import _lib
 from oracle import REF_LIB
 from oracle import dcn as odcn
@@ -52,7 +59,11 @@ def test_fp16_fused_tcgen05_path_matches_oracle_and_gather_gemm_path(case):
         plain = _call(bt.modulated_deformable_conv2d, x, off, mask, w, b, kw)
     finally:
         lib.b200_dcn_set_fused(prev)
-    tol = 5e-3 * max(1.0, np.abs(want).max())
+    # Error budget (FP16 in, FP16 out, FP32 accumulation over K = kh*kw*C): (1) the FP16 rounding of the OUTPUT, half a
+    # spacing of the largest |out| — unavoidable, 1.95e-3 at |out| in [4, 8) — plus (2) everything before it: FP16
+    # columns (the reference's im2col buffer is FP16 too, …Conv2dKernel.cu:321-388) and the packed-HFMA2 corner blend,
+    # both 2^-11 relative per term and averaged over K >= 576 terms, measured 1e-4 .. 2e-4; north_star's 1e-3 covers (2).
+    tol = fp16_tol(want)
     print(f"[dcn fp16 {case}] max|want| {np.abs(want).max():.3f}  err fused {np.abs(fused.float().cpu().numpy() - want).max():.2e}"
           f"  err generic {np.abs(plain.float().cpu().numpy() - want).max():.2e}  fp16 spacing at max "
           f"{np.spacing(np.float16(np.abs(want).max())):.2e}")
@@ -152,7 +163,7 @@ def test_fp16_matches_oracle(case):
     got = _call(bt.modulated_deformable_conv2d, x, off, mask, w, b, kw)
     assert got.dtype == torch.float16
     err = np.abs(got.float().cpu().numpy() - want).max()
-    assert err < 5e-3 * max(1.0, np.abs(want).max()), (case, err)
+    assert err < fp16_tol(want), (case, err, fp16_tol(want))
 
 
 def test_im2col_indices_bit_exact_through_identity_weights():
@@ -182,8 +193,13 @@ def test_base_backbone_shape_against_torchvision_gpu():
     want = torchvision.ops.deform_conv2d(x, off, w, b, padding=1, mask=mask)
     got = bt.modulated_deformable_conv2d(x, off, mask, w, b, 1, 1, 1, 1, 1)
     assert (got - want).abs().max().item() < 2e-3  # both sides may use TF32-free fp32 GEMMs with different orders
-    goth = bt.modulated_deformable_conv2d(x.half(), off.half(), mask.half(), w.half(), b.half(), 1, 1, 1, 1, 1)
-    assert (goth.float() - want).abs().max().item() < 3e-2
+    # FP16 op (the fused tcgen05 kernel at this shape) against the same FP32 formulas on the FP16-rounded inputs
+    h = [t.half() for t in (x, off, mask, w, b)]
+    want16 = torchvision.ops.deform_conv2d(h[0].float(), h[1].float(), h[3].float(), h[4].float(), padding=1, mask=h[2].float())
+    goth = bt.modulated_deformable_conv2d(h[0], h[1], h[2], h[3], h[4], 1, 1, 1, 1, 1)
+    err16 = (goth.float() - want16).abs().max().item()
+    print(f"[dcn fp16 base layer] max|want| {want16.abs().max().item():.3f} err {err16:.2e} budget {fp16_tol(want16.cpu().numpy()):.2e}")
+    assert err16 < fp16_tol(want16.cpu().numpy())
 
 
 @pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref not built")

@@ -77,6 +77,64 @@ def test_int8_chw4_matches_dequant_oracle(interp, pad, align):
     assert np.abs(got - real).max() <= 0.5 * so + 1e-6  # one requantisation: at most half an output step
 
 
+def _tile_grid(kind, N, Ho, Wo, seed):
+    """[-10, 10] grids: "rot" = a small rotation + shift (compact source windows: the TMA tile path), "wild" = the
+    reference test's sweep far beyond the image plus noise (windows larger than shared memory: the per-tile fallback),
+    "mixed" = rotation in one image, wild in the other."""
+    g = torch.Generator().manual_seed(seed)
+    rot = make_rotation_grid(Ho, Wo, 7.5, shift=(3.3, -2.1)).repeat(N, 1, 1, 1)
+    ys, xs = torch.meshgrid(torch.linspace(-14, 14, Ho), torch.linspace(-14, 14, Wo), indexing="ij")
+    wild = torch.stack([xs, ys], 0)[None].repeat(N, 1, 1, 1) + 2.0 * torch.randn(N, 2, Ho, Wo, generator=g)
+    if kind == "rot":
+        return rot.contiguous()
+    if kind == "wild":
+        return wild.contiguous()
+    out = rot.clone()
+    out[1:] = wild[1:]
+    return out.contiguous()
+
+
+@pytest.mark.parametrize("kind", ["rot", "wild", "mixed"])
+@pytest.mark.parametrize("pad,align", [("zeros", False), ("border", True), ("reflection", False)])
+def test_tile_path_is_bit_identical_to_generic_kernel(kind, pad, align):
+    """2-D bilinear at bulk-copy-legal layouts (row pitch a multiple of 16 bytes): the tile kernel (source window staged by
+    TMA bulk copies, or its per-tile fallback) and the generic kernel evaluate the same index arithmetic and the
+    same FMA sequence per element, so every format must agree bit for bit; FP32 additionally against the oracle.
+    Shapes leave partial tiles on both output axes and a partial channel block (37 channels)."""
+    N, C, Hi, Wi, Ho, Wo = 2, 37, 26, 40, 19, 45
+    g = torch.Generator().manual_seed(11)
+    inp = torch.randn(N, C, Hi, Wi, generator=g)
+    grid = _tile_grid(kind, N, Ho, Wo, 12)
+    lib = bt._lib.load()
+
+    def both(fn):
+        prev = lib.b200_grid_sample_set_tile_path(1)
+        try:
+            a = fn()
+            lib.b200_grid_sample_set_tile_path(0)
+            b = fn()
+        finally:
+            lib.b200_grid_sample_set_tile_path(prev)
+        return a, b
+
+    a, b = both(lambda: bt.grid_sampler(inp.cuda(), grid.cuda(), "bilinear", pad, align))
+    assert torch.equal(a, b)
+    want = ogs.grid_sample_2d(inp.numpy(), grid.numpy(), 0, PM[pad], align)
+    assert np.abs(a.cpu().numpy() - want).max() < 1e-5
+    ih, gh = inp.half(), grid.half()
+    a, b = both(lambda: bt.grid_sampler(ih.cuda(), gh.cuda(), "bilinear", pad, align))
+    assert torch.equal(a, b)
+    g2 = gh.permute(0, 2, 3, 1).unsqueeze(1).contiguous()
+    a, b = both(lambda: bt.grid_sampler_chw2(pack_chw(ih, 2).cuda(), g2.cuda(), C, "bilinear", pad, align))
+    assert torch.equal(a, b)
+    iq, si = quantize_per_tensor(inp)
+    gq, sg = quantize_per_tensor(grid)
+    g4 = torch.zeros(N, 1, Ho, Wo, 4, dtype=torch.int8)
+    g4[:, 0, :, :, 0], g4[:, 0, :, :, 1] = gq[:, 0], gq[:, 1]
+    a, b = both(lambda: bt.grid_sampler_int8(pack_chw(iq, 4).cuda(), si, g4.cuda(), sg, 0.05, C, "bilinear", pad, align))
+    assert torch.equal(a, b)
+
+
 def test_sampling_indices_bit_exact_via_nearest():
     """Nearest mode on an index-valued image returns the sampled flat index itself: the device's source-index
     arithmetic is compared bit-exactly with the oracle's (and thereby the reference kernel's formulas)."""
