@@ -87,6 +87,8 @@ def parse():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: reduce-scatter inside the camera group by our NVLink peer-memory kernel, or by NCCL")
     ap.add_argument("--no-graph", action="store_true", help="N>1: eager launches instead of the CUDA graph of the step")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N>1: overlapped step (peers' rows sampled first, pulled under the own-rows launch); measured slower")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other distribution / INT8) legs")
     return ap.parse_args()
@@ -563,7 +565,7 @@ def run_multi(args, cfg, peak, peak_src):
     plan = plan_grid(cfg.batch, cfg.num_query, world)
     shard = plan[rank]
     exchange = args.exchange
-    smp = GroupedSCASampler(shard, width, bt.multi_scale_deformable_attn_sca, exchange=exchange).load(
+    smp = GroupedSCASampler(shard, width, bt.multi_scale_deformable_attn_sca, exchange=exchange, overlap=args.overlap).load(
         value, shapes, ref, off, logits, bev_mask.to(td), dev)
     ok = torch.ones(1, device=dev)
     try:

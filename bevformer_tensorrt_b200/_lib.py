@@ -54,6 +54,10 @@ SIGNATURES = {
                                   ctypes.c_longlong, _vp, _i, _vp, ctypes.c_longlong, _vp]),
     "b200_sca_peer_reduce_auto": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, ctypes.c_longlong,
                                        ctypes.c_longlong, _vp, _i, ctypes.c_longlong, _vp]),
+    "b200_sca_peer_pull_auto": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, ctypes.c_longlong,
+                                     ctypes.c_longlong, _vp, _vp]),
+    "b200_sca_peer_add_auto": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp, _i,
+                                    ctypes.c_longlong, _vp]),
     "b200_msda_f32_trace": (_i, [_vp] * 5 + _MSDA_DIMS + [_vp, _vp, _vp]),
     "b200_msda_f16_trace": (_i, [_vp] * 5 + _MSDA_DIMS + [_vp, _vp, _vp]),
     "b200_msda_i8_trace": (_i, [_vp, _f, _vp, _vp, _i, _vp, _f, _vp, _f] + _MSDA_DIMS + [_vp, _f, _vp, _vp]),

@@ -190,20 +190,22 @@ __global__ void __launch_bounds__(256, INTERP == 2 ? 2 : 4) grid_sample_2d_kerne
   }
 }
 
-// ---- 2-D bilinear fast path: source window staged in shared memory by TMA bulk copies ---------------------------------
-// The generic kernel above pays ~30 instructions per output element, two thirds of them 64-bit address arithmetic for
-// four scattered 2/4-byte loads that each wait a full L2 round trip. For a smooth sampling grid (the prev-BEV warp is a
-// small rotation, onnx_ops.py:226-232) the source pixels of an 8 x 32 output tile form a compact window. One CTA = one
-// output tile x one block of channel packets:
+// ---- 2-D bilinear tile kernel (opt-in: b200_grid_sample_set_tile_path): source window staged in shared memory by TMA ------
+// For a smooth sampling grid (the prev-BEV warp is a small rotation, onnx_ops.py:226-232) the source pixels of an 8 x 32
+// output tile form a compact window. One CTA = one output tile x one block of channel packets:
 //   1. every thread evaluates the index arithmetic of its pixel (the same device functions as the generic kernel: the
 //      sampled pixel is bit-identical), and the CTA reduces the bounding box of the clamped tap coordinates;
-//   2. if the box fits kBH rows x kRowBytes, warp 0 issues one bulk copy (cp.async.bulk, SASS UBLKCP: 16-byte aligned row
-//      segments of the planar layout) per (channel packet, row) into shared memory, completion counted on one mbarrier;
-//      otherwise the CTA runs the generic per-tap global loads;
+//   2. if the box fits kBH rows x kRowBytes, warp 0 stages it: mode 2 = one 2-D tensor copy per channel packet
+//      (cp.async.bulk.tensor.2d over the [N*CP*Hi, Wi] view, SASS UTMALDG.2D), mode 1 = one bulk copy per (packet, row)
+//      (cp.async.bulk, SASS UBLKCP); completion counted on one mbarrier; otherwise the CTA runs the per-tap global loads;
 //   3. each packet is then 4 shared-memory loads at compile-time channel offsets + 4 FMAs + one coalesced store.
-// (A cp.async.bulk.tensor variant — 3-D box, then one 2-D box per packet — assembled to UTMALDG but raised "illegal
-// instruction" on the B200 boxes for window origins that are not 16-byte aligned; the 1-D bulk copies below align the
-// segment start themselves. gpurun r02q-r02s.)
+// Measured at the prev-BEV warp [1,256,200,200] (profiles/r02u_grid_sampler_tile_modes_ab.txt): mode 2 equals the generic
+// kernel (FP32 26.0 vs 28.3 us, FP16 22.8 vs 22.0, kCHW2 14.2 vs 14.2, INT8 19.2 vs 17.4), mode 1 is 1.6-2x slower (a
+// B200 SM retires one small bulk copy per ~8 clocks: 256-512 row copies per CTA serialise) — the op is bound by the
+// latency chain grid load -> index arithmetic -> first loads at 2 resident waves, not by the tap loads, so the generic
+// kernel stays the default. Two TMA facts learnt on the way (gpurun r02q-r02u): a tensor copy whose innermost origin
+// coordinate x element size is not a multiple of 16 bytes raises "illegal instruction" on this part (3-D and 2-D boxes
+// alike), so the window origin is rounded down to 16 bytes; rounding costs up to 7 halves / 3 words of row slack.
 constexpr int kTW = 32, kTH = 8;  // output tile (a warp = 32 consecutive x)
 constexpr int kBH = 16;           // source window rows held in shared memory
 

@@ -28,6 +28,7 @@ struct PeerReduceParams {
   int out_half;
   float *zero[2];  // [step parity]: local buffer of the NEXT step to zero-fill (may be null)
   long long zero_elems;
+  float *staging;  // overlapped step: the peers' contribution to the owned slice, [elems] floats, local memory
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -45,22 +46,29 @@ __device__ __forceinline__ float4 ld_peer(const float *p) {
   return v;
 }
 
+// MODE 0: the whole exchange in one launch (handshake, out = own + peers, zero the next buffer).
+// MODE 1 (overlapped step, first half): handshake, then staging = sum of the PEERS' partials of the owned slice; runs on a
+//         side stream while this rank still samples its own rows. MODE 2 (second half): out = own partial + staging,
+//         zero the next buffer; no handshake (stream order after both).
+template <int MODE>
 __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerReduceParams p) {
   const int t = threadIdx.x;
   // Step number: from the host, or (CUDA-graph replays: identical launch parameters every step) from this rank's own
-  // counter in device memory, which the last block of the previous launch advanced.
+  // counter in device memory, which the last block of the previous handshake launch advanced.
   uint32_t *ctr = p.flags[p.me] + kMaxPeers;  // [0] completed steps, [1] blocks done in this launch
-  const uint32_t epoch = p.epoch ? p.epoch : *reinterpret_cast<volatile uint32_t *>(ctr) + 1u;
+  const uint32_t epoch = p.epoch ? p.epoch : *reinterpret_cast<volatile uint32_t *>(ctr) + (MODE == 2 ? 0u : 1u);
   const int par = static_cast<int>((epoch - 1u) & 1u);
-  if (t < p.n && t != p.me) {
-    if (blockIdx.x == 0) {
-      __threadfence_system();
-      st_release_sys(p.flags[t] + p.me, epoch);
+  if (MODE != 2) {
+    if (t < p.n && t != p.me) {
+      if (blockIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys(p.flags[t] + p.me, epoch);
+      }
+      const uint32_t *mine = p.flags[p.me] + t;
+      while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) __nanosleep(32);
     }
-    const uint32_t *mine = p.flags[p.me] + t;
-    while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) __nanosleep(32);
+    __syncthreads();
   }
-  __syncthreads();
 
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + t;
@@ -72,39 +80,53 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerReduceParams
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const long long i = i0 + u * stride;
-      acc[u] = i < n4 ? *reinterpret_cast<const float4 *>(p.part[par][p.me] + p.elem0 + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[u] = (MODE != 1 && i < n4) ? *reinterpret_cast<const float4 *>(p.part[par][p.me] + p.elem0 + i * 4)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll 1
-    for (int r = 0; r < p.n; ++r) {
-      if (r == p.me) continue;
-      const float *src = p.part[par][r] + p.elem0;
-      float4 v[kUnroll];
+    if (MODE == 2) {
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const long long i = i0 + u * stride;
-        v[u] = i < n4 ? ld_peer(src + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n4) {
+          const float4 v = *reinterpret_cast<const float4 *>(p.staging + i * 4);
+          acc[u].x += v.x, acc[u].y += v.y, acc[u].z += v.z, acc[u].w += v.w;
+        }
       }
+    } else {
+#pragma unroll 1
+      for (int r = 0; r < p.n; ++r) {
+        if (r == p.me) continue;
+        const float *src = p.part[par][r] + p.elem0;
+        float4 v[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) acc[u].x += v[u].x, acc[u].y += v[u].y, acc[u].z += v[u].z, acc[u].w += v[u].w;
+        for (int u = 0; u < kUnroll; ++u) {
+          const long long i = i0 + u * stride;
+          v[u] = i < n4 ? ld_peer(src + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) acc[u].x += v[u].x, acc[u].y += v[u].y, acc[u].z += v[u].z, acc[u].w += v[u].w;
+      }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const long long i = i0 + u * stride;
       if (i >= n4) break;
       const float4 a = acc[u];
-      if (p.out_half) {
+      if (MODE != 1 && p.out_half) {
         const uint2 h = make_uint2(f2_to_h2(a.x, a.y), f2_to_h2(a.z, a.w));
         *reinterpret_cast<uint2 *>(static_cast<__half *>(p.out) + i * 4) = h;
       } else {
-        *reinterpret_cast<float4 *>(static_cast<float *>(p.out) + i * 4) = a;
+        *reinterpret_cast<float4 *>((MODE == 1 ? p.staging : static_cast<float *>(p.out)) + i * 4) = a;
       }
     }
   }
-  float *zero = p.zero[par];
-  if (zero != nullptr)
-    for (long long i = first; i < p.zero_elems / 4; i += stride)
-      *reinterpret_cast<float4 *>(zero + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.epoch == 0u) {  // device-side step counter: the last block to finish advances it (every block has read it by then)
+  if (MODE != 1) {
+    float *zero = p.zero[par];
+    if (zero != nullptr)
+      for (long long i = first; i < p.zero_elems / 4; i += stride)
+        *reinterpret_cast<float4 *>(zero + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (MODE != 2 && p.epoch == 0u) {  // device-side step counter: the last block to finish advances it
     __syncthreads();
     if (t == 0) {
       __threadfence();
@@ -121,13 +143,18 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerReduceParams
 
 using namespace b200;
 
-static int launch_peer_reduce(PeerReduceParams &p, cudaStream_t stream) {
-  const long long work = (p.elems > p.zero_elems ? p.elems : p.zero_elems) / 4;
+static int launch_peer_reduce(PeerReduceParams &p, cudaStream_t stream, int mode = 0) {
+  const long long work = (mode != 1 && p.zero_elems > p.elems ? p.zero_elems : p.elems) / 4;
   long long blocks = (work + 255) / 256 / 4;  // 4 x 16 bytes per thread and peer in flight
   // every block spins in the handshake: keep the grid within one wave so that no block waits behind a spinning one
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  peer_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+  if (mode == 1)
+    peer_reduce_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+  else if (mode == 2)
+    peer_reduce_kernel<2><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+  else
+    peer_reduce_kernel<0><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
   return check_launch();
 }
 
@@ -176,4 +203,45 @@ extern "C" int b200_sca_peer_reduce_auto(const void *const *partials_even, const
   p.zero[0] = zero_elems ? const_cast<float *>(p.part[1][my_index]) : nullptr;
   p.zero[1] = zero_elems ? const_cast<float *>(p.part[0][my_index]) : nullptr;
   return launch_peer_reduce(p, static_cast<cudaStream_t>(stream));
+}
+
+// Overlapped step (see peer_reduce_kernel MODE 1 / 2): `b200_sca_peer_pull_auto` on a side stream right after the launch
+// that samples the rows the PEERS own, `b200_sca_peer_add_auto` on the main stream after the launch that samples this
+// rank's own rows and after the pull. Same buffers / flags / device-side step counter as b200_sca_peer_reduce_auto.
+extern "C" int b200_sca_peer_pull_auto(const void *const *partials_even, const void *const *partials_odd,
+                                       void *const *flags, int group_size, int my_index, long long first_elem,
+                                       long long num_elems, float *staging, void *stream) {
+  if (!partials_even || !partials_odd || !flags || !staging || group_size < 2 || group_size > kMaxPeers || my_index < 0 ||
+      my_index >= group_size)
+    return B200_ERR_BAD_PARAM;
+  if (first_elem < 0 || num_elems < 0 || (first_elem % 4) || (num_elems % 4) || reinterpret_cast<uintptr_t>(staging) % 16)
+    return B200_ERR_BAD_PARAM;
+  PeerReduceParams p{};
+  for (int r = 0; r < group_size; ++r) {
+    if (!partials_even[r] || !partials_odd[r] || !flags[r]) return B200_ERR_BAD_PARAM;
+    p.part[0][r] = static_cast<const float *>(partials_even[r]);
+    p.part[1][r] = static_cast<const float *>(partials_odd[r]);
+    p.flags[r] = static_cast<uint32_t *>(flags[r]);
+  }
+  p.n = group_size, p.me = my_index, p.epoch = 0u, p.elem0 = first_elem, p.elems = num_elems, p.staging = staging;
+  return launch_peer_reduce(p, static_cast<cudaStream_t>(stream), 1);
+}
+
+extern "C" int b200_sca_peer_add_auto(const void *partial_even, const void *partial_odd, void *flags_local, int my_index,
+                                      long long first_elem, long long num_elems, const float *staging, void *out,
+                                      int out_is_half, long long zero_elems, void *stream) {
+  if (!partial_even || !partial_odd || !flags_local || !staging || !out || my_index < 0 || my_index >= kMaxPeers)
+    return B200_ERR_BAD_PARAM;
+  if (first_elem < 0 || num_elems < 0 || (first_elem % 4) || (num_elems % 4) || (zero_elems % 4) || zero_elems < 0 ||
+      reinterpret_cast<uintptr_t>(out) % 16 || reinterpret_cast<uintptr_t>(staging) % 16)
+    return B200_ERR_BAD_PARAM;
+  PeerReduceParams p{};
+  p.part[0][my_index] = static_cast<const float *>(partial_even);
+  p.part[1][my_index] = static_cast<const float *>(partial_odd);
+  p.flags[my_index] = static_cast<uint32_t *>(flags_local);
+  p.n = 1, p.me = my_index, p.epoch = 0u, p.elem0 = first_elem, p.elems = num_elems;
+  p.staging = const_cast<float *>(staging), p.out = out, p.out_half = out_is_half, p.zero_elems = zero_elems;
+  p.zero[0] = zero_elems ? const_cast<float *>(p.part[1][my_index]) : nullptr;
+  p.zero[1] = zero_elems ? const_cast<float *>(p.part[0][my_index]) : nullptr;
+  return launch_peer_reduce(p, static_cast<cudaStream_t>(stream), 2);
 }

@@ -318,8 +318,14 @@ class GroupedSCASampler:
                          has no reduce-scatter) — the library baseline and the CPU-test path.
     ``fused_sca(value, shapes, ref, off, logits, mask, accum)`` is the product kernel; the CPU tests inject a checker."""
 
-    def __init__(self, shard: GridShard, width: int, fused_sca: Callable, exchange: str = "nccl", out_dtype=torch.float32):
+    def __init__(self, shard: GridShard, width: int, fused_sca: Callable, exchange: str = "nccl", out_dtype=torch.float32,
+                 overlap: bool = False):
         self.shard, self.width, self.fused_sca, self.exchange = shard, width, fused_sca, exchange
+        # overlap: sample the peers' rows first and pull their results while sampling the own rows (two sampling launches,
+        # pull on a side stream, a separate add pass). Measured SLOWER than the single exchange launch at N = 2 (G 0.218 vs
+        # 0.201 ms, U 0.649 vs 0.621 ms: the extra pass over the accumulator and the second launch cost more than the
+        # 30 us of NVLink traffic they hide; profiles/r02v_*), so it is opt-in.
+        self.overlap = overlap and exchange == "peer"
         self.out_dtype = out_dtype
         self.rows = shard.q1 - shard.q0
         self.local = None
@@ -341,7 +347,20 @@ class GroupedSCASampler:
         self.shapes = shapes.to(device)
         # bev_mask as the fused kernel reads it (fp32 [cams, rows]): no per-step conversion launch
         mask32 = take(bev_mask).reshape(s.cam1 - s.cam0, -1).to(torch.float32)
-        self.local = tuple(t.to(device).contiguous() for t in (value[cs], take(ref), take(off), take(logits), mask32))
+        full = (take(ref), take(off), take(logits), mask32)
+        val = value[cs].to(device).contiguous()
+        # Row parts of the tile for the overlapped step: the rows the PEERS own are sampled first (so that the peers can pull
+        # them while this rank samples its own rows). Only when those rows are one contiguous range (always for 2 groups).
+        lo, hi, rows = s.own0 - s.q0, s.own1 - s.q0, s.q1 - s.q0
+        self.parts = None
+        if s.groups > 1 and self.overlap and (lo == 0 or hi == rows) and 0 < hi - lo < rows:
+            others = (hi, rows) if lo == 0 else (0, lo)
+            self.parts = []
+            for r0, r1 in (others, (lo, hi)):
+                self.parts.append((r0, r1, tuple(t[:, r0:r1].to(device).contiguous() for t in full)))
+            self.local = (val,) + self.parts[0][2] + self.parts[1][2]
+        else:
+            self.local = (val,) + tuple(t.to(device).contiguous() for t in full)
         self.out = torch.empty(s.own1 - s.own0, self.width, dtype=self.out_dtype, device=device)
         return self
 
@@ -383,8 +402,16 @@ class GroupedSCASampler:
 
     # -- one step ------------------------------------------------------------------------------------------------
     def compute(self, accum):
-        v, r, o, w, m = self.local
-        self.fused_sca(v, self.shapes, r, o, w, m, accum)
+        if self.parts is None:
+            v, r, o, w, m = self.local
+            self.fused_sca(v, self.shapes, r, o, w, m, accum)
+        else:
+            for i in (0, 1):
+                self._compute_part(i, accum)
+
+    def _compute_part(self, i, accum):
+        r0, r1, (r, o, w, m) = self.parts[i]
+        self.fused_sca(self.local[0], self.shapes, r, o, w, m, accum[r0:r1])
 
     def step(self):
         s = self.shard
@@ -426,6 +453,8 @@ class GroupedSCASampler:
         from . import _lib
 
         s, p = self.shard, self._peer
+        if compute and self.parts is not None and self.exchange == "peer":
+            return self._step_overlapped()
         k = self.epoch & 1  # the device counts the steps itself (flag row slot 8): same parity by construction
         self.epoch += 1
         if compute:
@@ -439,6 +468,45 @@ class GroupedSCASampler:
         with torch.cuda.device(self.out.device):
             st = _lib.load().b200_sca_peer_reduce_auto(*p["args"], _lib.current_stream_ptr())
         _lib.check("b200_sca_peer_reduce_auto", st)
+        return self.out
+
+    def _step_overlapped(self):
+        """Launch 1: the rows the peers own -> side stream: publish + pull the peers' launch-1 rows of MY slice into a staging
+        buffer (NVLink traffic under launch 2) -> launch 2: my own rows -> out = own partial + staging."""
+        from . import _lib
+
+        s, p = self.shard, self._peer
+        lib = _lib.load()
+        k = self.epoch & 1
+        self.epoch += 1
+        dev = self.out.device
+        if "ov" not in p:
+            n = len(s.peers)
+            loc = [p["part"][kk][s.my_index] for kk in (0, 1)]
+            p["ov"] = {
+                "side": torch.cuda.Stream(device=dev, priority=-1), "e1": torch.cuda.Event(), "e2": torch.cuda.Event(),
+                "staging": torch.empty((s.own1 - s.own0) * self.width, dtype=torch.float32, device=dev),
+                "pull": ((ctypes.c_void_p * n)(*p["part"][0]), (ctypes.c_void_p * n)(*p["part"][1]),
+                         (ctypes.c_void_p * n)(*p["flags"]), n, s.my_index, (s.own0 - s.q0) * self.width,
+                         (s.own1 - s.own0) * self.width),
+                "add": (loc[0], loc[1], p["flags"][s.my_index], s.my_index, (s.own0 - s.q0) * self.width,
+                        (s.own1 - s.own0) * self.width),
+            }
+        ov = p["ov"]
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            self._compute_part(0, self.partial[k])
+            ov["e1"].record(main)
+            ov["side"].wait_event(ov["e1"])
+            st = lib.b200_sca_peer_pull_auto(*ov["pull"], ov["staging"].data_ptr(), ctypes.c_void_p(ov["side"].cuda_stream))
+            _lib.check("b200_sca_peer_pull_auto", st)
+            ov["e2"].record(ov["side"])
+            self._compute_part(1, self.partial[k])
+            main.wait_event(ov["e2"])
+            st = lib.b200_sca_peer_add_auto(*ov["add"], ov["staging"].data_ptr(), self.out.data_ptr(),
+                                            int(self.out_dtype == torch.float16), self.rows * self.width,
+                                            ctypes.c_void_p(main.cuda_stream))
+            _lib.check("b200_sca_peer_add_auto", st)
         return self.out
 
     # -- CUDA graph of the step (peer exchange only: no library collective inside) -----------------------------------

@@ -163,6 +163,19 @@ int b200_sca_peer_reduce(const void *const *partials, void *const *flags, int gr
 int b200_sca_peer_reduce_auto(const void *const *partials_even, const void *const *partials_odd, void *const *flags,
                               int group_size, int my_index, long long first_elem, long long num_elems, void *out,
                               int out_is_half, long long zero_elems, void *stream);
+/* The overlapped form of the same exchange: a rank first samples the tile rows its PEERS own (launch 1), then its own rows
+ * (launch 2). b200_sca_peer_pull_auto — on a side stream, ordered after launch 1 — publishes the step, waits for the
+ * peers and pulls THEIR launch-1 results for this rank's slice into `staging` (floats [num_elems], local memory) while
+ * launch 2 runs; b200_sca_peer_add_auto — on the main stream after launch 2 and after the pull — writes
+ * out = own partial + staging and zero-fills the next step's buffer. Buffers, flags and the device-side step counter are
+ * those of b200_sca_peer_reduce_auto. */
+int b200_sca_peer_pull_auto(const void *const *partials_even, const void *const *partials_odd, void *const *flags,
+                            int group_size, int my_index, long long first_elem, long long num_elems, float *staging,
+                            void *stream);
+int b200_sca_peer_add_auto(const void *partial_even, const void *partial_odd, void *flags_local, int my_index,
+                           long long first_elem, long long num_elems, const float *staging, void *out, int out_is_half,
+                           long long zero_elems, void *stream);
+
 
 
 /* Trace entries: b200_msda_f32 / _f16 / _i8 with the production kernel's trace switch on (the same kernel template,
@@ -250,11 +263,12 @@ int b200_msda_supports_format(int pos, const b200_tensor_desc *in_out, int nb_in
  * ---------------------------------------------------------------------------------------------------------- */
 
 /* replaces grid_sample<float>   — gridSamplerKernel.h:14-18, .cu:1933-1964 */
-/* 2-D bilinear sampling runs a tile kernel by default (source window of an 8 x 32 output tile staged in shared memory by
- * TMA bulk copies, one per channel packet and row; falls back per tile to scattered loads when the window does not fit,
- * and per call when the layout does not meet the copies' 16-byte rules: input pointer and row pitch). 0 = always the
- * generic kernel. Same results bit for bit. Returns the previous setting. */
-int b200_grid_sample_set_tile_path(int on);
+/* Opt-in tile kernel for 2-D bilinear sampling: 0 (default) = the generic kernel; 1 / 2 = the source window of an 8 x 32
+ * output tile is staged in shared memory by TMA (1: one bulk copy per packet row, 2: one 2-D tensor copy per channel
+ * packet), with a per-tile fallback to scattered loads when the window does not fit and a per-call fallback when the
+ * layout does not meet TMA's 16-byte rules (input pointer, row pitch). Same results bit for bit; measured equal (mode 2)
+ * or slower (mode 1) than the generic kernel at the prev-BEV warp. Returns the previous setting. */
+int b200_grid_sample_set_tile_path(int mode);
 int b200_grid_sample_f32(float *output, const float *input, const float *grid, const int *output_dims,
                          const int *input_dims, const int *grid_dims, int nb_dims, int interp, int padding,
                          int align_corners, void *stream);

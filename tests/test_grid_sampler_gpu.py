@@ -94,13 +94,16 @@ def _tile_grid(kind, N, Ho, Wo, seed):
     return out.contiguous()
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("kind", ["rot", "wild", "mixed"])
 @pytest.mark.parametrize("pad,align", [("zeros", False), ("border", True), ("reflection", False)])
-def test_tile_path_is_bit_identical_to_generic_kernel(kind, pad, align):
-    """2-D bilinear at bulk-copy-legal layouts (row pitch a multiple of 16 bytes): the tile kernel (source window staged by
-    TMA bulk copies, or its per-tile fallback) and the generic kernel evaluate the same index arithmetic and the
-    same FMA sequence per element, so every format must agree bit for bit; FP32 additionally against the oracle.
-    Shapes leave partial tiles on both output axes and a partial channel block (37 channels)."""
+def test_tile_path_is_bit_identical_to_generic_kernel(kind, pad, align, mode):
+    """2-D bilinear at TMA-legal layouts (row pitch a multiple of 16 bytes): the opt-in tile kernel — source window staged
+    in shared memory by bulk copies per row (mode 1) or one 2-D tensor copy per channel packet (mode 2,
+    cp.async.bulk.tensor.2d with a 16-byte-aligned window origin), or its per-tile fallback — and the generic kernel
+    evaluate the same index arithmetic and the same FMA sequence per element, so every format must agree bit for bit; FP32
+    additionally against the oracle. Shapes leave partial tiles on both output axes and a partial channel block (37
+    channels)."""
     N, C, Hi, Wi, Ho, Wo = 2, 37, 26, 40, 19, 45
     g = torch.Generator().manual_seed(11)
     inp = torch.randn(N, C, Hi, Wi, generator=g)
@@ -108,7 +111,7 @@ def test_tile_path_is_bit_identical_to_generic_kernel(kind, pad, align):
     lib = bt._lib.load()
 
     def both(fn):
-        prev = lib.b200_grid_sample_set_tile_path(1)
+        prev = lib.b200_grid_sample_set_tile_path(mode)
         try:
             a = fn()
             lib.b200_grid_sample_set_tile_path(0)
