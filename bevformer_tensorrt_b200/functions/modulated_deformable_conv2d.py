@@ -180,7 +180,7 @@ def modulated_deformable_conv2d_int8(input_chw4, scale_i, offset_q, scale_off, m
     (``functions.grid_sampler.pack_chw(x, 4)``), ``offset_q`` / ``mask_q`` int8 NCHW, per-tensor scales
     (real = q*scale), ``bias`` float32/float16 or None. Returns int8 [N, Co, Ho, Wo] at ``scale_o``. Backbone shapes
     run on the fused tensor-core kernel; other shapes (groups / deform_groups > 1, small channel counts) dequantise
-    into the workspace and take the gather + cuBLAS path."""
+    into the workspace and take the generic hand-written kernel (csrc/dcn_generic.cu)."""
     assert input_chw4.is_cuda and input_chw4.dtype == torch.int8 and input_chw4.shape[-1] == 4
     (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
     n, c4, h, w, _ = input_chw4.shape

@@ -405,8 +405,8 @@ int b200_dcn_f16_ex(const void *input, const void *weight, const void *bias, con
  * accumulation, one requantisation T2int8((acc*scale_i*scale_w + bias)/scale_o) — the reference requantises the
  * sampled columns to int8 first (:536-545). Shapes of the fused path (groups == deformable_groups == 1,
  * channels % 64 == 0, channels_out in {128, 256, 512}) run on tensor cores in one kernel; any other shape with
- * channels % 4 == 0 and (channels / group) % 4 == 0 dequantises into the workspace and runs the gather + cuBLAS FP16
- * path (FP32 accumulation), one requantisation at the end. workspace: b200_dcn_i8_workspace_size(...) bytes,
+ * channels % 4 == 0 and (channels / group) % 4 == 0 dequantises into the workspace and runs the generic hand-written FP16
+ * kernel (csrc/dcn_generic.cu, FP32 accumulation), one requantisation at the end. workspace: b200_dcn_i8_workspace_size(...) bytes,
  * 256-byte aligned. */
 size_t b200_dcn_i8_workspace_size(int batch, int channels, int height, int width, int channels_out, int kernel_w,
                                   int kernel_h, int stride_w, int stride_h, int pad_w, int pad_h, int dilation_w,

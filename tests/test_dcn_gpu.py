@@ -268,7 +268,7 @@ def test_int8_matches_dequant_oracle(case, bias_dtype):
                                   "backbone_like"])  # fmt: skip
 def test_int8_unfused_shapes_match_dequant_oracle(case):
     """INT8 for the shapes the fused kernel does not take (groups / deformable groups > 1, small or odd channel
-    counts): dequantise -> gather + cuBLAS FP16 path -> one requantisation."""
+    counts): dequantise -> generic hand-written FP16 kernel -> one requantisation."""
     from bevformer_tensorrt_b200.functions.grid_sampler import pack_chw
     from bevformer_tensorrt_b200.workloads import quantize_per_tensor
 
