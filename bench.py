@@ -367,6 +367,8 @@ def run_single(args, cfg, peak, peak_src):
                      "kernel": ("msda_pack_kernel + msda_i8p_kernel: the op's two launches, timed together (pack pre-pass "
                                 "included in the denominator)") if args.dtype == "i8" and v2_on else "msda_gather_kernel",
                      "kernel_ms": k_ms, "kernel_ms_min": per[0],
+                     "launch_shape": "%d unit(s) per warp%s (b200_msda_set_batch_units / B200_MSDA_BATCH)"
+                                     % (bt.get_msda_batch_units()[0], ", grid-strided" if bt.get_msda_batch_units()[1] else ""),
                      "algorithmic_bytes": alg, "peak_source": peak_src},
         "wall_s": wall,
     }  # fmt: skip

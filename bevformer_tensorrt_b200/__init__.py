@@ -43,6 +43,8 @@ from .functions import (  # noqa: E402
     rotate_int8,
     set_msda_v2,
     set_msda_f16_path,
+    set_msda_batch_units,
+    get_msda_batch_units,
 )
 
 from .host_pipeline import HostMSDA, empty_pinned  # noqa: E402
@@ -74,5 +76,7 @@ __all__ = [
     "rotate_int8",
     "set_msda_v2",
     "set_msda_f16_path",
+    "set_msda_batch_units",
+    "get_msda_batch_units",
 ]
 __version__ = "0.1.0"

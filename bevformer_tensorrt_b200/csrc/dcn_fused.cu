@@ -39,6 +39,7 @@ struct DcnFusedParams {
   const void *bias, *offset, *mask;  // FP16 path: __half; INT8 path: offset/mask int8, bias float (converted by the host)
   void *out;                         // FP16 path: __half; INT8 path: int8
   float scale_off, scale_mask, out_mul, out_div;  // INT8 path: dequant scales; out = T2int8((acc*out_mul + bias)/out_div)
+  float out_inv;                                  // 1 / out_div, rounded once on the host
   int B, C, H, W, Co, kh, kw, pad_h, pad_w, stride_h, stride_w, dil_h, dil_w, Ho, Wo;
   int tiles_per_img, num_tiles, kb_per_tap, num_kb;
 };
@@ -154,6 +155,21 @@ __global__ void dcn_weight_reorder_kernel(const __half *__restrict__ w, __half *
     const long long co = i / (static_cast<long long>(C) * kk);
     wr[i] = w[(co * C + cc * kBK + ci) * kk + t];
   }
+}
+
+// T2int8(real / div) of the INT8 epilogue (…Conv2dKernel.cu:578-579, T2int8 :51-55) without the generic division
+// sequence (reciprocal, fix-ups, slow-path check: ~10 issue slots on each of 65 k outputs per tile, on the warps that
+// also feed the tensor core): quotient from the host-rounded reciprocal plus one Newton step on the exact remainder
+// (two FMAs) — the correctly rounded quotient except for isolated last-bit cases, which move a result only when it sits
+// within 2^-24 of a rounding boundary. Saturation and round-half-away-from-zero in one conversion: trunc(q + copysign(0.5, q))
+// with cvt.sat clamps to [-128, 127] exactly like the clamp-then-round of to_int8_sat (NaN -> 0 in both).
+__device__ __forceinline__ int requant_i8(float real, float div, float inv) {
+  float q = real * inv;
+  q = fmaf(fmaf(-q, div, real), inv, q);
+  const float h = __uint_as_float((__float_as_uint(q) & 0x80000000u) | 0x3f000000u);
+  int r;
+  asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(q + h));
+  return r;
 }
 
 // ---- the fused kernel -----------------------------------------------------------------------------------------------
@@ -391,7 +407,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float real = fmaf(__uint_as_float(r[16 * v + 4 * q + i]), p.out_mul, bias);
-                  word |= (static_cast<uint32_t>(to_int8_sat(real / p.out_div)) & 0xffu) << (8 * i);
+                  word |= (static_cast<uint32_t>(requant_i8(real, p.out_div, p.out_inv)) & 0xffu) << (8 * i);
                 }
                 w4[q] = word;
               }
@@ -401,7 +417,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (p0 + c0 + i < HoWo)
-                orow[c0 + i] = static_cast<int8_t>(to_int8_sat(fmaf(__uint_as_float(r[i]), p.out_mul, bias) / p.out_div));
+                orow[c0 + i] = static_cast<int8_t>(requant_i8(fmaf(__uint_as_float(r[i]), p.out_mul, bias), p.out_div, p.out_inv));
           }
         } else {
         const float bias = __half2float(__ldg(static_cast<const __half *>(p.bias) + co));
@@ -634,7 +650,7 @@ int dcn_fused_i8(const int8_t *input, float scale_i, const int8_t *weight, float
 
   DcnFusedParams p{};
   p.x_nhwc = x_nhwc, p.w_r = w_r, p.bias = bias_f, p.offset = offset, p.mask = mask, p.out = output;
-  p.scale_off = scale_off, p.scale_mask = scale_mask, p.out_mul = scale_i * scale_w, p.out_div = scale_o;
+  p.scale_off = scale_off, p.scale_mask = scale_mask, p.out_mul = scale_i * scale_w, p.out_div = scale_o, p.out_inv = 1.f / scale_o;
   p.B = batch, p.C = channels, p.H = height, p.W = width, p.Co = channels_out, p.kh = kernel_h, p.kw = kernel_w;
   p.pad_h = pad_h, p.pad_w = pad_w, p.stride_h = stride_h, p.stride_w = stride_w, p.dil_h = dilation_h,
   p.dil_w = dilation_w, p.Ho = Ho, p.Wo = Wo;

@@ -18,6 +18,9 @@
 //                     skipped with one ballot (the common case for cameras that do not see the BEV query).
 // Memory: value taps go through the read-only path and are meant to hit L1/L2 (the 95 MB value stack of the base
 // config fits the 126 MB L2); offsets/logits/out are streamed with L1::no_allocate so they do not evict taps.
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -36,6 +39,25 @@ static std::atomic<int> g_f16_mode{0};
 // round-1 gather kernel everywhere.
 static std::atomic<int> g_f16_path{0};
 static std::atomic<int> g_res_cap_bytes{128 * 1024};
+// Launch shape of the FP32 / FP16 plugin op, encoded as units | strided << 8. units: 1 = one block of items per CTA
+// (round-1 grid), 2 / 4 = batched launch with the visibility scan (see msda_gather_kernel); strided: where the units of
+// a CTA lie. -1 = not decided yet: the first launch reads the environment variable B200_MSDA_BATCH ("1", "2", "4",
+// "2s", "4s"), else kDefaultBatch. b200_msda_set_batch_units overrides.
+constexpr int kDefaultBatch = 1;
+static std::atomic<int> g_batch_units{-1};
+static int msda_batch_units() {
+  int v = g_batch_units.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char *e = getenv("B200_MSDA_BATCH");
+    v = kDefaultBatch;
+    if (e != nullptr && (e[0] == '1' || e[0] == '2' || e[0] == '4')) {
+      if (e[1] == '\0') v = e[0] - '0';
+      else if (e[1] == 's' && e[2] == '\0' && e[0] != '1') v = (e[0] - '0') | 0x100;
+    }
+    g_batch_units.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 // msda_res.cu
 int msda_res_f16(const void *value, const int32_t *shapes, const void *ref, const void *off, const void *logits, int B, int S,
@@ -58,6 +80,7 @@ struct MsdaParams {
   float *accum;
   float scale_value, scale_offset, scale_weight, scale_out;
   int4 *trace;  // DBG instantiations: per (item, point) sampling-index record {in_range, h_low, w_low, tap_mask}
+  int unit_stride;  // batched launch (UPW > 1): 0 = a CTA's units are consecutive blocks, 1 = a grid apart
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -125,6 +148,17 @@ struct Io<float, MODE> {
     ox[2] = __uint_as_float(b.x), oy[2] = __uint_as_float(b.y), ox[3] = __uint_as_float(b.z),
     oy[3] = __uint_as_float(b.w);
   }
+  // visibility scan (UPW > 1): the same two loads as load_off4, issued for several units before any is decoded
+  struct OffRaw {
+    uint4 a, b;
+  };
+  __device__ static OffRaw ld_off_raw(const float *p) { return OffRaw{ldg128_stream(p), ldg128_stream(p + 4)}; }
+  __device__ static void decode_off(const OffRaw &w, float, float (&ox)[4], float (&oy)[4]) {
+    ox[0] = __uint_as_float(w.a.x), oy[0] = __uint_as_float(w.a.y), ox[1] = __uint_as_float(w.a.z),
+    oy[1] = __uint_as_float(w.a.w);
+    ox[2] = __uint_as_float(w.b.x), oy[2] = __uint_as_float(w.b.y), ox[3] = __uint_as_float(w.b.z),
+    oy[3] = __uint_as_float(w.b.w);
+  }
   __device__ static void load_lg4(const float *p, float, float (&lg)[4]) {
     const uint4 a = ldg128_stream(p);
     lg[0] = __uint_as_float(a.x), lg[1] = __uint_as_float(a.y), lg[2] = __uint_as_float(a.z),
@@ -158,6 +192,12 @@ struct Io<__half, MODE> {
   __device__ static void store_zero(__half *p) { stg128_stream(p, make_uint4(0u, 0u, 0u, 0u)); }
   __device__ static void load_off4(const __half *p, float, float (&ox)[4], float (&oy)[4]) {
     const uint4 a = ldg128_stream(p);
+    const float2 p0 = h2_to_f2(a.x), p1 = h2_to_f2(a.y), p2 = h2_to_f2(a.z), p3 = h2_to_f2(a.w);
+    ox[0] = p0.x, oy[0] = p0.y, ox[1] = p1.x, oy[1] = p1.y, ox[2] = p2.x, oy[2] = p2.y, ox[3] = p3.x, oy[3] = p3.y;
+  }
+  using OffRaw = uint4;
+  __device__ static OffRaw ld_off_raw(const __half *p) { return ldg128_stream(p); }
+  __device__ static void decode_off(const OffRaw &a, float, float (&ox)[4], float (&oy)[4]) {
     const float2 p0 = h2_to_f2(a.x), p1 = h2_to_f2(a.y), p2 = h2_to_f2(a.z), p3 = h2_to_f2(a.w);
     ox[0] = p0.x, oy[0] = p0.y, ox[1] = p1.x, oy[1] = p1.y, ox[2] = p2.x, oy[2] = p2.y, ox[3] = p3.x, oy[3] = p3.y;
   }
@@ -311,6 +351,43 @@ __device__ __forceinline__ void load_ref<float>(const float *p, int G, float (&p
   }
 }
 
+// The same reference-point words as load_ref, split into "issue the load" and "decode" so that the visibility scan of a
+// batched launch (UPW > 1) can put the loads of several units in flight before the first one is consumed. The raw
+// words are replicated so that decode is the G == 4 pattern whatever G is (G = 2: {p0, p1, p0, p1}; G = 1: p0 four times).
+template <typename R>
+struct RefRaw;
+template <>
+struct RefRaw<__half> {
+  uint4 a;
+  __device__ __forceinline__ void load4(const __half *p) { a = ldg128(p); }
+  __device__ __forceinline__ void load2(const __half *p) {
+    const uint2 t = ldg64(p);
+    a = make_uint4(t.x, t.y, t.x, t.y);
+  }
+  __device__ __forceinline__ void load1(const __half *p) {
+    const uint32_t t = ldg32(p);
+    a = make_uint4(t, t, t, t);
+  }
+  __device__ __forceinline__ void decode(float (&px)[4], float (&py)[4]) const {
+    const float2 f0 = h2_to_f2(a.x), f1 = h2_to_f2(a.y), f2 = h2_to_f2(a.z), f3 = h2_to_f2(a.w);
+    px[0] = f0.x, py[0] = f0.y, px[1] = f1.x, py[1] = f1.y, px[2] = f2.x, py[2] = f2.y, px[3] = f3.x, py[3] = f3.y;
+  }
+};
+template <>
+struct RefRaw<float> {
+  uint4 a, b;
+  __device__ __forceinline__ void load4(const float *p) { a = ldg128(p), b = ldg128(p + 4); }
+  __device__ __forceinline__ void load2(const float *p) { a = ldg128(p), b = a; }
+  __device__ __forceinline__ void load1(const float *p) {
+    const uint2 t = ldg64(p);
+    a = make_uint4(t.x, t.y, t.x, t.y), b = a;
+  }
+  __device__ __forceinline__ void decode(float (&px)[4], float (&py)[4]) const {
+    px[0] = __uint_as_float(a.x), py[0] = __uint_as_float(a.y), px[1] = __uint_as_float(a.z), py[1] = __uint_as_float(a.w);
+    px[2] = __uint_as_float(b.x), py[2] = __uint_as_float(b.y), px[3] = __uint_as_float(b.z), py[3] = __uint_as_float(b.w);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // Main kernel. T = storage type of value/offsets/logits/out, R = storage type of reference points.
 // Requirements checked on the host: LPI = C*sizeof(T)/16 in {1,2,4,8,16,32}, P % 4 == 0, G in {1,2,4},
@@ -318,8 +395,19 @@ __device__ __forceinline__ void load_ref<float>(const float *p, int G, float (&p
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxChunks = 64;
 
-template <typename T, typename R, int C, int ROUNDS, int MODE, int EPI, bool DBG = false>
+//
+// UPW ("units per warp", plugin-op form EPI = 0 only) > 1 is the batched launch: a CTA covers UPW consecutive blocks of
+// IPB items and each warp walks UPW units (unit u of warp w = the 32/LPI items at item0 + u*IPB + w*IPW, the same item
+// groups as the UPW = 1 grid, so results are bit-identical). Before the walk the warp runs a VISIBILITY SCAN: the
+// offsets and reference points of all its UPW units are loaded back to back (raw words, nothing decoded until every
+// load is issued) and phase A's range test is evaluated per unit. Units no point of which lands in an image — 4 of 5 on
+// a camera ring — are answered with zeros straight away; their memory latencies overlap instead of each costing a
+// CTA slot one full DRAM round trip (the UPW = 1 grid spends ~4 k cycles of a CTA slot per invisible block). Visible
+// units run the unchanged body below (which re-reads its 2 offset vectors per lane from L2).
+template <typename T, typename R, int C, int ROUNDS, int MODE, int EPI, bool DBG = false, int UPW = 1>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const MsdaParams prm) {
+  static_assert(UPW == 1 || EPI == 0, "the batched launch exists for the plugin-op form only");
+  static_assert(UPW >= 1 && UPW <= 8, "visibility bits live in one register");
   using IO = Io<T, MODE>;
   constexpr int VEC = IO::kVec;
   constexpr int LPI = C / VEC;
@@ -337,14 +425,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
   const int M = prm.M, Q = prm.Q, P = prm.P, G = prm.G, L = prm.L;
   const int NP = L * P, NCH = NP >> 2, CPL = P >> 2;  // chunks (4 points) in total / per level
   constexpr int IPB_ = IPB;
-  const long long item0 = static_cast<long long>(blockIdx.x) * IPB_;
+  // Block of IPB items a unit stands for: unit u of CTA x is block x*UPW + u (consecutive: a CTA covers UPW*IPB
+  // neighbouring items) or block x + u*gridDim.x (prm.unit_stride: the units of a CTA are a grid apart, so visible and
+  // invisible units mix inside every CTA and CTA run times even out). The host only takes UPW > 1 when IPB % M == 0,
+  // so unit u's (batch, query) is bq0 + u * ustep * (IPB / M) and the head index m is the same for every unit.
+  long long blk0 = blockIdx.x, ustep = 1;
+  if constexpr (UPW > 1) {
+    if (prm.unit_stride) ustep = gridDim.x;
+    else blk0 *= UPW;
+  }
+  const long long item0 = blk0 * IPB_;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % LPI;
+  // unit 0 of this warp; the unit loop below re-derives these for u > 0 (UPW > 1 only)
   const long long it_raw = item0 + warp * IPW + lane / LPI;
-  const bool active = it_raw < prm.items;
-  const long long it = active ? it_raw : prm.items - 1;  // inactive lanes shadow the last item, never store
-  const long long bq0 = it / M;  // EPI < 2: b * Q + q; EPI == 2: q
+  bool active = it_raw < prm.items;
+  long long it = active ? it_raw : prm.items - 1;  // inactive lanes shadow the last item, never store
+  long long bq0 = it / M;  // EPI < 2: b * Q + q; EPI == 2: q
   const int m = static_cast<int>(it - bq0 * M);
   const T *off_item = static_cast<const T *>(prm.off) + it * NP * 2;
   const T *lg_item = static_cast<const T *>(prm.logits) + it * NP;
@@ -378,6 +476,85 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
     }
     lvStart = incl - area;
   }
+
+  // ---- visibility scan (batched launch): bit u of vis = some point of some ACTIVE item of unit u is in range
+  unsigned vis = 1u;
+  if constexpr (UPW > 1) {
+    typename IO::OffRaw oraw[UPW][ROUNDS];
+    RefRaw<R> rraw[UPW];
+    bool act[UPW];
+#pragma unroll
+    for (int u = 0; u < UPW; ++u) {
+      const long long itr = it_raw + u * ustep * IPB_;
+      act[u] = itr < prm.items;
+      const long long itu = act[u] ? itr : it;  // units past the end shadow unit 0's item (valid address; act[] gates them)
+      const T *offu = static_cast<const T *>(prm.off) + itu * NP * 2;
+#pragma unroll
+      for (int r = 0; r < ROUNDS; ++r) {
+        const int c = r * LPI + sub;
+        oraw[u][r] = IO::ld_off_raw(offu + (c < NCH ? c : 0) * 8);
+      }
+    }
+    long long bqu[UPW];
+#pragma unroll
+    for (int u = 0; u < UPW; ++u) bqu[u] = act[u] ? bq0 + u * ustep * (IPB_ / M) : bq0;
+    const R *refp = static_cast<const R *>(prm.ref);
+    if (G == 4) {
+#pragma unroll
+      for (int u = 0; u < UPW; ++u) rraw[u].load4(refp + bqu[u] * 8);
+    } else if (G == 2) {
+#pragma unroll
+      for (int u = 0; u < UPW; ++u) rraw[u].load2(refp + bqu[u] * 4);
+    } else {
+#pragma unroll
+      for (int u = 0; u < UPW; ++u) rraw[u].load1(refp + bqu[u] * 2);
+    }
+    vis = 0u;
+#pragma unroll
+    for (int u = 0; u < UPW; ++u) {
+      float spx[4], spy[4];
+      rraw[u].decode(spx, spy);
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < ROUNDS; ++r) {
+        const int c = r * LPI + sub;
+        const bool have = c < NCH;
+        const int lv = (have ? c : 0) / CPL;
+        const int H = __shfl_sync(kFullMask, lvH, lv), W = __shfl_sync(kFullMask, lvW, lv);
+        float ox[4], oy[4];
+        IO::decode_off(oraw[u][r], prm.scale_offset, ox, oy);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // the statement of phase A below, word for word
+          const float w_im = __fadd_rn(__fmaf_rn(spx[k], static_cast<float>(W), ox[k]), -0.5f);
+          const float h_im = __fadd_rn(__fmaf_rn(spy[k], static_cast<float>(H), oy[k]), -0.5f);
+          any |= have && h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(H) && w_im < static_cast<float>(W);
+        }
+      }
+      if (__ballot_sync(kFullMask, act[u] && any) != 0u) vis |= 1u << u;
+    }
+  }
+
+  const long long it_first = it, bq_first = bq0;  // unit 0 (clamped), the base the later units derive from
+#pragma unroll 1
+  for (int u = 0; u < UPW; ++u) {
+  if constexpr (UPW > 1) {
+    if (u > 0) {
+      const long long itr = it_raw + u * ustep * IPB_;
+      active = itr < prm.items;
+      it = active ? itr : it_first;  // lane groups past the end shadow unit 0's item, never store
+      out_item = static_cast<T *>(prm.out) + it * C + sub * VEC;
+    }
+    if (((vis >> u) & 1u) == 0u) {  // warp-uniform
+      if (active) IO::store_zero(out_item);
+      continue;
+    }
+    if (u > 0) {
+      bq0 = active ? bq_first + u * ustep * (IPB_ / M) : bq_first;
+      off_item = static_cast<const T *>(prm.off) + it * NP * 2;
+      lg_item = static_cast<const T *>(prm.logits) + it * NP;
+    }
+  }
+  bool zero_stored = false;  // batched launch: phase A's own early-out fired (it cannot after a positive scan, but stays correct)
   float lg[ROUNDS][4];
   float sum = 0.f;
   bool have_sm = false;  // warp-uniform
@@ -426,7 +603,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
   if (__ballot_sync(kFullMask, inr != 0u) == 0u) {
     if (EPI == 2) continue;                            // next camera
     if (EPI == 0 && active) IO::store_zero(out_item);  // the fused epilogue adds nothing for invisible items
-    return;
+    if constexpr (UPW == 1) {
+      return;
+    } else {
+      zero_stored = true;
+      break;
+    }
   }
 
   // ---- phase B: softmax statistics over the item's NP logits (…Kernel.cu:642-648, :667-669); camera-independent,
@@ -528,7 +710,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
   }  // cameras
 
   if (EPI == 0) {
-    if (active) IO::store(out_item, acc, 1.f / sum, prm);
+    if (active && !zero_stored) IO::store(out_item, acc, 1.f / sum, prm);
   } else if (EPI == 2) {
     // one plain store per (query, head): the camera sum happened in registers, queries no camera sees get zeros
     if (active) {
@@ -556,6 +738,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
                      : "memory");
     }
   }
+  }  // units
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -681,6 +864,25 @@ static int launch_gather(const MsdaParams &p, cudaStream_t s) {
   constexpr int IPB = (32 / LPI) * (kThreads / 32);
   const long long blocks = (p.items + IPB - 1) / IPB;
   if (blocks > 0x7fffffffll) return B200_ERR_BAD_PARAM;
+  // Batched launch (visibility scan over UPW units per warp): the FP32 / FP16 plugin op at <= 2 rounds, which covers
+  // every BEVFormer shape (NP = 32 points: 2 rounds FP16, 1 round FP32). The traced instantiation follows the same
+  // switch, so the index records the parity tests read come out of whichever kernel the plugin op runs.
+  if constexpr (EPI == 0 && MODE == 0 && ROUNDS <= 2 && !std::is_same<T, int8_t>::value) {
+    const int cfg = msda_batch_units(), upw = cfg & 0xff;
+    if ((upw == 4 || upw == 2) && IPB % p.M == 0) {
+      const long long bb = (blocks + upw - 1) / upw;
+      MsdaParams q = p;
+      q.unit_stride = (cfg >> 8) & 1;
+      if (p.trace != nullptr) {
+        if (upw == 4) msda_gather_kernel<T, R, C, ROUNDS, 0, 0, true, 4><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);
+        else msda_gather_kernel<T, R, C, ROUNDS, 0, 0, true, 2><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);
+      } else {
+        if (upw == 4) msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 4><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);
+        else msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 2><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);
+      }
+      return check_launch();
+    }
+  }
   if constexpr (EPI == 0 && MODE == 0) {
     if (p.trace != nullptr) {
       msda_gather_kernel<T, R, C, ROUNDS, MODE, 0, true><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(p);
@@ -728,6 +930,8 @@ static int dispatch(const MsdaParams &p, cudaStream_t s) {
   return EPI == 0 ? launch_generic<T, R>(p, s) : B200_ERR_UNSUPPORTED;
 }
 
+int msda_batch_units_cfg() { return msda_batch_units(); }  // read by the INT8 path (msda_v2.cu)
+
 static MsdaParams make_params(const void *value, const int32_t *shapes, const void *ref, const void *off,
                               const void *logits, int B, int S, int M, int C, int L, int Q, int P, int G, void *out) {
   MsdaParams p{};
@@ -746,6 +950,12 @@ extern "C" {
 
 int b200_msda_set_f16_mode(int mode) { return g_f16_mode.exchange(mode ? 1 : 0); }
 int b200_msda_set_f16_path(int path) { return g_f16_path.exchange(path ? 1 : 0); }
+int b200_msda_set_batch_units(int units, int strided) {
+  const int before = msda_batch_units();
+  if (units == 1) g_batch_units.store(1, std::memory_order_relaxed);
+  else if (units == 2 || units == 4) g_batch_units.store(units | (strided ? 0x100 : 0), std::memory_order_relaxed);
+  return before;  // any other `units` (e.g. 0) only queries
+}
 int b200_msda_set_resident_bytes(int bytes) { return g_res_cap_bytes.exchange(bytes < 8192 ? 8192 : (bytes > 200 * 1024 ? 200 * 1024 : bytes)); }
 
 int b200_msda_f32(const float *value, const int32_t *spatial_shapes, const float *reference_points,

@@ -16,6 +16,8 @@ from .multi_scale_deformable_attn import (
     multi_scale_deformable_attn_queue_mean,
     set_msda_v2,
     set_msda_f16_path,
+    set_msda_batch_units,
+    get_msda_batch_units,
 )
 from .point_sampling import bev_point_sampling, get_reference_points_3d, point_sampling_trt
 from .rotate import rotate, rotate2, rotate_chw2, rotate_hwc, rotate_int8

@@ -29,9 +29,9 @@ def set_msda_v2(enabled: bool) -> bool:
 
 
 def set_msda_f16_path(resident: bool, resident_bytes: int = None):
-    """Selects the kernel behind the FP16 plugin op: True (library default) = the resident-tail kernel
-    (csrc/msda_res.cu: coarse pyramid levels staged in shared memory by TMA) where its envelope holds, False = the round-1
-    gather kernel (csrc/msda.cu). ``resident_bytes``: shared memory the resident kernel may use for the tail.
+    """Selects the kernel behind the FP16 plugin op: False (library default) = the gather kernel (csrc/msda.cu);
+    True = the resident-tail kernel (csrc/msda_res.cu: coarse pyramid levels staged in shared memory by TMA) where its
+    envelope holds — measured slower, opt-in. ``resident_bytes``: shared memory the resident kernel may use for the tail.
     Returns the previous (path, bytes-or-None)."""
     lib = _lib.load()
     prev = bool(lib.b200_msda_set_f16_path(int(bool(resident))))
@@ -39,6 +39,24 @@ def set_msda_f16_path(resident: bool, resident_bytes: int = None):
     if resident_bytes is not None:
         prev_bytes = int(lib.b200_msda_set_resident_bytes(int(resident_bytes)))
     return prev, prev_bytes
+
+
+def set_msda_batch_units(units: int, strided: bool = False):
+    """Launch shape of the FP32 / FP16 plugin op (C entry b200_msda_set_batch_units): ``units`` = 1 is one block of
+    items per CTA; 2 or 4 is the batched launch, where every warp first scans the visibility of that many item groups
+    with all their loads in flight, writes zeros for the invisible ones and samples the rest. ``strided``: the units of
+    a CTA lie a grid apart instead of side by side. Results are bit-identical for every setting.
+    Returns the previous (units, strided)."""
+    if units not in (1, 2, 4):
+        raise ValueError("units must be 1, 2 or 4")
+    prev = int(_lib.load().b200_msda_set_batch_units(int(units), int(bool(strided))))
+    return prev & 0xFF, bool(prev >> 8)
+
+
+def get_msda_batch_units():
+    """Current (units, strided) of the FP32 / FP16 plugin-op launch."""
+    prev = int(_lib.load().b200_msda_set_batch_units(0, 0))
+    return prev & 0xFF, bool(prev >> 8)
 
 
 def _v2_workspace(lib, dims, device):

@@ -210,14 +210,25 @@ int b200_msda_debug_indices(int dtype, const int32_t *spatial_shapes, const void
  * on O(1) outputs, so it is opt-in. Returns the previous setting. */
 int b200_msda_set_f16_mode(int mode);
 
-/* Selects the kernel behind b200_msda_f16 / _f16_h2 / _f16_trace. 1 (default) = the resident-tail kernel (csrc/msda_res.cu:
- * CTAs bound to one (batch, head), the coarsest pyramid levels staged in shared memory by TMA, taps of those levels served
- * from shared memory) whenever channels == 32, num_levels*num_point <= 32, num_point % 4 == 0; 0 = the round-1 gather
- * kernel (csrc/msda.cu) for every shape. Same results either way (same index arithmetic, FP32 accumulation).
+/* Selects the kernel behind b200_msda_f16 / _f16_h2 / _f16_trace. 0 (default) = the gather kernel (csrc/msda.cu) for
+ * every shape; 1 = the resident-tail kernel (csrc/msda_res.cu: CTAs bound to one (batch, head), the coarsest pyramid
+ * levels staged in shared memory by TMA, taps of those levels served from shared memory) whenever channels == 32,
+ * num_levels*num_point <= 32, num_point % 4 == 0 — measured slower on B200, hence opt-in. Same
+ * results either way (same index arithmetic, FP32 accumulation).
  * b200_msda_set_resident_bytes: shared memory the resident kernel may use for the tail (default 128 KiB). Both return
  * the previous setting. */
 int b200_msda_set_f16_path(int path);
 int b200_msda_set_resident_bytes(int bytes);
+
+/* Launch shape of the FP32 / FP16 plugin op (b200_msda_f32 / _f16 / _f16_h2 and their _trace twins): units = 1 is one
+ * block of items per CTA; 2 or 4 is the batched launch — every warp first scans the visibility of `units` of its item
+ * groups with all their offset / reference-point loads in flight together, answers the invisible ones with zeros and
+ * runs the sampling body on the rest (csrc/msda.cu, UPW). strided = 0: the units of a CTA are neighbouring blocks of
+ * items; 1: they lie a whole grid apart (evens out CTA run times when visibility comes in long runs). Results are
+ * bit-identical for every setting. Any other `units` (e.g. 0) only queries. The initial value is the environment
+ * variable B200_MSDA_BATCH ("1", "2", "4", "2s", "4s") if set, else the library default. Returns the previous setting
+ * as units | strided << 8. */
+int b200_msda_set_batch_units(int units, int strided);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Plugin-shaped entry: the argument list of IPluginV2DynamicExt::enqueue

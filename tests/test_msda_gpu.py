@@ -210,6 +210,70 @@ def test_gather_kernel_indices_bit_exact_at_base_shapes(dist):
     assert (frac > 0.9) if dist == "U" else (0.05 < frac < 0.5)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# batched launch of the FP32 / FP16 plugin op (visibility scan over 2 / 4 units per warp, csrc/msda.cu UPW)
+# ---------------------------------------------------------------------------------------------------------------
+BATCH_SHAPES = [(2, False), (4, False), (2, True), (4, True)]
+
+
+@pytest.fixture
+def restore_batch_units():
+    prev = bt.get_msda_batch_units()
+    yield
+    bt.set_msda_batch_units(*prev)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("name,dist,seed", [("small_sca", "edge", 81), ("small_sca", "U", 82), ("tiny_sca", "G", 83),
+                                            ("tsa_like", "edge", 84), ("g2", "edge", 85), ("ragged_tail", "edge", 86),
+                                            ("one_pixel", "edge", 87), ("many_points", "edge", 88),
+                                            ("cpu_plumbing", "U", 89), ("decoder_like", "edge", 90)])  # fmt: skip
+def test_batched_launch_is_bit_identical(name, dist, seed, dtype, restore_batch_units):
+    """Every launch shape of the plugin op (1 / 2 / 4 units per warp, neighbouring or grid-strided) must give the same
+    bytes: same item groups per warp, same arithmetic, only the order in which a warp meets its groups changes. The
+    traced launch follows the same switch, so the index records of the batched kernel are checked against the oracle
+    too. Shapes outside the batched envelope (heads that do not divide a block, > 2 rounds) silently take the
+    one-unit grid and must of course agree as well."""
+    cfg = _cfg(name)
+    inputs = make_msda_inputs(cfg, dist, seed, dtype)
+    dev = _cuda(inputs)
+    bt.set_msda_batch_units(1)
+    base = bt.multi_scale_deformable_attn(*dev)
+    err = np.abs(base.float().cpu().numpy() - _oracle_f32(inputs)).max()
+    assert err < (FP32_TOL if dtype == torch.float32 else FP16_TOL)
+    want = _want_records(inputs[1], inputs[2].float().numpy(), inputs[3].float().numpy(), cfg)
+    for units, strided in BATCH_SHAPES:
+        bt.set_msda_batch_units(units, strided)
+        assert bt.get_msda_batch_units() == (units, strided)
+        got = bt.multi_scale_deformable_attn(*dev)
+        assert torch.equal(got, base), (name, units, strided, (got.float() - base.float()).abs().max().item())
+        out_t, rec = msda_trace(*dev)
+        assert torch.equal(out_t, base), (name, units, strided)
+        assert (rec.cpu().numpy() == want).all(), (name, units, strided)
+
+
+@pytest.mark.parametrize("dist", ["U", "G"])
+def test_batched_launch_bit_identical_at_base_shapes(dist, restore_batch_units):
+    """BASELINE configs[2] at full size, FP16 and FP32, against the one-unit grid (itself checked against the
+    reference's own kernel and the oracle elsewhere in this file); the FP16 index records of the 4-unit kernel against
+    the oracle."""
+    cfg = CONFIGS["base_sca"]
+    inputs = make_msda_inputs(cfg, dist, 2, torch.float16)
+    dev = _cuda(inputs)
+    dev32 = [t.float() if t.is_floating_point() else t for t in dev]
+    bt.set_msda_batch_units(1)
+    base16, base32 = bt.multi_scale_deformable_attn(*dev), bt.multi_scale_deformable_attn(*dev32)
+    for units, strided in BATCH_SHAPES:
+        bt.set_msda_batch_units(units, strided)
+        assert torch.equal(bt.multi_scale_deformable_attn(*dev), base16), (units, strided)
+        assert torch.equal(bt.multi_scale_deformable_attn(*dev32), base32), (units, strided)
+    bt.set_msda_batch_units(4, False)
+    out_t, rec = msda_trace(*dev)
+    assert torch.equal(out_t, base16)
+    want = _want_records(inputs[1], inputs[2].float().numpy(), inputs[3].float().numpy(), cfg)
+    assert (rec.cpu().numpy() != want).any(-1).sum() == 0
+
+
 @pytest.mark.parametrize("ref_dtype", [torch.float32, torch.float16])
 def test_int8_gather_kernel_indices_bit_exact(ref_dtype):
     cfg = _cfg("small_sca")
@@ -230,12 +294,14 @@ def test_int8_gather_kernel_indices_bit_exact(ref_dtype):
 # ---------------------------------------------------------------------------------------------------------------
 # INT8
 # ---------------------------------------------------------------------------------------------------------------
-def _quantised(cfg, dist, seed, ref_dtype):
+def _quantised(cfg, dist, seed, ref_dtype, want_real=True):
     value, shapes, ref, off, logits = make_msda_inputs(cfg, dist, seed, torch.float32)
     vq, sv = quantize_per_tensor(value)
     oq, so = quantize_per_tensor(off)
     wq, sw = quantize_per_tensor(logits)
     ref = ref.to(ref_dtype)
+    if not want_real:  # kernel-against-kernel comparisons at sizes the CPU oracle does not finish in seconds
+        return (vq, sv, shapes, ref, oq, so, wq, sw, 1.6 / 127.0), None
     real = omsda.msda_f32(vq.float().numpy() * sv, shapes.numpy(), ref.float().numpy(), oq.float().numpy() * so,
                           wq.float().numpy() * sw)  # fmt: skip
     sout = float(np.abs(real).max()) / 127.0
@@ -460,6 +526,42 @@ def test_v2_int8_matches_oracle_and_round1_kernel(name, dist, seed, ref_dtype, i
         set_msda_v2(prev)
     d1 = np.abs(v1.astype(np.int32) - got.astype(np.int32))
     assert d1.max() <= 1 and (d1 != 0).mean() < 0.03
+
+
+@pytest.mark.parametrize("ref_dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("name,dist,seed", [("small_sca", "edge", 121), ("tiny_sca", "G", 122), ("v2_odd_levels", "edge", 123),
+                                            ("v2_np16", "U", 124), ("many_pairs", "edge", 125), ("g2", "edge", 126)])  # fmt: skip
+def test_v2_int8_batched_walk_is_bit_identical(name, dist, seed, ref_dtype, i8_resident_bytes, restore_batch_units):
+    """The INT8 gather kernel walking 2 / 4 query blocks at a time (visibility scan staged through the warp's record
+    area by cp.async) against the one-block walk: same bytes, and the index records traced out of the batched kernel
+    itself are the oracle's."""
+    cfg = CONFIGS.get(name) or V2_CASES.get(name) or RES_EXTRA.get(name) or EXTRA[name]
+    (vq, sv, shapes, ref, oq, so, wq, sw, sout), _ = _quantised(cfg, dist, seed, ref_dtype)
+    args = (vq.cuda(), sv, shapes.cuda(), ref.cuda(), oq.cuda(), so, wq.cuda(), sw, sout)
+    bt.set_msda_batch_units(1)
+    base = bt.multi_scale_deformable_attn_int8(*args)
+    off_real = oq.numpy().astype(np.float32) * np.float32(so)
+    want = _want_records(shapes, ref.float().numpy(), off_real, cfg)
+    for units in (2, 4):
+        bt.set_msda_batch_units(units)
+        assert torch.equal(bt.multi_scale_deformable_attn_int8(*args), base), (name, units)
+        out_t, rec = msda_trace(args[0], args[2], args[3], args[4], args[6], scales=(sv, so, sw, sout))
+        assert torch.equal(out_t, base), (name, units)
+        assert (rec.cpu().numpy() == want).all(), (name, units)
+
+
+@pytest.mark.parametrize("dist", ["U", "G"])
+def test_v2_int8_batched_walk_bit_identical_at_base_shapes(dist, restore_batch_units):
+    """BASELINE configs[3] tensors (INT8 at base shapes), half and float reference points."""
+    cfg = CONFIGS["base_sca"]
+    for ref_dtype in (torch.float16, torch.float32):
+        (vq, sv, shapes, ref, oq, so, wq, sw, sout), _ = _quantised(cfg, dist, 4, ref_dtype, want_real=False)
+        args = (vq.cuda(), sv, shapes.cuda(), ref.cuda(), oq.cuda(), so, wq.cuda(), sw, sout)
+        bt.set_msda_batch_units(1)
+        base = bt.multi_scale_deformable_attn_int8(*args)
+        for units in (2, 4):
+            bt.set_msda_batch_units(units)
+            assert torch.equal(bt.multi_scale_deformable_attn_int8(*args), base), (dist, ref_dtype, units)
 
 
 def test_v2_envelope_and_fallback():
