@@ -48,7 +48,9 @@ def timeit_eager(fn, n=20, warm=3):
 
 def main():
     peak = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
-    out = {}
+    out = {"_note": "CUDA-graph replay of back-to-back calls: every tensor here is smaller than the 126 MB L2 and stays "
+                    "resident between launches, so `rate_over_hbm_peak` (algorithmic bytes / time / HBM peak) is an "
+                    "on-chip-warm rate that can exceed 1 — it is NOT an HBM roofline fraction"}
     # grid sampler: rotation grid like onnx_ops.py:226-232 (prev-BEV warp)
     H = W = 200
     x = torch.randn(1, 256, H, W, device="cuda")
@@ -58,16 +60,16 @@ def main():
     for name, xx, gg in (("f32", x, grid), ("f16", x.half(), grid.half())):
         us = timeit(lambda: bt.grid_sampler(xx, gg, "bilinear", "zeros", False))
         nbytes = 2 * xx.numel() * xx.element_size() + gg.numel() * gg.element_size()
-        out[f"grid_sampler_{name}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+        out[f"grid_sampler_{name}"] = {"us": us, "alg_bytes": nbytes, "rate_over_hbm_peak": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
     x2, g2 = pack_chw(x.half(), 2), grid.half().permute(0, 2, 3, 1).unsqueeze(1).contiguous()
     us = timeit(lambda: bt.grid_sampler_chw2(x2, g2, 256, "bilinear", "zeros", False))
-    out["grid_sampler_f16_chw2"] = {"us": us, "hbm_frac": 41120000 / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+    out["grid_sampler_f16_chw2"] = {"us": us, "rate_over_hbm_peak": 41120000 / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
     xi = torch.randint(-127, 127, (1, 64, H, W, 4), dtype=torch.int8, device="cuda")
     gi = torch.zeros(1, 1, H, W, 4, dtype=torch.int8, device="cuda")
     gi[..., 0] = (grid[0, 0] * 12.7).round().clamp(-127, 127).to(torch.int8)
     gi[..., 1] = (grid[0, 1] * 12.7).round().clamp(-127, 127).to(torch.int8)
     us = timeit(lambda: bt.grid_sampler_int8(xi, 0.03, gi, 10 / 127, 0.03, 256, "bilinear", "zeros", False))
-    out["grid_sampler_i8_chw4"] = {"us": us, "hbm_frac": 20640000 / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+    out["grid_sampler_i8_chw4"] = {"us": us, "rate_over_hbm_peak": 20640000 / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
 
     # DCNv2 base backbone layer
     xd = torch.randn(6, 256, 58, 100, device="cuda")
@@ -102,17 +104,17 @@ def main():
             ins = [t.cuda() for t in make_msda_inputs(cfg, "U", 0, dt)]
             us = timeit(lambda: bt.multi_scale_deformable_attn(*ins), n=20)
             nbytes = cfg.algorithmic_bytes(2 if dt == torch.float16 else 4)
-            out[f"msda_{name}_{tag}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+            out[f"msda_{name}_{tag}"] = {"us": us, "alg_bytes": nbytes, "rate_over_hbm_peak": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
     # RotateTRT: prev_bev [256, 200, 200] by a few degrees about the BEV centre (transformer.py:296-304)
     ang, ctr = torch.tensor([2.3], device="cuda"), torch.tensor([100.0, 100.0], device="cuda")
     for tag, xx, aa, cc in (("f32", x[0], ang, ctr), ("f16", x[0].half(), ang.half(), ctr.half())):
         nbytes = 2 * xx.numel() * xx.element_size()
         for interp in ("bilinear", "nearest"):
             us = timeit(lambda: bt.rotate(xx, aa, cc, interp))
-            out[f"rotate_{tag}_{interp}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+            out[f"rotate_{tag}_{interp}"] = {"us": us, "alg_bytes": nbytes, "rate_over_hbm_peak": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
         hwc = xx.permute(1, 2, 0).contiguous()
         us = timeit(lambda: bt.rotate_hwc(hwc, aa, cc, "bilinear"))
-        out[f"rotate_hwc_{tag}_bilinear"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+        out[f"rotate_hwc_{tag}_bilinear"] = {"us": us, "alg_bytes": nbytes, "rate_over_hbm_peak": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
         # what the reference call site does around the plugin: permute -> rotate -> permute back (two extra copies)
         us = timeit(lambda: bt.rotate(hwc.permute(2, 0, 1).contiguous(), aa, cc, "bilinear").permute(1, 2, 0).contiguous())
         out[f"rotate_{tag}_bilinear_with_permutes"] = {"us": us}
@@ -124,7 +126,7 @@ def main():
     for tag, dt in (("f32", torch.float32), ("f16", torch.float16)):
         us = timeit(lambda: bt.bev_point_sampling(200, 200, pcr, l2i, (928, 1600), 4, dtype=dt))
         nbytes = (6 * 40000 * 8 + 6 * 40000) * (4 if dt == torch.float32 else 2)
-        out[f"bev_point_sampling_{tag}"] = {"us": us, "alg_bytes": nbytes, "hbm_frac": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
+        out[f"bev_point_sampling_{tag}"] = {"us": us, "alg_bytes": nbytes, "rate_over_hbm_peak": nbytes / (us * 1e-6) / 1e9 / peak["hbm_gbs"]}
     us = timeit_eager(lambda: bev_reference_points_cam((200, 200), l2i), n=10)  # builds tensors from lists: not capturable
     out["bev_point_sampling_eager_torch_f32"] = {"us": us}
     print(json.dumps(out))
