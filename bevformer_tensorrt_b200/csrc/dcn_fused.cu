@@ -397,27 +397,37 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
           uint32_t r[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mh * kBN + c0, r);
           // out = T2int8((acc * scale_i*scale_w + bias) / scale_o)   (…Conv2dKernel.cu:578-579)
-          if (p0 + c0 + 32 <= HoWo && (reinterpret_cast<uintptr_t>(orow + c0) & 15) == 0) {
+          // The 32 outputs of this lane are 32 consecutive bytes of ONE output row; word j holds pixels 4j .. 4j+3.
+          uint32_t ow[8];
 #pragma unroll
-            for (int v = 0; v < 2; ++v) {
-              uint32_t w4[4];
+          for (int j = 0; j < 8; ++j) {
+            uint32_t word = 0;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint32_t word = 0;
+            for (int i = 0; i < 4; ++i) {
+              const float real = fmaf(__uint_as_float(r[4 * j + i]), p.out_mul, bias);
+              word |= (static_cast<uint32_t>(requant_i8(real, p.out_div, p.out_inv)) & 0xffu) << (8 * i);
+            }
+            ow[j] = word;
+          }
+          // An INT8 row is Ho*Wo BYTES long, so rows start 16-byte aligned only when Ho*Wo % 16 == 0 (the R101 stage-3
+          // map is 58 x 100 = 5800 = 8 mod 16: every other row starts on an 8-byte boundary). Widest store the row's
+          // alignment allows; byte stores (one 32-byte sector touched per byte) only for ragged tails and odd widths.
+          const uintptr_t oa = reinterpret_cast<uintptr_t>(orow + c0);
+          if (p0 + c0 + 32 <= HoWo && (oa & 3) == 0) {
+            if ((oa & 15) == 0) {
+              *reinterpret_cast<uint4 *>(orow + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              *reinterpret_cast<uint4 *>(orow + c0 + 16) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+            } else if ((oa & 7) == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float real = fmaf(__uint_as_float(r[16 * v + 4 * q + i]), p.out_mul, bias);
-                  word |= (static_cast<uint32_t>(requant_i8(real, p.out_div, p.out_inv)) & 0xffu) << (8 * i);
-                }
-                w4[q] = word;
-              }
-              *reinterpret_cast<uint4 *>(orow + c0 + 16 * v) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint2 *>(orow + c0 + 8 * j) = make_uint2(ow[2 * j], ow[2 * j + 1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t *>(orow + c0 + 4 * j) = ow[j];
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (p0 + c0 + i < HoWo)
-                orow[c0 + i] = static_cast<int8_t>(requant_i8(fmaf(__uint_as_float(r[i]), p.out_mul, bias), p.out_div, p.out_inv));
+              if (p0 + c0 + i < HoWo) orow[c0 + i] = static_cast<int8_t>((ow[i >> 2] >> (8 * (i & 3))) & 0xffu);
           }
         } else {
         const float bias = __half2float(__ldg(static_cast<const __half *>(p.bias) + co));

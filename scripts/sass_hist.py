@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "bevformer_tensorrt_b200", "lib", "libb200_bev_ops.so")
 pat = re.compile(sys.argv[1] if len(sys.argv) > 1 else "msda_gather_kernelI6__halfS1_Li32ELi2ELi0ELi0ELb0|msda_gather_kernelIaS|"
-                 "msda_i8p_kernelI6__halfLb0|msda_pack|msda_res_kernelILb0|dcn_fused_kernelILi2ELb0|dcn_generic|"
+                 "msda_i8p_kernelI6__halfLb0|msda_pack|msda_res_kernelILb0|dcn_fused_kernelILi2ELb|dcn_generic|"
                  "grid_sample_2d_kernelILi1ELi0|peer_reduce|rotate_hwc_kernelILi1ELi0|point_sampling_kernelILi4")
 SPECIAL = re.compile(r"^(UTC\w*MMA|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|HMMA|IDP|UTCBAR|SYNCS|FFMA2|FHFMA|REDG|RED)")
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
