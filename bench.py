@@ -92,6 +92,9 @@ def parse():
                          "once at N = 4 on this image, so it is opt-in")
     ap.add_argument("--overlap", action="store_true",
                     help="N>1: overlapped step (peers' rows sampled first, pulled under the own-rows launch); measured slower")
+    ap.add_argument("--no-autotune", action="store_true",
+                    help="keep the library's default MSDA launch shape instead of letting bt.autotune_msda pick one on the "
+                         "step's tensors during warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other distribution / INT8) legs")
     return ap.parse_args()
@@ -290,6 +293,24 @@ def make_op(dtype, tensors):
     return (lambda: bt.multi_scale_deformable_attn(*dev)), (2 if dtype == "f16" else 4), None, dev
 
 
+def autotune_launch_shape(bt, dev, enabled=True):
+    """The product's own tactic selection (bt.autotune_msda: every launch shape of the FP16 / FP32 plugin op is run on
+    THESE tensors, checked bit for bit against the default shape and timed with CUDA events; the fastest identical one is
+    made the process-wide setting). Runs before the warm-up, outside every timed region. Any failure falls back to the
+    default shape and is reported in the line."""
+    if not enabled:
+        bt.set_msda_launch_shape("default")
+        return {"chosen": "default", "note": "--no-autotune"}
+    try:
+        return bt.autotune_msda(*dev)
+    except Exception as e:  # noqa: BLE001 — the bench must still produce its line on the default shape
+        try:
+            bt.set_msda_launch_shape("default")
+        except Exception:  # noqa: BLE001
+            pass
+        return {"chosen": "default", "error": repr(e)}
+
+
 def time_kernel(fn, steps, warmup, flush=None):
     """Per-launch CUDA-event timing on the launching stream. Returns (total ms over steps, per-launch ms list)."""
     for _ in range(warmup):
@@ -321,6 +342,7 @@ def run_single(args, cfg, peak, peak_src):
     host = make_msda_inputs(cfg, args.dist, 0, torch.float32)
     fn, eb, rb, dev = make_op(args.dtype, host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if args.flush_l2 else None
+    tune = autotune_launch_shape(bt, dev, not args.no_autotune) if args.dtype in ("f16", "f32") else None
 
     for _ in range(max(3, args.warmup)):
         fn()
@@ -367,11 +389,17 @@ def run_single(args, cfg, peak, peak_src):
                      "kernel": ("msda_pack_kernel + msda_i8p_kernel: the op's two launches, timed together (pack pre-pass "
                                 "included in the denominator)") if args.dtype == "i8" and v2_on else "msda_gather_kernel",
                      "kernel_ms": k_ms, "kernel_ms_min": per[0],
-                     "launch_shape": "%d unit(s) per warp%s (b200_msda_set_batch_units / B200_MSDA_BATCH)"
-                                     % (bt.get_msda_batch_units()[0], ", grid-strided" if bt.get_msda_batch_units()[1] else ""),
+                     "launch_shape": "%s: %d unit(s) per warp%s, gather variant %d (bt.MSDA_LAUNCH_SHAPES)"
+                                     % ((tune or {}).get("chosen", "default"), bt.get_msda_batch_units()[0],
+                                        ", grid-strided" if bt.get_msda_batch_units()[1] else "", bt.get_msda_gather_variant()),
                      "algorithmic_bytes": alg, "peak_source": peak_src},
         "wall_s": wall,
     }  # fmt: skip
+    if tune is not None:
+        out["autotune"] = dict(tune, what="bt.autotune_msda on this step's device tensors before the warm-up (the product's "
+                                          "tactic selection, as a TensorRT builder times a plugin's tactics): median ms of "
+                                          "every launch shape whose output equals the default shape's bit for bit; the "
+                                          "fastest is used for the timed region, the e2e leg and nothing else is changed")
     return out, fn, dev, host
 
 
@@ -802,6 +830,7 @@ def main():
             h = make_msda_inputs(cfg, dist_name, 0, torch.float32)
             prev = bt.set_msda_v2(v2)
             f2, eb, rb, _d = make_op(dtype, h)
+            leg_tune = autotune_launch_shape(bt, _d, not args.no_autotune) if dtype in ("f16", "f32") else None
             _, per = time_kernel(f2, 30, 5)
             bt.set_msda_v2(prev)
             k = sum(per) / len(per)
@@ -809,8 +838,12 @@ def main():
             key = f"{dtype}_{dist_name}" + ("" if v2 else "_round1_kernel")
             sec[key] = {"kernel_ms": k, "bev_queries_per_s": cfg.num_query / (k * 1e-3),
                         "roofline_frac": alg / (k * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg}
+            if leg_tune is not None:
+                sec[key]["autotune"] = leg_tune
             del f2, _d, h
             torch.cuda.empty_cache()
+        # back to the headline's launch shape for everything that follows
+        bt.set_msda_launch_shape((out.get("autotune") or {}).get("chosen", "default"))
         other = "U" if args.dist == "G" else "G"
         o = sec.get(f"{args.dtype}_{other}")
         if o is not None:

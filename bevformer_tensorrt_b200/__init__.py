@@ -45,6 +45,11 @@ from .functions import (  # noqa: E402
     set_msda_f16_path,
     set_msda_batch_units,
     get_msda_batch_units,
+    set_msda_gather_variant,
+    get_msda_gather_variant,
+    autotune_msda,
+    set_msda_launch_shape,
+    MSDA_LAUNCH_SHAPES,
 )
 
 from .host_pipeline import HostMSDA, empty_pinned  # noqa: E402
@@ -78,5 +83,10 @@ __all__ = [
     "set_msda_f16_path",
     "set_msda_batch_units",
     "get_msda_batch_units",
+    "set_msda_gather_variant",
+    "get_msda_gather_variant",
+    "autotune_msda",
+    "set_msda_launch_shape",
+    "MSDA_LAUNCH_SHAPES",
 ]
 __version__ = "0.1.0"

@@ -65,6 +65,7 @@ SIGNATURES = {
     "b200_msda_set_f16_mode": (_i, [_i]),
     "b200_msda_set_f16_path": (_i, [_i]),
     "b200_msda_set_batch_units": (_i, [_i, _i]),
+    "b200_msda_set_gather_variant": (_i, [_i]),
     "b200_msda_set_resident_bytes": (_i, [_i]),
     "b200_msda_set_i8_resident_bytes": (_i, [_i]),
     "b200_msda_enqueue": (_i, [ctypes.POINTER(TensorDesc), ctypes.POINTER(TensorDesc), ctypes.POINTER(_vp),

@@ -44,6 +44,20 @@ static std::atomic<int> g_res_cap_bytes{128 * 1024};
 // a CTA lie. -1 = not decided yet: the first launch reads the environment variable B200_MSDA_BATCH ("1", "2", "4",
 // "2s", "4s"), else kDefaultBatch. b200_msda_set_batch_units overrides.
 constexpr int kDefaultBatch = 1;
+// Gather-depth variant of the same launch (one-unit grid only): 0 = default (3 CTAs per SM, one point = 4 tap loads in
+// flight per warp), 1 = 2 CTAs per SM (128-register budget, same source: the compiler keeps a chunk's 16 tap loads in
+// flight), 2 = the same with the 16 loads written before the FMAs in the source. Initial value: environment variable
+// B200_MSDA_VARIANT ("0" .. "2"), else 0.
+static std::atomic<int> g_gather_variant{-1};
+static int msda_gather_variant() {
+  int v = g_gather_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char *e = getenv("B200_MSDA_VARIANT");
+    v = (e != nullptr && e[0] >= '0' && e[0] <= '2' && e[1] == '\0') ? e[0] - '0' : 0;
+    g_gather_variant.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 static std::atomic<int> g_batch_units{-1};
 static int msda_batch_units() {
   int v = g_batch_units.load(std::memory_order_relaxed);
@@ -404,9 +418,20 @@ constexpr int kMaxChunks = 64;
 // a camera ring — are answered with zeros straight away; their memory latencies overlap instead of each costing a
 // CTA slot one full DRAM round trip (the UPW = 1 grid spends ~4 k cycles of a CTA slot per invisible block). Visible
 // units run the unchanged body below (which re-reads its 2 offset vectors per lane from L2).
-template <typename T, typename R, int C, int ROUNDS, int MODE, int EPI, bool DBG = false, int UPW = 1>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const MsdaParams prm) {
+//
+// MINB / PIF ("points in flight") are the gather-depth variants (b200_msda_set_gather_variant). At the default register
+// cap (85: 3 CTAs = 24 warps per SM) the compiler rotates four 16-byte tap buffers, i.e. ONE point = 4 tap loads are in
+// flight per warp (SASS: each LDG.E.128 is consumed ~70 instructions after it issues). On camera-ring inputs the kernel
+// is latency-bound (ncu: issue 57 %, L1 58 %, long-scoreboard stalls dominant), so the variants trade warps for loads
+// per warp: MINB = 2 lifts the cap to 128 registers (16 warps per SM) and ptxas then hoists all 16 tap loads of a 4-point
+// chunk above the first FMA by itself (126 registers, no spills; PIF = 2 compiles to the same code and is not
+// instantiated); PIF = 4 states that order in the source. 16 warps x 16 loads against 24 x 4 in flight per SM. The FMA
+// order is unchanged, so every variant returns the same bits.
+template <typename T, typename R, int C, int ROUNDS, int MODE, int EPI, bool DBG = false, int UPW = 1, int MINB = kMinBlocks,
+          int PIF = 1>
+__global__ void __launch_bounds__(kThreads, MINB) msda_gather_kernel(const MsdaParams prm) {
   static_assert(UPW == 1 || EPI == 0, "the batched launch exists for the plugin-op form only");
+  static_assert(PIF == 1 || PIF == 2 || PIF == 4, "points in flight: 1, 2 or 4 of a chunk's 4 points");
   static_assert(UPW >= 1 && UPW <= 8, "visibility bits live in one register");
   using IO = Io<T, MODE>;
   constexpr int VEC = IO::kVec;
@@ -689,6 +714,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) msda_gather_kernel(const
       if (r * LPI + j >= NCH) break;             // uniform
       if ((vm & (OWNER0 << j)) == 0u) continue;  // uniform: chunk out of range for every item of the warp
       const int src = (lane & ~(LPI - 1)) | j;
+      if constexpr (PIF > 1) {
+#pragma unroll
+        for (int k0 = 0; k0 < 4; k0 += PIF) {
+          typename IO::Tap tp[PIF][4];
+          float wp[PIF][NW];
+#pragma unroll
+          for (int i = 0; i < PIF; ++i) {  // addresses, weights and the 4 tap loads of PIF points first ...
+            const unsigned ot = __shfl_sync(kFullMask, otop[k0 + i], src);
+            const unsigned ob = __shfl_sync(kFullMask, obot[k0 + i], src);
+#pragma unroll
+            for (int n = 0; n < NW; ++n) wp[i][n] = __shfl_sync(kFullMask, tw[k0 + i][n], src);
+            const unsigned dx = (ot & 1u) ? step_b : 0u;
+            const char *p0 = vbase + (ot & ~1u);
+            const char *p1 = vbase + ob;
+            tp[i][0] = IO::ld(p0), tp[i][1] = IO::ld(p0 + dx), tp[i][2] = IO::ld(p1), tp[i][3] = IO::ld(p1 + dx);
+          }
+#pragma unroll
+          for (int i = 0; i < PIF; ++i) IO::fma_point(acc, tp[i], wp[i]);  // ... then the FMAs, in the default order
+        }
+        continue;
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const unsigned ot = __shfl_sync(kFullMask, otop[k], src);
@@ -889,6 +935,15 @@ static int launch_gather(const MsdaParams &p, cudaStream_t s) {
       return check_launch();
     }
   }
+  // Gather-depth variants of the same plugin op (one-unit grid, untraced launches): see the kernel's header comment.
+  if constexpr (EPI == 0 && MODE == 0 && ROUNDS <= 2 && !std::is_same<T, int8_t>::value) {
+    const unsigned gb = static_cast<unsigned>(blocks);
+    switch (msda_gather_variant()) {
+      case 1: msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 1, 2, 1><<<gb, kThreads, 0, s>>>(p); return check_launch();
+      case 2: msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 1, 2, 4><<<gb, kThreads, 0, s>>>(p); return check_launch();
+      default: break;
+    }
+  }
   msda_gather_kernel<T, R, C, ROUNDS, MODE, EPI><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(p);
   return check_launch();
 }
@@ -950,6 +1005,12 @@ extern "C" {
 
 int b200_msda_set_f16_mode(int mode) { return g_f16_mode.exchange(mode ? 1 : 0); }
 int b200_msda_set_f16_path(int path) { return g_f16_path.exchange(path ? 1 : 0); }
+int b200_msda_set_gather_variant(int variant) {
+  const int before = msda_gather_variant();
+  if (variant >= 0 && variant <= 2) g_gather_variant.store(variant, std::memory_order_relaxed);
+  return before;  // any other value (e.g. -1) only queries
+}
+
 int b200_msda_set_batch_units(int units, int strided) {
   const int before = msda_batch_units();
   if (units == 1) g_batch_units.store(1, std::memory_order_relaxed);

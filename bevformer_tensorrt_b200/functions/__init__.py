@@ -18,6 +18,11 @@ from .multi_scale_deformable_attn import (
     set_msda_f16_path,
     set_msda_batch_units,
     get_msda_batch_units,
+    set_msda_gather_variant,
+    get_msda_gather_variant,
+    autotune_msda,
+    set_msda_launch_shape,
+    MSDA_LAUNCH_SHAPES,
 )
 from .point_sampling import bev_point_sampling, get_reference_points_3d, point_sampling_trt
 from .rotate import rotate, rotate2, rotate_chw2, rotate_hwc, rotate_int8

@@ -59,6 +59,82 @@ def get_msda_batch_units():
     return prev & 0xFF, bool(prev >> 8)
 
 
+def set_msda_gather_variant(variant: int) -> int:
+    """Gather depth of the FP32 / FP16 plugin op (C entry b200_msda_set_gather_variant): 0 = default (24 warps per SM,
+    one sampling point = 4 tap loads in flight per warp), 1 / 2 = 16 warps per SM with the 16 tap loads of a 4-point chunk
+    in flight per warp (compiler-scheduled / written out). Same bits for every variant. Returns the previous variant."""
+    if variant not in (0, 1, 2):
+        raise ValueError("variant must be 0, 1 or 2")
+    return int(_lib.load().b200_msda_set_gather_variant(int(variant)))
+
+
+def get_msda_gather_variant() -> int:
+    return int(_lib.load().b200_msda_set_gather_variant(-1))
+
+
+#: launch shapes autotune_msda tries: name -> (units per warp, grid-strided units, gather variant)
+MSDA_LAUNCH_SHAPES = {
+    "default": (1, False, 0),
+    "batch2_strided": (2, True, 0),
+    "deep_gather": (1, False, 1),
+    "deep_gather_explicit": (1, False, 2),
+}
+
+
+def autotune_msda(value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights, iters=12, warmup=3,
+                  min_gain=0.02):
+    """Picks the launch shape of the FP32 / FP16 plugin op for THESE tensors the way a TensorRT builder picks a tactic:
+    every shape in ``MSDA_LAUNCH_SHAPES`` is run on the given CUDA tensors, its output is compared bit for bit with the
+    default shape's (a shape that differs is discarded, whatever its speed), and it is timed with CUDA events on the
+    current stream (median of ``iters`` after ``warmup``). The fastest shape is made the process-wide setting if it beats
+    the default by more than ``min_gain``; otherwise the default stays. Which shape wins depends on the input
+    distribution (dense sampling is bound by the L1 line rate and wants warps; camera-ring inputs are latency-bound and
+    want loads in flight), which the op cannot know from its arguments. Returns a report dict
+    ``{"chosen": name, "ms": {name: median ms}, "rejected": [names]}``."""
+    if not value.is_cuda or value.dtype not in (torch.float16, torch.float32):
+        raise ValueError("autotune_msda: FP16 / FP32 CUDA tensors only (the INT8 op has a single launch shape)")
+    args = (value, value_spatial_shapes, reference_points, sampling_offsets, attention_weights)
+    report = {"chosen": "default", "ms": {}, "rejected": []}
+    set_msda_batch_units(1)
+    set_msda_gather_variant(0)
+    try:
+        base = multi_scale_deformable_attn(*args)
+        for name, (units, strided, variant) in MSDA_LAUNCH_SHAPES.items():
+            set_msda_batch_units(units, strided)
+            set_msda_gather_variant(variant)
+            out = multi_scale_deformable_attn(*args)
+            if not torch.equal(out, base):
+                report["rejected"].append(name)
+                continue
+            for _ in range(warmup):
+                multi_scale_deformable_attn(*args)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+            for a, b in evs:
+                a.record()
+                multi_scale_deformable_attn(*args)
+                b.record()
+            torch.cuda.synchronize(value.device)
+            per = sorted(a.elapsed_time(b) for a, b in evs)
+            report["ms"][name] = per[len(per) // 2]
+    finally:
+        set_msda_batch_units(1)
+        set_msda_gather_variant(0)
+    best = min(report["ms"], key=report["ms"].get)
+    if best != "default" and report["ms"][best] < report["ms"]["default"] * (1.0 - min_gain):
+        report["chosen"] = best
+    units, strided, variant = MSDA_LAUNCH_SHAPES[report["chosen"]]
+    set_msda_batch_units(units, strided)
+    set_msda_gather_variant(variant)
+    return report
+
+
+def set_msda_launch_shape(name: str):
+    """Applies one of ``MSDA_LAUNCH_SHAPES`` by name (e.g. the ``chosen`` entry of an earlier ``autotune_msda`` report)."""
+    units, strided, variant = MSDA_LAUNCH_SHAPES[name]
+    set_msda_batch_units(units, strided)
+    set_msda_gather_variant(variant)
+
+
 def _v2_workspace(lib, dims, device):
     """Workspace tensor for the INT8 v2 path, or None when the shape is outside its envelope (or v2 is switched off)."""
     if not _V2["enabled"]:

@@ -280,3 +280,117 @@ def test_c_header_is_plain_c_and_the_example_host_runs(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "accepted for all six tensors" in r.stdout and "status 2" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# launch-shape switches and the autotuner (host logic: no kernel is launched here)
+# ---------------------------------------------------------------------------------------------------------------
+def test_launch_shape_setters_round_trip_without_gpu():
+    lib = _lib.load()
+    prev_units, prev_var = bt.get_msda_batch_units(), bt.get_msda_gather_variant()
+    try:
+        assert bt.set_msda_batch_units(4, True) == prev_units
+        assert bt.get_msda_batch_units() == (4, True)
+        assert lib.b200_msda_set_batch_units(3, 0) == (4 | 0x100)  # 3 is not a launch shape: query only
+        assert bt.get_msda_batch_units() == (4, True)
+        assert bt.set_msda_batch_units(1) == (4, True) and bt.get_msda_batch_units() == (1, False)
+        with pytest.raises(ValueError):
+            bt.set_msda_batch_units(8)
+        assert bt.set_msda_gather_variant(2) == prev_var and bt.get_msda_gather_variant() == 2
+        assert lib.b200_msda_set_gather_variant(7) == 2 and bt.get_msda_gather_variant() == 2  # out of range: query only
+        with pytest.raises(ValueError):
+            bt.set_msda_gather_variant(3)
+        for name, (units, strided, variant) in bt.MSDA_LAUNCH_SHAPES.items():
+            bt.set_msda_launch_shape(name)
+            assert bt.get_msda_batch_units() == (units, strided) and bt.get_msda_gather_variant() == variant
+    finally:
+        bt.set_msda_batch_units(*prev_units)
+        bt.set_msda_gather_variant(prev_var)
+
+
+def test_launch_shape_environment_variables(tmp_path):
+    """B200_MSDA_BATCH / B200_MSDA_VARIANT are read once, by the first query of a fresh process."""
+    import subprocess
+    import sys
+
+    code = ("import bevformer_tensorrt_b200 as bt; "
+            "print(bt.get_msda_batch_units(), bt.get_msda_gather_variant())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(env):
+        e = dict(os.environ, PYTHONPATH=root, **env)
+        return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, cwd=root).stdout.strip()
+
+    assert run({}) == "(1, False) 0"
+    assert run({"B200_MSDA_BATCH": "4s", "B200_MSDA_VARIANT": "1"}) == "(4, True) 1"
+    assert run({"B200_MSDA_BATCH": "2", "B200_MSDA_VARIANT": "2"}) == "(2, False) 2"
+    assert run({"B200_MSDA_BATCH": "3", "B200_MSDA_VARIANT": "9"}) == "(1, False) 0"  # not launch shapes: ignored
+    assert run({"B200_MSDA_BATCH": "1s"}) == "(1, False) 0"
+
+
+class _FakeCudaTensor:
+    """Stands in for a CUDA tensor in the autotuner's argument checks (no kernel runs in this test)."""
+
+    is_cuda, dtype, device = True, torch.float16, "cpu"
+
+
+def _run_fake_autotune(monkeypatch, speeds, wrong=()):
+    """Drives autotune_msda with a fake op: `speeds` = simulated ms per launch shape name, `wrong` = shapes whose output
+    differs from the default's."""
+    import sys
+
+    mod = sys.modules["bevformer_tensorrt_b200.functions.multi_scale_deformable_attn"]  # the module, not the op of that name
+    clock = {"t": 0.0}
+    shapes_by_setting = {v: k for k, v in bt.MSDA_LAUNCH_SHAPES.items()}
+
+    def current():
+        units, strided = bt.get_msda_batch_units()
+        return shapes_by_setting[(units, strided, bt.get_msda_gather_variant())]
+
+    def fake_op(*_a):
+        name = current()
+        clock["t"] += speeds[name]
+        return torch.full((4,), 1.0 if name in wrong else 0.0)
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            self.t = None
+
+        def record(self):
+            self.t = clock["t"]
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    monkeypatch.setattr(mod, "multi_scale_deformable_attn", fake_op)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *_a, **_k: None)
+    t = _FakeCudaTensor()
+    return mod.autotune_msda(t, t, t, t, t)
+
+
+def test_autotuner_picks_the_fastest_identical_shape(monkeypatch):
+    prev_units, prev_var = bt.get_msda_batch_units(), bt.get_msda_gather_variant()
+    try:
+        # a clearly faster shape wins and becomes the process-wide setting
+        rep = _run_fake_autotune(monkeypatch, {"default": 1.0, "batch2_strided": 0.97, "deep_gather": 0.80,
+                                               "deep_gather_explicit": 0.85})
+        assert rep["chosen"] == "deep_gather" and rep["rejected"] == []
+        assert abs(rep["ms"]["deep_gather"] - 0.80) < 1e-9 and abs(rep["ms"]["default"] - 1.0) < 1e-9
+        assert bt.get_msda_batch_units() == (1, False) and bt.get_msda_gather_variant() == 1
+        # a faster shape whose bits differ is never taken, whatever its speed
+        rep = _run_fake_autotune(monkeypatch, {"default": 1.0, "batch2_strided": 0.9, "deep_gather": 0.1,
+                                               "deep_gather_explicit": 0.95}, wrong=("deep_gather",))
+        assert rep["chosen"] == "batch2_strided" and rep["rejected"] == ["deep_gather"] and "deep_gather" not in rep["ms"]
+        assert bt.get_msda_batch_units() == (2, True) and bt.get_msda_gather_variant() == 0
+        # gains inside the noise band (min_gain = 2 %) leave the default in place
+        rep = _run_fake_autotune(monkeypatch, {"default": 1.0, "batch2_strided": 0.99, "deep_gather": 0.985,
+                                               "deep_gather_explicit": 1.2})
+        assert rep["chosen"] == "default"
+        assert bt.get_msda_batch_units() == (1, False) and bt.get_msda_gather_variant() == 0
+        # CPU tensors are refused before anything is touched
+        with pytest.raises(ValueError):
+            bt.autotune_msda(*(torch.zeros(1),) * 5)
+    finally:
+        bt.set_msda_batch_units(*prev_units)
+        bt.set_msda_gather_variant(prev_var)

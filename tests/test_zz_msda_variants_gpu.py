@@ -1,0 +1,80 @@
+"""GPU tests of the gather-depth variants of the MSDA plugin op (csrc/msda.cu MINB / PIF) and of the launch-shape
+autotuner. The variants change how many tap loads a warp keeps in flight, not a single arithmetic statement or its
+order, so the bar is identity of bytes with the default launch — which tests/test_msda_gpu.py holds against the oracle,
+the reference's golden vectors and the reference's own CUDA kernels. (The file sorts last on purpose: these variants
+were written after the round's last GPU minute was spent, so the driver's run is their first execution on hardware.)"""
+import numpy as np
+import pytest
+import torch
+
+import bevformer_tensorrt_b200 as bt
+from bevformer_tensorrt_b200.workloads import CONFIGS, MSDAConfig, make_msda_inputs
+from oracle import msda as omsda
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "g2": MSDAConfig("g2", 2, 129, 8, 32, ((9, 11), (5, 6)), 8, 2),
+    "ragged_tail": MSDAConfig("ragged_tail", 1, 37, 5, 32, ((8, 8), (4, 4)), 4, 1),
+    "tsa_like": MSDAConfig("tsa_like", 2, 1000, 8, 32, ((30, 30),), 4, 1),
+    "one_pixel": MSDAConfig("one_pixel", 1, 64, 8, 32, ((1, 1), (1, 7), (7, 1)), 4, 4),
+    "many_points": MSDAConfig("many_points", 1, 40, 8, 32, ((10, 12), (5, 6), (3, 3), (2, 2)), 16, 4),
+}
+
+
+@pytest.fixture
+def restore_launch_shape():
+    units, variant = bt.get_msda_batch_units(), bt.get_msda_gather_variant()
+    yield
+    bt.set_msda_batch_units(*units)
+    bt.set_msda_gather_variant(variant)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("name,dist,seed", [("small_sca", "edge", 131), ("small_sca", "U", 132), ("tiny_sca", "G", 133),
+                                            ("tsa_like", "edge", 134), ("g2", "edge", 135), ("ragged_tail", "edge", 136),
+                                            ("one_pixel", "edge", 137), ("many_points", "edge", 138)])  # fmt: skip
+def test_gather_variants_are_bit_identical(name, dist, seed, dtype, restore_launch_shape):
+    cfg = CONFIGS.get(name) or CASES[name]
+    inputs = make_msda_inputs(cfg, dist, seed, dtype)
+    dev = [t.cuda() for t in inputs]
+    bt.set_msda_batch_units(1)
+    bt.set_msda_gather_variant(0)
+    base = bt.multi_scale_deformable_attn(*dev)
+    want = omsda.msda_f32(*(t.float().numpy() for t in inputs))
+    assert np.abs(base.float().cpu().numpy() - want).max() < (1e-5 if dtype == torch.float32 else 1e-3)
+    for variant in (1, 2):
+        bt.set_msda_gather_variant(variant)
+        got = bt.multi_scale_deformable_attn(*dev)
+        assert torch.equal(got, base), (name, variant, (got.float() - base.float()).abs().max().item())
+
+
+@pytest.mark.parametrize("dist", ["U", "G"])
+def test_gather_variants_bit_identical_at_base_shapes(dist, restore_launch_shape):
+    cfg = CONFIGS["base_sca"]
+    dev = [t.cuda() for t in make_msda_inputs(cfg, dist, 2, torch.float16)]
+    dev32 = [t.float() if t.is_floating_point() else t for t in dev]
+    bt.set_msda_batch_units(1)
+    bt.set_msda_gather_variant(0)
+    base16, base32 = bt.multi_scale_deformable_attn(*dev), bt.multi_scale_deformable_attn(*dev32)
+    for variant in (1, 2):
+        bt.set_msda_gather_variant(variant)
+        assert torch.equal(bt.multi_scale_deformable_attn(*dev), base16), variant
+        assert torch.equal(bt.multi_scale_deformable_attn(*dev32), base32), variant
+
+
+@pytest.mark.parametrize("dist", ["U", "G"])
+def test_autotuner_on_hardware(dist, restore_launch_shape):
+    """The autotuner on real tensors: every shape it timed produced the default's bits (nothing rejected), it leaves a
+    valid launch shape behind, and the op's result under that shape is still the default's."""
+    cfg = CONFIGS["base_sca"]
+    dev = [t.cuda() for t in make_msda_inputs(cfg, dist, 3, torch.float16)]
+    bt.set_msda_launch_shape("default")
+    base = bt.multi_scale_deformable_attn(*dev)
+    rep = bt.autotune_msda(*dev, iters=6, warmup=2)
+    print(f"\n[autotune {dist}] {rep}")
+    assert rep["rejected"] == []
+    assert set(rep["ms"]) == set(bt.MSDA_LAUNCH_SHAPES) and all(v > 0 for v in rep["ms"].values())
+    units, strided, variant = bt.MSDA_LAUNCH_SHAPES[rep["chosen"]]
+    assert bt.get_msda_batch_units() == (units, strided) and bt.get_msda_gather_variant() == variant
+    assert torch.equal(bt.multi_scale_deformable_attn(*dev), base)
