@@ -46,14 +46,14 @@ static std::atomic<int> g_res_cap_bytes{128 * 1024};
 constexpr int kDefaultBatch = 1;
 // Gather-depth variant of the same launch (one-unit grid only): 0 = default (3 CTAs per SM, one point = 4 tap loads in
 // flight per warp), 1 = 2 CTAs per SM (128-register budget, same source: the compiler keeps a chunk's 16 tap loads in
-// flight), 2 = the same with the 16 loads written before the FMAs in the source. Initial value: environment variable
-// B200_MSDA_VARIANT ("0" .. "2"), else 0.
+// flight), 2 = the same with the 16 loads written before the FMAs in the source, 3 = 128-thread CTAs, 5 per SM (20 warps,
+// 96 registers: the point in between). Initial value: environment variable B200_MSDA_VARIANT ("0" .. "3"), else 0.
 static std::atomic<int> g_gather_variant{-1};
 static int msda_gather_variant() {
   int v = g_gather_variant.load(std::memory_order_relaxed);
   if (v < 0) {
     const char *e = getenv("B200_MSDA_VARIANT");
-    v = (e != nullptr && e[0] >= '0' && e[0] <= '2' && e[1] == '\0') ? e[0] - '0' : 0;
+    v = (e != nullptr && e[0] >= '0' && e[0] <= '3' && e[1] == '\0') ? e[0] - '0' : 0;
     g_gather_variant.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -427,9 +427,12 @@ constexpr int kMaxChunks = 64;
 // chunk above the first FMA by itself (126 registers, no spills; PIF = 2 compiles to the same code and is not
 // instantiated); PIF = 4 states that order in the source. 16 warps x 16 loads against 24 x 4 in flight per SM. The FMA
 // order is unchanged, so every variant returns the same bits.
+// NT = threads per CTA: warps never synchronise with each other and there is no shared memory, so a CTA is only a
+// scheduling and register-allocation unit; NT = 128 with MINB = 5 is the middle point (20 warps per SM, 96 registers).
 template <typename T, typename R, int C, int ROUNDS, int MODE, int EPI, bool DBG = false, int UPW = 1, int MINB = kMinBlocks,
-          int PIF = 1>
-__global__ void __launch_bounds__(kThreads, MINB) msda_gather_kernel(const MsdaParams prm) {
+          int PIF = 1, int NT = kThreads>
+__global__ void __launch_bounds__(NT, MINB) msda_gather_kernel(const MsdaParams prm) {
+  static_assert(NT % 32 == 0 && NT >= 32 && NT <= 1024, "whole warps");
   static_assert(UPW == 1 || EPI == 0, "the batched launch exists for the plugin-op form only");
   static_assert(PIF == 1 || PIF == 2 || PIF == 4, "points in flight: 1, 2 or 4 of a chunk's 4 points");
   static_assert(UPW >= 1 && UPW <= 8, "visibility bits live in one register");
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_gather_kernel(const MsdaP
   constexpr int VEC = IO::kVec;
   constexpr int LPI = C / VEC;
   constexpr int IPW = 32 / LPI;
-  constexpr int IPB = IPW * (kThreads / 32);
+  constexpr int IPB = IPW * (NT / 32);
   constexpr int NW = IO::kWt;
   // lanes whose sub-index is 0 (one per item of the warp); shifted by j it selects the owner lanes j
   constexpr unsigned OWNER0 = LPI == 1 ? 0xffffffffu
@@ -941,6 +944,13 @@ static int launch_gather(const MsdaParams &p, cudaStream_t s) {
     switch (msda_gather_variant()) {
       case 1: msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 1, 2, 1><<<gb, kThreads, 0, s>>>(p); return check_launch();
       case 2: msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 1, 2, 4><<<gb, kThreads, 0, s>>>(p); return check_launch();
+      case 3: {  // 128-thread CTAs, 5 per SM
+        constexpr int IPB128 = (32 / LPI) * (128 / 32);
+        const long long b128 = (p.items + IPB128 - 1) / IPB128;
+        if (b128 > 0x7fffffffll) break;
+        msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 1, 5, 2, 128><<<static_cast<unsigned>(b128), 128, 0, s>>>(p);
+        return check_launch();
+      }
       default: break;
     }
   }
@@ -1007,7 +1017,7 @@ int b200_msda_set_f16_mode(int mode) { return g_f16_mode.exchange(mode ? 1 : 0);
 int b200_msda_set_f16_path(int path) { return g_f16_path.exchange(path ? 1 : 0); }
 int b200_msda_set_gather_variant(int variant) {
   const int before = msda_gather_variant();
-  if (variant >= 0 && variant <= 2) g_gather_variant.store(variant, std::memory_order_relaxed);
+  if (variant >= 0 && variant <= 3) g_gather_variant.store(variant, std::memory_order_relaxed);
   return before;  // any other value (e.g. -1) only queries
 }
 

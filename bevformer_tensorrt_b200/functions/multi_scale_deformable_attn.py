@@ -62,9 +62,10 @@ def get_msda_batch_units():
 def set_msda_gather_variant(variant: int) -> int:
     """Gather depth of the FP32 / FP16 plugin op (C entry b200_msda_set_gather_variant): 0 = default (24 warps per SM,
     one sampling point = 4 tap loads in flight per warp), 1 / 2 = 16 warps per SM with the 16 tap loads of a 4-point chunk
-    in flight per warp (compiler-scheduled / written out). Same bits for every variant. Returns the previous variant."""
-    if variant not in (0, 1, 2):
-        raise ValueError("variant must be 0, 1 or 2")
+    in flight per warp (compiler-scheduled / written out), 3 = 20 warps per SM in 128-thread CTAs with 2 points = 8 loads
+    issued together. Same bits for every variant. Returns the previous variant."""
+    if variant not in (0, 1, 2, 3):
+        raise ValueError("variant must be 0, 1, 2 or 3")
     return int(_lib.load().b200_msda_set_gather_variant(int(variant)))
 
 
@@ -78,6 +79,7 @@ MSDA_LAUNCH_SHAPES = {
     "batch2_strided": (2, True, 0),
     "deep_gather": (1, False, 1),
     "deep_gather_explicit": (1, False, 2),
+    "mid_gather": (1, False, 3),
 }
 
 

@@ -232,9 +232,10 @@ int b200_msda_set_batch_units(int units, int strided);
 
 /* Gather depth of the same plugin op (one-unit grid, untraced launches): 0 (default) = 3 CTAs of 8 warps per SM, the 4 tap
  * loads of one sampling point in flight per warp; 1 = 2 CTAs per SM (128-register budget): the 16 tap loads of a 4-point
- * chunk in flight per warp; 2 = the same with that order written out in the source — fewer warps, more loads per warp, for
- * inputs on which the kernel is latency-bound. Same bits for every variant (the FMA order does not change). Any other
- * value (e.g. -1) only queries. Initial value: environment variable B200_MSDA_VARIANT ("0" .. "2"), else 0. Returns the
+ * chunk in flight per warp; 2 = the same with that order written out in the source; 3 = 128-thread CTAs, 5 per SM (20 warps,
+ * 96 registers), two points = 8 loads issued together — fewer warps, more loads per warp, for inputs on which the kernel is
+ * latency-bound. Same bits for every variant (the FMA order does not change). Any other value (e.g. -1) only queries.
+ * Initial value: environment variable B200_MSDA_VARIANT ("0" .. "3"), else 0. Returns the
  * previous setting. A batched launch (units > 1 above) takes precedence over the variant. */
 int b200_msda_set_gather_variant(int variant);
 

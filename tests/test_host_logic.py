@@ -299,7 +299,7 @@ def test_launch_shape_setters_round_trip_without_gpu():
         assert bt.set_msda_gather_variant(2) == prev_var and bt.get_msda_gather_variant() == 2
         assert lib.b200_msda_set_gather_variant(7) == 2 and bt.get_msda_gather_variant() == 2  # out of range: query only
         with pytest.raises(ValueError):
-            bt.set_msda_gather_variant(3)
+            bt.set_msda_gather_variant(4)
         for name, (units, strided, variant) in bt.MSDA_LAUNCH_SHAPES.items():
             bt.set_msda_launch_shape(name)
             assert bt.get_msda_batch_units() == (units, strided) and bt.get_msda_gather_variant() == variant
@@ -374,18 +374,18 @@ def test_autotuner_picks_the_fastest_identical_shape(monkeypatch):
     try:
         # a clearly faster shape wins and becomes the process-wide setting
         rep = _run_fake_autotune(monkeypatch, {"default": 1.0, "batch2_strided": 0.97, "deep_gather": 0.80,
-                                               "deep_gather_explicit": 0.85})
+                                               "deep_gather_explicit": 0.85, "mid_gather": 0.9})
         assert rep["chosen"] == "deep_gather" and rep["rejected"] == []
         assert abs(rep["ms"]["deep_gather"] - 0.80) < 1e-9 and abs(rep["ms"]["default"] - 1.0) < 1e-9
         assert bt.get_msda_batch_units() == (1, False) and bt.get_msda_gather_variant() == 1
         # a faster shape whose bits differ is never taken, whatever its speed
         rep = _run_fake_autotune(monkeypatch, {"default": 1.0, "batch2_strided": 0.9, "deep_gather": 0.1,
-                                               "deep_gather_explicit": 0.95}, wrong=("deep_gather",))
+                                               "deep_gather_explicit": 0.95, "mid_gather": 0.93}, wrong=("deep_gather",))
         assert rep["chosen"] == "batch2_strided" and rep["rejected"] == ["deep_gather"] and "deep_gather" not in rep["ms"]
         assert bt.get_msda_batch_units() == (2, True) and bt.get_msda_gather_variant() == 0
         # gains inside the noise band (min_gain = 2 %) leave the default in place
         rep = _run_fake_autotune(monkeypatch, {"default": 1.0, "batch2_strided": 0.99, "deep_gather": 0.985,
-                                               "deep_gather_explicit": 1.2})
+                                               "deep_gather_explicit": 1.2, "mid_gather": 1.01})
         assert rep["chosen"] == "default"
         assert bt.get_msda_batch_units() == (1, False) and bt.get_msda_gather_variant() == 0
         # CPU tensors are refused before anything is touched
