@@ -311,6 +311,22 @@ def autotune_launch_shape(bt, dev, enabled=True):
         return {"chosen": "default", "error": repr(e)}
 
 
+def autotune_fused(bt, run, result, enabled=True):
+    """bt.autotune_msda_fused for the fused spatial-cross-attention forms (default launch vs 2 CTAs per SM), with the same
+    fall-back rule as autotune_launch_shape. Local launches only: safe per rank before a collective step."""
+    if not enabled:
+        bt.set_msda_gather_variant(0)
+        return {"chosen": "default", "note": "--no-autotune"}
+    try:
+        return bt.autotune_msda_fused(run, result)
+    except Exception as e:  # noqa: BLE001
+        try:
+            bt.set_msda_gather_variant(0)
+        except Exception:  # noqa: BLE001
+            pass
+        return {"chosen": "default", "error": repr(e)}
+
+
 def time_kernel(fn, steps, warmup, flush=None):
     """Per-launch CUDA-event timing on the launching stream. Returns (total ms over steps, per-launch ms list)."""
     for _ in range(warmup):
@@ -632,6 +648,19 @@ def run_multi(args, cfg, peak, peak_src):
         smp = GroupedSCASampler(shard, width, bt.multi_scale_deformable_attn_sca, exchange="nccl").load(
             value, shapes, ref, off, logits, bev_mask.to(td), dev).connect(plan, dev)
 
+    # launch shape of the fused sampling kernel, picked per rank on its own shard (local launches only, no collective inside)
+    tune_scratch = torch.zeros(shard.q1 - shard.q0, width, device=dev)
+
+    def tune_run():
+        tune_scratch.zero_()
+        smp.compute(tune_scratch)
+
+    fused_tune = autotune_fused(bt, tune_run, lambda: tune_scratch, not args.no_autotune)
+    my_variant = bt.get_msda_gather_variant()
+    deep = torch.tensor([1.0 if fused_tune.get("chosen") == "deep_gather" else 0.0], device=dev)
+    dist.all_reduce(deep, op=dist.ReduceOp.SUM)
+    del tune_scratch
+
     for _ in range(max(3, args.warmup)):
         smp.step()
     torch.cuda.synchronize()
@@ -655,7 +684,7 @@ def run_multi(args, cfg, peak, peak_src):
     pad[: got.shape[0]] = got
     gathered = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
     dist.gather(pad, gathered, dst=0)
-    max_abs_vs_1gpu = anchor_ms = None
+    max_abs_vs_1gpu = anchor_ms = anchor_tune = None
     if rank == 0:
         full = [t.to(dev) for t in (value, shapes, ref, off, logits)]
         want = bt.multi_scale_deformable_attn_sca(*full, bev_mask.to(dev))
@@ -670,8 +699,10 @@ def run_multi(args, cfg, peak, peak_src):
             want.zero_()
             bt.multi_scale_deformable_attn_sca(*full, bm_d, want)
 
+        anchor_tune = autotune_fused(bt, one_gpu_step, lambda: want, not args.no_autotune)  # the anchor gets its own best shape
         _, per1 = time_kernel(one_gpu_step, 20, 3)
         anchor_ms = sum(per1) / len(per1)
+        bt.set_msda_gather_variant(my_variant)  # back to the shape picked for this rank's shard
         del full, want, bm_d
     del value, ref, off, logits
     torch.cuda.empty_cache()
@@ -768,6 +799,9 @@ def run_multi(args, cfg, peak, peak_src):
                                       "none": "no exchange (one camera group)"}[smp.exchange],
                          "result": f"every rank owns the final fp32 rows of {shard.own1 - shard.own0} BEV queries"},
             "max_abs_vs_1gpu": max_abs_vs_1gpu,
+            "autotune": {"what": "bt.autotune_msda_fused per rank on its own shard before the warm-up (default launch vs 2 CTAs "
+                                 "per SM with 16 tap loads in flight per warp; result checked against the default's)",
+                         "rank0": fused_tune, "ranks_on_deep_gather": int(deep.item()), "scaling_anchor": anchor_tune},
             "launch_mode": ("CUDA graph replay, two steps per graph (sampling launch + exchange launch each)" if graphed
                             else "eager launches (two per step)"),
             "scaling_anchor": {"what": "the same fused step (all cameras, all queries, no exchange) on rank 0's GPU alone, "
@@ -870,24 +904,33 @@ def main():
                 acc.zero_()
                 bt.multi_scale_deformable_attn_sca(*h, bm, acc)
 
+            tune_f = autotune_fused(bt, fused, lambda: acc, not args.no_autotune)
             _, per = time_kernel(fused, 30, 5)
             k = sum(per) / len(per)
             sec[f"f16_{dist_name}_fused_sca_{'uniform' if dist_name == 'U' else 'ring'}_mask"] = {
-                "kernel_ms": k, "bev_queries_per_s": cfg.num_query / (k * 1e-3),
+                "kernel_ms": k, "bev_queries_per_s": cfg.num_query / (k * 1e-3), "autotune": tune_f,
                 "note": "zero the 41 MB fp32 accumulator + fused kernel; no per-camera output; "
                         + ("uniform 1/6 visibility = same sampling work as the plugin op (N=1 anchor of the scaling curve)"
                            if dist_name == "U" else "camera-ring bev_mask")}
             # camera-shared form: offsets / logits passed once (the reference repeats the query per camera, so the
             # plugin's six copies are identical), cameras looped in registers, one plain store per slot
             hs = [h[0], h[1], h[2], h[3][:1].contiguous(), h[4][:1].contiguous()]
-            _, per = time_kernel(lambda: bt.multi_scale_deformable_attn_sca_shared(*hs, bm), 30, 5)
+            last = [None]
+
+            def shared():
+                last[0] = bt.multi_scale_deformable_attn_sca_shared(*hs, bm)
+
+            tune_s = autotune_fused(bt, shared, lambda: last[0], not args.no_autotune)
+            _, per = time_kernel(shared, 30, 5)
             k = sum(per) / len(per)
             sb = 2 * (h[0].numel() + h[2].numel() + hs[3].numel() + hs[4].numel()) + 4 * bm.numel() + 4 * acc.numel()
             sec[f"f16_{dist_name}_shared_sca"] = {"kernel_ms": k, "bev_queries_per_s": cfg.num_query / (k * 1e-3),
                                                   "algorithmic_bytes": sb,
                                                   "roofline_frac": sb / (k * 1e-3) / 1e9 / peak,
+                                                  "autotune": tune_s,
                                                   "note": "offsets/logits once for all cameras; single kernel, no memset"}
-            del h, hs
+            del h, hs, last
+        bt.set_msda_launch_shape((out.get("autotune") or {}).get("chosen", "default"))  # the headline's launch shape again
         torch.cuda.empty_cache()
         anchor = sec.get(f"f16_{args.dist}_fused_sca_{'uniform' if args.dist == 'U' else 'ring'}_mask")
         if anchor is not None and args.dtype == "f16":

@@ -48,6 +48,7 @@ from .functions import (  # noqa: E402
     set_msda_gather_variant,
     get_msda_gather_variant,
     autotune_msda,
+    autotune_msda_fused,
     set_msda_launch_shape,
     MSDA_LAUNCH_SHAPES,
 )
@@ -86,6 +87,7 @@ __all__ = [
     "set_msda_gather_variant",
     "get_msda_gather_variant",
     "autotune_msda",
+    "autotune_msda_fused",
     "set_msda_launch_shape",
     "MSDA_LAUNCH_SHAPES",
 ]

@@ -954,6 +954,14 @@ static int launch_gather(const MsdaParams &p, cudaStream_t s) {
       default: break;
     }
   }
+  // The fused spatial-cross-attention forms follow the same switch with one alternative: any non-zero gather variant runs
+  // them at 2 CTAs per SM (same source, 128-register budget: a chunk's 16 tap loads in flight per warp).
+  if constexpr (EPI != 0 && MODE == 0 && ROUNDS <= 2) {
+    if (msda_gather_variant() != 0) {
+      msda_gather_kernel<T, R, C, ROUNDS, 0, EPI, false, 1, 2, 1><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(p);
+      return check_launch();
+    }
+  }
   msda_gather_kernel<T, R, C, ROUNDS, MODE, EPI><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(p);
   return check_launch();
 }

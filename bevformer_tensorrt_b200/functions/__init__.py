@@ -21,6 +21,7 @@ from .multi_scale_deformable_attn import (
     set_msda_gather_variant,
     get_msda_gather_variant,
     autotune_msda,
+    autotune_msda_fused,
     set_msda_launch_shape,
     MSDA_LAUNCH_SHAPES,
 )

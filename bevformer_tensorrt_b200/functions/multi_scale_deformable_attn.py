@@ -130,6 +130,47 @@ def autotune_msda(value, value_spatial_shapes, reference_points, sampling_offset
     return report
 
 
+def autotune_msda_fused(run, result, iters=10, warmup=2, tol=1e-4, min_gain=0.02):
+    """Same idea for the fused spatial-cross-attention forms (``multi_scale_deformable_attn_sca`` /
+    ``…_sca_shared``, and through them the sharded multi-GPU step), which have two launch shapes: the default and the
+    2-CTAs-per-SM one (any non-zero gather variant). ``run()`` launches the caller's step on the current stream (e.g.
+    zero the accumulator + fused op), ``result()`` returns the tensor it produced. The alternative is accepted only if
+    its result agrees with the default's to ``tol`` x max|result| (the camera sum uses floating-point atomics, so the last
+    bits depend on arrival order in either shape) and it is faster by more than ``min_gain``. Leaves the winner as the
+    process-wide gather variant and returns ``{"chosen": "default" | "deep_gather", "ms": {...}, "rejected": [...]}``.
+    Local launches only — safe to call per rank before a collective step."""
+    report = {"chosen": "default", "ms": {}, "rejected": []}
+    names = {"default": 0, "deep_gather": 1}
+    set_msda_gather_variant(0)
+    try:
+        run()
+        base = result().detach().float().clone()
+        scale = max(1.0, float(base.abs().max()))
+        for name, variant in names.items():
+            set_msda_gather_variant(variant)
+            run()
+            if float((result().detach().float() - base).abs().max()) > tol * scale:
+                report["rejected"].append(name)
+                continue
+            for _ in range(warmup):
+                run()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+            for a, b in evs:
+                a.record()
+                run()
+                b.record()
+            torch.cuda.synchronize()
+            per = sorted(a.elapsed_time(b) for a, b in evs)
+            report["ms"][name] = per[len(per) // 2]
+    finally:
+        set_msda_gather_variant(0)
+    ms = report["ms"]
+    if "deep_gather" in ms and "default" in ms and ms["deep_gather"] < ms["default"] * (1.0 - min_gain):
+        report["chosen"] = "deep_gather"
+    set_msda_gather_variant(names[report["chosen"]])
+    return report
+
+
 def set_msda_launch_shape(name: str):
     """Applies one of ``MSDA_LAUNCH_SHAPES`` by name (e.g. the ``chosen`` entry of an earlier ``autotune_msda`` report)."""
     units, strided, variant = MSDA_LAUNCH_SHAPES[name]

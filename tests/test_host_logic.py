@@ -394,3 +394,44 @@ def test_autotuner_picks_the_fastest_identical_shape(monkeypatch):
     finally:
         bt.set_msda_batch_units(*prev_units)
         bt.set_msda_gather_variant(prev_var)
+
+
+def test_fused_autotuner_logic(monkeypatch):
+    """autotune_msda_fused with a fake step: picks the 2-CTA shape only when it is faster AND agrees with the default."""
+    import sys
+
+    mod = sys.modules["bevformer_tensorrt_b200.functions.multi_scale_deformable_attn"]
+    clock = {"t": 0.0}
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            self.t = None
+
+        def record(self):
+            self.t = clock["t"]
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *_a, **_k: None)
+    prev = bt.get_msda_gather_variant()
+    box = {"out": None}
+
+    def make_run(ms, err):
+        def run():
+            v = bt.get_msda_gather_variant()
+            clock["t"] += ms[v]
+            box["out"] = torch.full((8,), 2.0 + (err if v else 0.0))
+
+        return run
+
+    try:
+        rep = mod.autotune_msda_fused(make_run({0: 1.0, 1: 0.7}, 1e-6), lambda: box["out"])
+        assert rep["chosen"] == "deep_gather" and bt.get_msda_gather_variant() == 1 and rep["rejected"] == []
+        rep = mod.autotune_msda_fused(make_run({0: 1.0, 1: 0.7}, 1e-2), lambda: box["out"])  # wrong result: never taken
+        assert rep["chosen"] == "default" and rep["rejected"] == ["deep_gather"] and bt.get_msda_gather_variant() == 0
+        rep = mod.autotune_msda_fused(make_run({0: 1.0, 1: 0.99}, 0.0), lambda: box["out"])  # inside the noise band
+        assert rep["chosen"] == "default" and bt.get_msda_gather_variant() == 0
+    finally:
+        bt.set_msda_gather_variant(prev)
