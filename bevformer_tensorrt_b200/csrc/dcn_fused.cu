@@ -435,20 +435,32 @@ __global__ void __launch_bounds__(kFusedThreads, 1) dcn_fused_kernel(const DcnFu
         {
           uint32_t r[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mh * kBN + c0, r);
-          if (p0 + c0 + 32 <= HoWo && (reinterpret_cast<uintptr_t>(orow + c0) & 15) == 0) {
+          // the lane's 32 outputs = 64 consecutive bytes of one output row; word j holds pixels 2j, 2j+1
+          uint32_t hw[16];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 o;
-              o.x = f2_to_h2(__uint_as_float(r[8 * v + 0]) + bias, __uint_as_float(r[8 * v + 1]) + bias);
-              o.y = f2_to_h2(__uint_as_float(r[8 * v + 2]) + bias, __uint_as_float(r[8 * v + 3]) + bias);
-              o.z = f2_to_h2(__uint_as_float(r[8 * v + 4]) + bias, __uint_as_float(r[8 * v + 5]) + bias);
-              o.w = f2_to_h2(__uint_as_float(r[8 * v + 6]) + bias, __uint_as_float(r[8 * v + 7]) + bias);
-              *reinterpret_cast<uint4 *>(orow + c0 + 8 * v) = o;
+          for (int j = 0; j < 16; ++j)
+            hw[j] = f2_to_h2(__uint_as_float(r[2 * j]) + bias, __uint_as_float(r[2 * j + 1]) + bias);
+          // Rows are Ho*Wo halves long: 16-byte aligned when Ho*Wo % 8 == 0 (58 x 100), only 4-byte aligned for the R101
+          // stage-4 map (29 x 50 = 1450). Widest store the row's alignment allows; 2-byte stores only for ragged tails
+          // and odd Ho*Wo.
+          const uintptr_t oa = reinterpret_cast<uintptr_t>(orow + c0);
+          if (p0 + c0 + 32 <= HoWo && (oa & 3) == 0) {
+            if ((oa & 15) == 0) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                *reinterpret_cast<uint4 *>(orow + c0 + 8 * v) = make_uint4(hw[4 * v], hw[4 * v + 1], hw[4 * v + 2], hw[4 * v + 3]);
+            } else if ((oa & 7) == 0) {
+#pragma unroll
+              for (int v = 0; v < 8; ++v) *reinterpret_cast<uint2 *>(orow + c0 + 4 * v) = make_uint2(hw[2 * v], hw[2 * v + 1]);
+            } else {
+#pragma unroll
+              for (int v = 0; v < 16; ++v) *reinterpret_cast<uint32_t *>(orow + c0 + 2 * v) = hw[v];
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (p0 + c0 + i < HoWo) orow[c0 + i] = __float2half_rn(__uint_as_float(r[i]) + bias);
+              if (p0 + c0 + i < HoWo)
+                reinterpret_cast<unsigned short *>(orow)[c0 + i] = static_cast<unsigned short>(hw[i >> 1] >> (16 * (i & 1)));
           }
         }
         }
