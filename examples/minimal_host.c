@@ -45,6 +45,14 @@ int main(void) {
   printf("b200_msda_f16 with no buffers -> status %d (%s)\n", st, b200_status_string(st));
   if (st != B200_ERR_BAD_PARAM) return 1;
 
+  /* launch-shape switches: same bits for every setting; a host picks one by timing them once on its own tensors */
+  const int shape_before = b200_msda_set_batch_units(0, 0); /* 0 = query */
+  const int variant_before = b200_msda_set_gather_variant(-1);
+  b200_msda_set_gather_variant(1);
+  printf("MSDA launch shape: units %d%s, gather variant %d -> %d\n", shape_before & 0xff, (shape_before >> 8) ? " (strided)" : "",
+         variant_before, b200_msda_set_gather_variant(variant_before));
+  if (b200_msda_set_gather_variant(-1) != variant_before) return 1;
+
   printf("DCN workspace for the R101 stage-3 layer: %zu bytes\n",
          b200_dcn_workspace_size(1, 6, 256, 58, 100, 3, 3, 1, 1, 1, 1, 1, 1));
   printf("kernels launched by this process so far: %llu\n", b200_launch_count());
