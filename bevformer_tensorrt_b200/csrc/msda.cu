@@ -925,6 +925,9 @@ static int launch_gather(const MsdaParams &p, cudaStream_t s) {
       if (p.trace != nullptr) {
         if (upw == 4) msda_gather_kernel<T, R, C, ROUNDS, 0, 0, true, 4><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);
         else msda_gather_kernel<T, R, C, ROUNDS, 0, 0, true, 2><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);
+      } else if (msda_gather_variant() == 1) {  // batched scan AND 2 CTAs per SM (128-register budget)
+        if (upw == 4) msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 4, 2><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);
+        else msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 2, 2><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);
       } else {
         if (upw == 4) msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 4><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);
         else msda_gather_kernel<T, R, C, ROUNDS, 0, 0, false, 2><<<static_cast<unsigned>(bb), kThreads, 0, s>>>(q);

@@ -80,6 +80,8 @@ MSDA_LAUNCH_SHAPES = {
     "deep_gather": (1, False, 1),
     "deep_gather_explicit": (1, False, 2),
     "mid_gather": (1, False, 3),
+    "deep_batch2_strided": (2, True, 1),
+    "deep_batch4_strided": (4, True, 1),
 }
 
 

@@ -236,7 +236,8 @@ int b200_msda_set_batch_units(int units, int strided);
  * 96 registers), two points = 8 loads issued together — fewer warps, more loads per warp, for inputs on which the kernel is
  * latency-bound. Same bits for every variant (the FMA order does not change). Any other value (e.g. -1) only queries.
  * Initial value: environment variable B200_MSDA_VARIANT ("0" .. "3"), else 0. Returns the
- * previous setting. A batched launch (units > 1 above) takes precedence over the variant. The fused forms
+ * previous setting. A batched launch (units > 1 above) combines with variant 1 (batched scan at 2 CTAs per SM) and takes
+ * precedence over variants 2 and 3. The fused forms
  * (b200_msda_sca_* / b200_msda_sca_shared_*) have one alternative: any non-zero variant runs them at 2 CTAs per SM. */
 int b200_msda_set_gather_variant(int variant);
 

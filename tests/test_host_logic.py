@@ -374,18 +374,21 @@ def test_autotuner_picks_the_fastest_identical_shape(monkeypatch):
     try:
         # a clearly faster shape wins and becomes the process-wide setting
         rep = _run_fake_autotune(monkeypatch, {"default": 1.0, "batch2_strided": 0.97, "deep_gather": 0.80,
-                                               "deep_gather_explicit": 0.85, "mid_gather": 0.9})
+                                               "deep_gather_explicit": 0.85, "mid_gather": 0.9, "deep_batch2_strided": 0.95,
+                                               "deep_batch4_strided": 0.96})
         assert rep["chosen"] == "deep_gather" and rep["rejected"] == []
         assert abs(rep["ms"]["deep_gather"] - 0.80) < 1e-9 and abs(rep["ms"]["default"] - 1.0) < 1e-9
         assert bt.get_msda_batch_units() == (1, False) and bt.get_msda_gather_variant() == 1
         # a faster shape whose bits differ is never taken, whatever its speed
         rep = _run_fake_autotune(monkeypatch, {"default": 1.0, "batch2_strided": 0.9, "deep_gather": 0.1,
-                                               "deep_gather_explicit": 0.95, "mid_gather": 0.93}, wrong=("deep_gather",))
+                                               "deep_gather_explicit": 0.95, "mid_gather": 0.93, "deep_batch2_strided": 0.97,
+                                               "deep_batch4_strided": 0.98}, wrong=("deep_gather",))
         assert rep["chosen"] == "batch2_strided" and rep["rejected"] == ["deep_gather"] and "deep_gather" not in rep["ms"]
         assert bt.get_msda_batch_units() == (2, True) and bt.get_msda_gather_variant() == 0
         # gains inside the noise band (min_gain = 2 %) leave the default in place
         rep = _run_fake_autotune(monkeypatch, {"default": 1.0, "batch2_strided": 0.99, "deep_gather": 0.985,
-                                               "deep_gather_explicit": 1.2, "mid_gather": 1.01})
+                                               "deep_gather_explicit": 1.2, "mid_gather": 1.01, "deep_batch2_strided": 1.1,
+                                               "deep_batch4_strided": 1.3})
         assert rep["chosen"] == "default"
         assert bt.get_msda_batch_units() == (1, False) and bt.get_msda_gather_variant() == 0
         # CPU tensors are refused before anything is touched

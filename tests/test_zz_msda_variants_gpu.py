@@ -43,10 +43,10 @@ def test_gather_variants_are_bit_identical(name, dist, seed, dtype, restore_laun
     base = bt.multi_scale_deformable_attn(*dev)
     want = omsda.msda_f32(*(t.float().numpy() for t in inputs))
     assert np.abs(base.float().cpu().numpy() - want).max() < (1e-5 if dtype == torch.float32 else 1e-3)
-    for variant in (1, 2, 3):
-        bt.set_msda_gather_variant(variant)
+    for shape in bt.MSDA_LAUNCH_SHAPES:  # every shape the autotuner may pick, incl. the batched-scan x 2-CTA combinations
+        bt.set_msda_launch_shape(shape)
         got = bt.multi_scale_deformable_attn(*dev)
-        assert torch.equal(got, base), (name, variant, (got.float() - base.float()).abs().max().item())
+        assert torch.equal(got, base), (name, shape, (got.float() - base.float()).abs().max().item())
 
 
 @pytest.mark.parametrize("dist", ["U", "G"])
@@ -57,10 +57,10 @@ def test_gather_variants_bit_identical_at_base_shapes(dist, restore_launch_shape
     bt.set_msda_batch_units(1)
     bt.set_msda_gather_variant(0)
     base16, base32 = bt.multi_scale_deformable_attn(*dev), bt.multi_scale_deformable_attn(*dev32)
-    for variant in (1, 2, 3):
-        bt.set_msda_gather_variant(variant)
-        assert torch.equal(bt.multi_scale_deformable_attn(*dev), base16), variant
-        assert torch.equal(bt.multi_scale_deformable_attn(*dev32), base32), variant
+    for shape in bt.MSDA_LAUNCH_SHAPES:
+        bt.set_msda_launch_shape(shape)
+        assert torch.equal(bt.multi_scale_deformable_attn(*dev), base16), shape
+        assert torch.equal(bt.multi_scale_deformable_attn(*dev32), base32), shape
 
 
 @pytest.mark.parametrize("dist", ["U", "G"])
